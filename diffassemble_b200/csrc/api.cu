@@ -1,0 +1,664 @@
+// C-ABI entry points and per-step orchestration (include/diffassemble_b200.h).
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace da;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// launch-site tags for the built-in CUDA-event profiler
+enum Tag : int {
+  TAG_HOIST_GEMM = 0, TAG_PROLOGUE, TAG_MLP2_GEMM, TAG_QKVS_GEMM_FIRST, TAG_QKVS_GEMM_MID, TAG_QKVS_GEMM_LAST,
+  TAG_ATTN_HIDDEN, TAG_ATTN_LAST, TAG_HEAD_GEMM, TAG_HEAD_FINAL, TAG_OTHER, TAG_COUNT
+};
+const char* kTagNames[TAG_COUNT] = {"hoist_gemm", "prologue", "mlp2_gemm", "qkvs_gemm_first", "qkvs_gemm_mid",
+                                    "qkvs_gemm_last", "attn_hidden", "attn_last", "head_gemm", "head_final", "other"};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need ? need : 16);
+    if (e == cudaSuccess) bytes = need ? need : 16;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Linear {  // y = x @ w^T + b ; w [N, K] row-major
+  DevBuf w, b, w_hi, w_lo;
+  int N = 0, K = 0;
+  void release() { w.release(); b.release(); w_hi.release(); w_lo.release(); }
+};
+
+struct ProfEvent { cudaEvent_t a, b; int tag; };
+
+}  // namespace
+
+struct da_handle {
+  da_config cfg{};
+  int D = 0, L = 0, Nh = 0;
+  std::string err;
+  bool weights_loaded = false, graph_set = false, feats_set = false, feats_zero = false;
+  // packed weights
+  Linear hoist, mlp2, head1;
+  std::vector<Linear> layer;
+  DevBuf pos_w0, pos_b0, pos_w2, pos_b2, time_emb, w1pt_T, b1, headb_w, headb_b, headr_w, headr_b, virt_emb;
+  // graph
+  CsrGraph csr;
+  int num_real = 0, num_total = 0;
+  // activations / workspace
+  DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
+  // split-bf16 operand planes for the tensor-core path
+  DevBuf feats_sp_hi, feats_sp_lo, h_hi, h_lo, comb_hi, comb_lo, xa_hi, xa_lo, xb_hi, xb_lo, r_hi, r_lo;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<ProfEvent> prof_events;
+  double prof_ms[TAG_COUNT] = {0};
+  int64_t prof_n[TAG_COUNT] = {0};
+
+  int fail(da_status st, const std::string& m) { err = m; return (int)st; }
+  int cuda_fail(cudaError_t e, const char* where) {
+    err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)DA_ERR_CUDA;
+  }
+  size_t workspace_bytes() const {
+    const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats,
+                           &feats_sp_hi, &feats_sp_lo, &h_hi, &h_lo, &comb_hi, &comb_lo, &xa_hi, &xa_lo,
+                           &xb_hi, &xb_lo, &r_hi, &r_lo};
+    size_t s = 0;
+    for (auto* b : all) s += b->bytes;
+    return s;
+  }
+};
+
+namespace {
+
+struct Scoped {  // records profiler events around one launch
+  da_handle* h; cudaStream_t s; int tag; ProfEvent ev{};
+  Scoped(da_handle* h_, cudaStream_t s_, int tag_) : h(h_), s(s_), tag(tag_) {
+    h->launches++;
+    if (h->profiling) {
+      cudaEventCreate(&ev.a); cudaEventCreate(&ev.b); ev.tag = tag;
+      cudaEventRecord(ev.a, s);
+    }
+  }
+  ~Scoped() {
+    if (h->profiling) { cudaEventRecord(ev.b, s); h->prof_events.push_back(ev); }
+  }
+};
+
+void drain_profile(da_handle* h) {
+  for (auto& e : h->prof_events) {
+    cudaEventSynchronize(e.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { h->prof_ms[e.tag] += ms; h->prof_n[e.tag]++; }
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  h->prof_events.clear();
+}
+
+int layer_in(const da_handle* h, int l) { return l == 0 ? h->D : h->cfg.hidden; }
+int layer_hc(const da_handle* h, int l) { return l == h->L - 1 ? h->D : h->cfg.hidden; }
+
+bool use_umma(const da_handle* h) { return h->cfg.gemm_mode == DA_GEMM_BF16X3_UMMA; }
+
+// One linear layer through whichever GEMM path the handle is configured for.
+// a_f32 is used by the SIMT path, (a_hi, a_lo) by the tensor-core path.
+cudaError_t run_linear(da_handle* h, const Linear& lin, const float* a_f32, int lda, const __nv_bfloat16* a_hi,
+                       const __nv_bfloat16* a_lo, int ld_sp, int M, int act, const LinearOut& out, int tag,
+                       cudaStream_t s) {
+  Scoped sc(h, s, tag);
+  if (use_umma(h)) {
+    return launch_linear_umma(a_hi, a_lo, ld_sp, lin.w_hi.as<__nv_bfloat16>(), lin.w_lo.as<__nv_bfloat16>(), lin.K,
+                              lin.b.as<float>(), out, M, lin.N, lin.K, act, s);
+  }
+  return launch_linear_simt(a_f32, lda, lin.w.as<float>(), lin.K, lin.b.as<float>(), out, M, lin.N, lin.K, act, s);
+}
+
+cudaError_t upload(DevBuf& dst, const float* src, size_t n) {
+  cudaError_t e = dst.ensure(n * sizeof(float));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(dst.p, src, n * sizeof(float), cudaMemcpyDefault);
+}
+
+struct WView { const float* data; int64_t rows, cols; };
+
+int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_uniform, float* out, float* alpha_last,
+                 int step_mode, const da_step_coef* coef, const float* x_in, const float* noise, cudaStream_t s) {
+  if (!h->weights_loaded) return h->fail(DA_ERR_MISSING, "weights not loaded (da_load_weights)");
+  if (!h->graph_set) return h->fail(DA_ERR_INVALID, "graph not set (da_set_graph)");
+  if (!h->feats_set) return h->fail(DA_ERR_INVALID, "features not set (da_set_features)");
+  if (alpha_last && h->cfg.attn_mode != DA_ATTN_CSR)
+    return h->fail(DA_ERR_UNSUPPORTED, "attention weights are only produced with attn_mode = DA_ATTN_CSR");
+  const da_config& c = h->cfg;
+  const int Mr = h->num_real, Mt = h->num_total, D = h->D, Hm = c.mlp_hidden, L = h->L;
+  const bool umma = use_umma(h);
+  cudaError_t ce;
+#define DA_CK(call, where) do { ce = (call); if (ce != cudaSuccess) return h->cuda_fail(ce, where); } while (0)
+
+  // 1. prologue -> h [Mr, Hm]
+  {
+    PrologueArgs a{};
+    a.x = x; a.t = t_arr; a.t_uniform = t_uniform;
+    a.P = h->feats_zero ? nullptr : h->P.as<float>();
+    a.b1 = h->b1.as<float>();
+    a.pos_w0 = h->pos_w0.as<float>(); a.pos_b0 = h->pos_b0.as<float>();
+    a.pos_w2 = h->pos_w2.as<float>(); a.pos_b2 = h->pos_b2.as<float>();
+    a.time_emb = h->time_emb.as<float>(); a.w1pt_T = h->w1pt_T.as<float>();
+    a.M = Mr; a.C_in = c.in_channels; a.Hm = Hm; a.T = c.steps;
+    a.act = (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_GELU;
+    if (umma) { a.out.hi = h->h_hi.as<__nv_bfloat16>(); a.out.lo = h->h_lo.as<__nv_bfloat16>(); a.out.ld_split = Hm; }
+    else { a.out.f32 = h->hbuf.as<float>(); a.out.ldc = Hm; }
+    Scoped sc(h, s, TAG_PROLOGUE);
+    DA_CK(launch_prologue(a, s), "prologue");
+  }
+  // 2. combined = act2(h @ W2^T + b2) -> [Mr, D] (fp32 kept for the trunk residual)
+  {
+    LinearOut o; o.f32 = h->combined.as<float>(); o.ldc = D;
+    if (umma) { o.hi = h->comb_hi.as<__nv_bfloat16>(); o.lo = h->comb_lo.as<__nv_bfloat16>(); o.ld_split = D; }
+    DA_CK(run_linear(h, h->mlp2, h->hbuf.as<float>(), Hm, h->h_hi.as<__nv_bfloat16>(), h->h_lo.as<__nv_bfloat16>(), Hm,
+                     Mr, (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_NONE, o, TAG_MLP2_GEMM, s),
+          "mlp2 gemm");
+  }
+  // 3. graph-transformer layers
+  const float* xin = h->combined.as<float>();
+  const __nv_bfloat16* xin_hi = h->comb_hi.as<__nv_bfloat16>();
+  const __nv_bfloat16* xin_lo = h->comb_lo.as<__nv_bfloat16>();
+  int ld_in = D;
+  for (int l = 0; l < L; ++l) {
+    const int HC = layer_hc(h, l), C = HC / c.heads;
+    const bool last = (l == L - 1);
+    {
+      LinearOut o; o.f32 = h->qkvs.as<float>(); o.ldc = 4 * HC;
+      int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
+      DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
+    }
+    AttnCsrArgs a{};
+    a.qkvs = h->qkvs.as<float>(); a.ld = 4 * HC;
+    a.rowptr = h->csr.rowptr; a.col = h->csr.col;
+    a.H = c.heads; a.C = C;
+    a.act = (!last && c.arch == DA_ARCH_TRANSFORMER) ? ACT_GELU : ACT_NONE;
+    if (last) {
+      a.n_targets = alpha_last ? Mt : Mr;
+      a.resid = h->combined.as<float>(); a.ld_resid = D;  // trunk residual feats + combined (efficient_gat.py:145)
+      if (umma) { a.out.hi = h->r_hi.as<__nv_bfloat16>(); a.out.lo = h->r_lo.as<__nv_bfloat16>(); a.out.ld_split = D; }
+      else { a.out.f32 = h->r.as<float>(); a.out.ldc = D; }
+      if (alpha_last) {
+        DA_CK(h->scores.ensure((size_t)(h->csr.E > 0 ? h->csr.E : 1) * c.heads * sizeof(float)), "alloc scores");
+        DA_CK(h->stats.ensure((size_t)Mt * c.heads * 2 * sizeof(float)), "alloc stats");
+        a.scores = h->scores.as<float>(); a.stats = h->stats.as<float>();
+      }
+    } else {
+      a.n_targets = Mt;
+      DevBuf& yb = (l & 1) ? h->xb : h->xa;
+      DevBuf& yh = (l & 1) ? h->xb_hi : h->xa_hi;
+      DevBuf& yl = (l & 1) ? h->xb_lo : h->xa_lo;
+      if (umma) { a.out.hi = yh.as<__nv_bfloat16>(); a.out.lo = yl.as<__nv_bfloat16>(); a.out.ld_split = HC; }
+      else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
+      xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
+    }
+    {
+      Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
+      DA_CK(launch_attn_csr(a, s), "graph attention");
+    }
+    if (last && alpha_last) {
+      Scoped sc(h, s, TAG_OTHER);
+      DA_CK(launch_alpha_normalize(h->scores.as<float>(), h->stats.as<float>(), h->csr.rowptr, h->csr.eid, Mt,
+                                   c.heads, alpha_last, s), "alpha normalize");
+    }
+  }
+  // 4. head: u = GELU(r @ Wa^T + ba) ; then final linear(s) + pose map + sampler update
+  {
+    LinearOut o; o.f32 = h->u.as<float>(); o.ldc = h->Nh;
+    DA_CK(run_linear(h, h->head1, h->r.as<float>(), D, h->r_hi.as<__nv_bfloat16>(), h->r_lo.as<__nv_bfloat16>(), D, Mr,
+                     ACT_GELU, o, TAG_HEAD_GEMM, s), "head gemm");
+    HeadFinalArgs a{};
+    a.u = h->u.as<float>(); a.Nh = h->Nh;
+    a.w_b = h->headb_w.as<float>(); a.b_b = h->headb_b.as<float>();
+    a.w_r = h->headr_w.as<float>(); a.b_r = h->headr_b.as<float>();
+    a.M = Mr; a.C_out = c.out_channels; a.head_kind = c.head_kind;
+    a.step_mode = step_mode;
+    if (coef) a.coef = *coef;
+    a.x_in = x_in; a.noise = noise; a.out = out;
+    Scoped sc(h, s, TAG_HEAD_FINAL);
+    DA_CK(launch_head_final(a, s), "head final");
+  }
+#undef DA_CK
+  return DA_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int da_abi_version(void) { return DA_ABI_VERSION; }
+
+const char* da_last_error(const da_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int da_create(da_handle** out, const da_config* cfg) {
+  if (!out || !cfg) { g_create_error = "null argument"; return DA_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->abi_version != DA_ABI_VERSION) { g_create_error = "abi_version mismatch"; return DA_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+                     " (this library has no CPU fallback)";
+    return DA_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return DA_ERR_INVALID; }
+  cudaDeviceProp prop{};
+  ce = cudaGetDeviceProperties(&prop, cfg->device);
+  if (ce != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return DA_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "device is not sm_100 (B200); kernels are built for sm_100a only";
+    return DA_ERR_CUDA;
+  }
+  const da_config& c = *cfg;
+  if (c.heads <= 0 || c.hidden <= 0 || c.hidden % c.heads || c.n_layers < 2 || c.feat_dim <= 0 || c.steps <= 0 ||
+      c.in_channels <= 0 || c.in_channels > 8 || c.out_channels <= 0 || c.mlp_hidden <= 0) {
+    g_create_error = "invalid configuration value";
+    return DA_ERR_INVALID;
+  }
+  const int D = c.feat_dim + 64;  // efficient_gat.py:48 (Dv + 32 + 32)
+  if (D % c.heads) { g_create_error = "combined feature dim must be divisible by heads"; return DA_ERR_INVALID; }
+  if (c.head_kind == DA_HEAD_SE3 && c.out_channels != 7) { g_create_error = "SE3 head has 7 output channels"; return DA_ERR_INVALID; }
+  if (c.head_kind != DA_HEAD_SE3 && c.head_kind != DA_HEAD_2D) { g_create_error = "unknown head_kind"; return DA_ERR_INVALID; }
+  if (c.gemm_mode == DA_GEMM_BF16X3_UMMA) {
+    // tensor-core tiles: K in multiples of 64 bf16 (one 128-byte swizzle row), N in multiples of 16
+    if (c.feat_dim % 64 || c.mlp_hidden % 64 || c.hidden % 64 || D % 64) {
+      g_create_error = "DA_GEMM_BF16X3_UMMA needs feat_dim, mlp_hidden, hidden and D to be multiples of 64";
+      return DA_ERR_UNSUPPORTED;
+    }
+  } else if (c.gemm_mode != DA_GEMM_FP32_SIMT) { g_create_error = "unknown gemm_mode"; return DA_ERR_INVALID; }
+  if ((D % 4) || (c.feat_dim % 4) || (c.mlp_hidden % 4) || (c.hidden % 4)) {
+    g_create_error = "feature widths must be multiples of 4";
+    return DA_ERR_UNSUPPORTED;
+  }
+  if ((D / c.heads + 31) / 32 > 13) { g_create_error = "head dim above 416 not supported"; return DA_ERR_UNSUPPORTED; }
+  cudaSetDevice(c.device);
+  da_handle* h = new da_handle();
+  h->cfg = c;
+  h->D = D;
+  h->L = c.n_layers;
+  h->Nh = (c.head_kind == DA_HEAD_SE3) ? 512 : 32;
+  h->layer.resize(h->L);
+  *out = h;
+  return DA_OK;
+}
+
+void da_destroy(da_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  drain_profile(h);
+  h->hoist.release(); h->mlp2.release(); h->head1.release();
+  for (auto& l : h->layer) l.release();
+  DevBuf* all[] = {&h->pos_w0, &h->pos_b0, &h->pos_w2, &h->pos_b2, &h->time_emb, &h->w1pt_T, &h->b1, &h->headb_w,
+                   &h->headb_b, &h->headr_w, &h->headr_b, &h->virt_emb, &h->P, &h->hbuf, &h->combined, &h->qkvs,
+                   &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
+                   &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
+                   &h->xb_lo, &h->r_hi, &h->r_lo};
+  for (auto* b : all) b->release();
+  free_csr(&h->csr);
+  delete h;
+}
+
+int da_load_weights(da_handle* h, const da_weight_desc* w, int32_t n) {
+  if (!h || !w || n <= 0) return h ? h->fail(DA_ERR_INVALID, "null weights") : DA_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  const da_config& c = h->cfg;
+  std::map<std::string, WView> m;
+  for (int i = 0; i < n; ++i) {
+    if (!w[i].name || !w[i].data) return h->fail(DA_ERR_INVALID, "weight descriptor with null name/data");
+    m[w[i].name] = WView{w[i].data, w[i].rows, w[i].cols};
+  }
+  std::string missing;
+  auto need = [&](const std::string& name, int64_t rows, int64_t cols) -> const WView* {
+    auto it = m.find(name);
+    if (it == m.end()) { missing = "missing weight '" + name + "'"; return nullptr; }
+    if (it->second.rows != rows || it->second.cols != cols) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "weight '%s' has shape [%lld,%lld], expected [%lld,%lld]", name.c_str(),
+               (long long)it->second.rows, (long long)it->second.cols, (long long)rows, (long long)cols);
+      missing = buf;
+      return nullptr;
+    }
+    return &it->second;
+  };
+  // Stage everything on the host first (weights may live in host or device memory).
+  auto fetch = [&](const WView* v, std::vector<float>& dst) -> cudaError_t {
+    dst.resize((size_t)v->rows * v->cols);
+    return cudaMemcpy(dst.data(), v->data, dst.size() * sizeof(float), cudaMemcpyDefault);
+  };
+  cudaError_t ce;
+#define DA_NEED(var, name, r, cc) const WView* var = need(name, r, cc); if (!var) return h->fail(DA_ERR_MISSING, missing)
+#define DA_CK(call) do { ce = (call); if (ce != cudaSuccess) return h->cuda_fail(ce, "da_load_weights"); } while (0)
+  const int D = h->D, Dv = c.feat_dim, Hm = c.mlp_hidden, Cin = c.in_channels;
+  std::vector<float> tmp, tmp2;
+  auto up_direct = [&](DevBuf& dst, const WView* v) -> cudaError_t {
+    cudaError_t e = fetch(v, tmp);
+    if (e != cudaSuccess) return e;
+    return upload(dst, tmp.data(), tmp.size());
+  };
+  auto finish_linear = [&](Linear& lin, const std::vector<float>& wv, const std::vector<float>& bv, int N, int K) -> cudaError_t {
+    lin.N = N; lin.K = K;
+    cudaError_t e = upload(lin.w, wv.data(), wv.size());
+    if (e != cudaSuccess) return e;
+    e = upload(lin.b, bv.data(), bv.size());
+    if (e != cudaSuccess) return e;
+    if (use_umma(h)) {
+      e = lin.w_hi.ensure(wv.size() * sizeof(__nv_bfloat16)); if (e != cudaSuccess) return e;
+      e = lin.w_lo.ensure(wv.size() * sizeof(__nv_bfloat16)); if (e != cudaSuccess) return e;
+      e = launch_split_bf16(lin.w.as<float>(), K, lin.w_hi.as<__nv_bfloat16>(), lin.w_lo.as<__nv_bfloat16>(), K, N, K, 0);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+
+  {
+    DA_NEED(v0, "pos_mlp.0.weight", 16, Cin); DA_CK(up_direct(h->pos_w0, v0));
+    DA_NEED(v1, "pos_mlp.0.bias", 16, 1); DA_CK(up_direct(h->pos_b0, v1));
+    DA_NEED(v2, "pos_mlp.2.weight", 32, 16); DA_CK(up_direct(h->pos_w2, v2));
+    DA_NEED(v3, "pos_mlp.2.bias", 32, 1); DA_CK(up_direct(h->pos_b2, v3));
+    DA_NEED(v4, "time_emb.weight", c.steps, 32); DA_CK(up_direct(h->time_emb, v4));
+  }
+  {  // mlp[0]: split into the step-invariant feature block and the 64 pose+time columns
+    DA_NEED(vw, "mlp.0.weight", Hm, D);
+    DA_NEED(vb, "mlp.0.bias", Hm, 1);
+    DA_CK(fetch(vw, tmp));
+    std::vector<float> wf((size_t)Hm * Dv), wpt((size_t)64 * Hm), bias;
+    for (int n_ = 0; n_ < Hm; ++n_) {
+      memcpy(&wf[(size_t)n_ * Dv], &tmp[(size_t)n_ * D], sizeof(float) * Dv);
+      for (int k = 0; k < 64; ++k) wpt[(size_t)k * Hm + n_] = tmp[(size_t)n_ * D + Dv + k];
+    }
+    DA_CK(fetch(vb, bias));
+    DA_CK(finish_linear(h->hoist, wf, bias, Hm, Dv));
+    DA_CK(upload(h->w1pt_T, wpt.data(), wpt.size()));
+    DA_CK(upload(h->b1, bias.data(), bias.size()));
+  }
+  {
+    DA_NEED(vw, "mlp.2.weight", D, Hm);
+    DA_NEED(vb, "mlp.2.bias", D, 1);
+    DA_CK(fetch(vw, tmp)); DA_CK(fetch(vb, tmp2));
+    DA_CK(finish_linear(h->mlp2, tmp, tmp2, D, Hm));
+  }
+  for (int l = 0; l < h->L; ++l) {  // [Q | K | V | skip] concatenated along the output dim
+    const int in = layer_in(h, l), HC = layer_hc(h, l);
+    std::vector<float> wcat((size_t)4 * HC * in), bcat((size_t)4 * HC);
+    const char* parts[4] = {"lin_query", "lin_key", "lin_value", "lin_skip"};
+    for (int p = 0; p < 4; ++p) {
+      std::string base = "gnn_backbone.module_list." + std::to_string(l) + "." + parts[p];
+      DA_NEED(vw, base + ".weight", HC, in);
+      DA_NEED(vb, base + ".bias", HC, 1);
+      DA_CK(fetch(vw, tmp)); DA_CK(fetch(vb, tmp2));
+      memcpy(&wcat[(size_t)p * HC * in], tmp.data(), tmp.size() * sizeof(float));
+      memcpy(&bcat[(size_t)p * HC], tmp2.data(), tmp2.size() * sizeof(float));
+    }
+    DA_CK(finish_linear(h->layer[l], wcat, bcat, 4 * HC, in));
+  }
+  if (c.arch == DA_ARCH_EXOPHORMER && c.virt_nodes > 0) {
+    DA_NEED(v, "gnn_backbone.virt_node_embedding.weight", c.virt_nodes, D);
+    DA_CK(up_direct(h->virt_emb, v));
+  }
+  if (c.head_kind == DA_HEAD_2D) {
+    DA_NEED(vw, "final_mlp.0.weight", 32, D);
+    DA_NEED(vb, "final_mlp.0.bias", 32, 1);
+    DA_CK(fetch(vw, tmp)); DA_CK(fetch(vb, tmp2));
+    DA_CK(finish_linear(h->head1, tmp, tmp2, 32, D));
+    DA_NEED(v2, "final_mlp.2.weight", c.out_channels, 32); DA_CK(up_direct(h->headb_w, v2));
+    DA_NEED(v3, "final_mlp.2.bias", c.out_channels, 1); DA_CK(up_direct(h->headb_b, v3));
+  } else {
+    DA_NEED(vtw, "mlp_t.0.weight", 256, D);
+    DA_NEED(vtb, "mlp_t.0.bias", 256, 1);
+    DA_NEED(vrw, "mlp_r.0.weight", 256, D);
+    DA_NEED(vrb, "mlp_r.0.bias", 256, 1);
+    std::vector<float> wcat((size_t)512 * D), bcat(512);
+    DA_CK(fetch(vtw, tmp)); memcpy(wcat.data(), tmp.data(), tmp.size() * sizeof(float));
+    DA_CK(fetch(vrw, tmp)); memcpy(wcat.data() + (size_t)256 * D, tmp.data(), tmp.size() * sizeof(float));
+    DA_CK(fetch(vtb, tmp)); memcpy(bcat.data(), tmp.data(), 256 * sizeof(float));
+    DA_CK(fetch(vrb, tmp)); memcpy(bcat.data() + 256, tmp.data(), 256 * sizeof(float));
+    DA_CK(finish_linear(h->head1, wcat, bcat, 512, D));
+    DA_NEED(v2, "mlp_t.2.weight", 3, 256); DA_CK(up_direct(h->headb_w, v2));
+    DA_NEED(v3, "mlp_t.2.bias", 3, 1); DA_CK(up_direct(h->headb_b, v3));
+    DA_NEED(v4, "mlp_r.2.weight", 3, 256); DA_CK(up_direct(h->headr_w, v4));
+    DA_NEED(v5, "mlp_r.2.bias", 3, 1); DA_CK(up_direct(h->headr_b, v5));
+  }
+  DA_CK(cudaDeviceSynchronize());
+#undef DA_NEED
+#undef DA_CK
+  h->weights_loaded = true;
+  h->feats_set = false;  // the hoisted product depends on the weights
+  return DA_OK;
+}
+
+int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, const int64_t* batch,
+                 int32_t num_real, int32_t num_total, const int32_t* virt_ids, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_real <= 0 || num_total < num_real || E < 0) return h->fail(DA_ERR_INVALID, "bad graph sizes");
+  if (E > 0 && (!edge_src || !edge_dst)) return h->fail(DA_ERR_INVALID, "null edge arrays");
+  if (num_total > num_real && (!virt_ids || h->cfg.arch != DA_ARCH_EXOPHORMER))
+    return h->fail(DA_ERR_INVALID, "virtual rows need arch = EXOPHORMER and virt_ids");
+  if (num_total > num_real && !h->weights_loaded)
+    return h->fail(DA_ERR_MISSING, "load weights before da_set_graph when virtual nodes are used");
+  (void)batch;  // graph membership is only needed by the dense-tile attention planner
+  const char* why = "";
+  cudaError_t ce = build_csr(edge_src, edge_dst, E, num_total, &h->csr, s, &why);
+  if (ce != cudaSuccess) {
+    if (ce == cudaErrorInvalidValue && why[0]) return h->fail(DA_ERR_INVALID, why);
+    return h->cuda_fail(ce, why);
+  }
+  h->num_real = num_real; h->num_total = num_total;
+  const da_config& c = h->cfg;
+  const int D = h->D, Hm = c.mlp_hidden, hid = c.hidden;
+  const size_t Mt = num_total, Mr = num_real;
+  const bool umma = use_umma(h);
+#define DA_CK(call) do { ce = (call); if (ce != cudaSuccess) return h->cuda_fail(ce, "da_set_graph alloc"); } while (0)
+  DA_CK(h->P.ensure(Mr * Hm * sizeof(float)));
+  DA_CK(h->combined.ensure(Mt * D * sizeof(float)));
+  DA_CK(h->qkvs.ensure(Mt * 4 * (size_t)(D > hid ? D : hid) * sizeof(float)));
+  DA_CK(h->u.ensure(Mr * h->Nh * sizeof(float)));
+  DA_CK(h->model_out.ensure(Mr * c.out_channels * sizeof(float)));
+  if (umma) {
+    const size_t b2 = sizeof(__nv_bfloat16);
+    DA_CK(h->h_hi.ensure(Mr * Hm * b2)); DA_CK(h->h_lo.ensure(Mr * Hm * b2));
+    DA_CK(h->comb_hi.ensure(Mt * D * b2)); DA_CK(h->comb_lo.ensure(Mt * D * b2));
+    DA_CK(h->xa_hi.ensure(Mt * hid * b2)); DA_CK(h->xa_lo.ensure(Mt * hid * b2));
+    DA_CK(h->xb_hi.ensure(Mt * hid * b2)); DA_CK(h->xb_lo.ensure(Mt * hid * b2));
+    DA_CK(h->r_hi.ensure(Mt * D * b2)); DA_CK(h->r_lo.ensure(Mt * D * b2));
+  } else {
+    DA_CK(h->hbuf.ensure(Mr * Hm * sizeof(float)));
+    DA_CK(h->xa.ensure(Mt * hid * sizeof(float)));
+    DA_CK(h->xb.ensure(Mt * hid * sizeof(float)));
+    DA_CK(h->r.ensure(Mt * D * sizeof(float)));
+  }
+  if (num_total > num_real) {  // virtual rows: constant embeddings appended after the real nodes (exophormer_gnn.py:169-178)
+    const int nv = num_total - num_real;
+    float* dst = h->combined.as<float>() + Mr * D;
+    h->launches++;
+    DA_CK(launch_fill_rows(dst, D, h->virt_emb.as<float>(), virt_ids, nv, D, s));
+    if (umma) {
+      h->launches++;
+      DA_CK(launch_split_bf16(dst, D, h->comb_hi.as<__nv_bfloat16>() + Mr * D, h->comb_lo.as<__nv_bfloat16>() + Mr * D, D, nv, D, s));
+    }
+  }
+#undef DA_CK
+  h->graph_set = true;
+  h->feats_set = false;
+  return DA_OK;
+}
+
+int da_set_features(da_handle* h, const float* feats, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (!h->weights_loaded) return h->fail(DA_ERR_MISSING, "weights not loaded");
+  if (!h->graph_set) return h->fail(DA_ERR_INVALID, "graph not set");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!feats) { h->feats_zero = true; h->feats_set = true; return DA_OK; }
+  h->feats_zero = false;
+  const int Mr = h->num_real, Dv = h->cfg.feat_dim, Hm = h->cfg.mlp_hidden;
+  cudaError_t ce;
+  if (use_umma(h)) {
+    const size_t b2 = sizeof(__nv_bfloat16);
+    ce = h->feats_sp_hi.ensure((size_t)Mr * Dv * b2); if (ce != cudaSuccess) return h->cuda_fail(ce, "alloc");
+    ce = h->feats_sp_lo.ensure((size_t)Mr * Dv * b2); if (ce != cudaSuccess) return h->cuda_fail(ce, "alloc");
+    Scoped sc(h, s, TAG_OTHER);
+    ce = launch_split_bf16(feats, Dv, h->feats_sp_hi.as<__nv_bfloat16>(), h->feats_sp_lo.as<__nv_bfloat16>(), Dv, Mr, Dv, s);
+    if (ce != cudaSuccess) return h->cuda_fail(ce, "split features");
+  }
+  LinearOut o; o.f32 = h->P.as<float>(); o.ldc = Hm;
+  ce = run_linear(h, h->hoist, feats, Dv, h->feats_sp_hi.as<__nv_bfloat16>(), h->feats_sp_lo.as<__nv_bfloat16>(), Dv, Mr,
+                  ACT_NONE, o, TAG_HOIST_GEMM, s);
+  if (ce != cudaSuccess) return h->cuda_fail(ce, "hoist gemm");
+  h->feats_set = true;
+  return DA_OK;
+}
+
+int da_forward(da_handle* h, const float* x, const int64_t* t, float* out, float* alpha_last, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x || !t || !out) return h->fail(DA_ERR_INVALID, "null x / t / out");
+  cudaSetDevice(h->cfg.device);
+  return forward_impl(h, x, t, 0, out, alpha_last, STEP_NONE, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int da_ddpm_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c, const float* noise, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x_in || !x_out || !c) return h->fail(DA_ERR_INVALID, "null argument");
+  if (h->cfg.head_kind != DA_HEAD_2D) return h->fail(DA_ERR_UNSUPPORTED, "DDPM step is defined for the 2D head only (the 3D module binds DDIM only)");
+  if (c->t_index != 0 && !noise) return h->fail(DA_ERR_INVALID, "DDPM step with t_index > 0 needs noise");
+  cudaSetDevice(h->cfg.device);
+  return forward_impl(h, x_in, nullptr, c->t, x_out, nullptr, STEP_DDPM, c, x_in, noise, (cudaStream_t)stream);
+}
+
+int da_ddim_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c, const float* noise, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x_in || !x_out || !c) return h->fail(DA_ERR_INVALID, "null argument");
+  if (c->eta > 0.f && !noise) return h->fail(DA_ERR_INVALID, "DDIM step with eta > 0 needs noise");
+  if (c->eta > 0.f && h->cfg.head_kind == DA_HEAD_SE3) return h->fail(DA_ERR_UNSUPPORTED, "SE3 sampler is eta = 0 only");
+  cudaSetDevice(h->cfg.device);
+  return forward_impl(h, x_in, nullptr, c->t, x_out, nullptr, STEP_DDIM, c, x_in, noise, (cudaStream_t)stream);
+}
+
+int da_ddim_update(da_handle* h, const float* x_in, const float* model_out, float* x_out, const da_step_coef* c,
+                   const float* noise, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x_in || !model_out || !x_out || !c) return h->fail(DA_ERR_INVALID, "null argument");
+  if (!h->graph_set) return h->fail(DA_ERR_INVALID, "graph not set");
+  if (c->eta > 0.f && !noise) return h->fail(DA_ERR_INVALID, "eta > 0 needs noise");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  Scoped sc(h, s, TAG_OTHER);
+  cudaError_t ce = launch_sampler_update(x_in, model_out, x_out, h->num_real, h->cfg.out_channels, h->cfg.head_kind,
+                                         STEP_DDIM, *c, noise, s);
+  if (ce != cudaSuccess) return h->cuda_fail(ce, "sampler update");
+  return DA_OK;
+}
+
+size_t da_workspace_bytes(const da_handle* h) { return h ? h->workspace_bytes() : 0; }
+int64_t da_launch_count(const da_handle* h) { return h ? h->launches : 0; }
+
+int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_edges, int32_t* n_dense_graphs) {
+  if (!h || !h->graph_set) return DA_ERR_INVALID;
+  if (n_dense_edges) *n_dense_edges = 0;
+  if (n_csr_edges) *n_csr_edges = h->csr.E;
+  if (n_dense_graphs) *n_dense_graphs = 0;
+  return DA_OK;
+}
+
+int da_set_profiling(da_handle* h, int32_t enable) {
+  if (!h) return DA_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  if (!enable) drain_profile(h);
+  h->profiling = enable != 0;
+  return DA_OK;
+}
+
+int da_get_profile(da_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset) {
+  if (!h) return DA_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  drain_profile(h);
+  for (int i = 0; i < n_classes && i < TAG_COUNT; ++i) {
+    if (ms_out) ms_out[i] = h->prof_ms[i];
+    if (launches_out) launches_out[i] = h->prof_n[i];
+  }
+  if (reset) for (int i = 0; i < TAG_COUNT; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+  return TAG_COUNT;
+}
+
+const char* da_profile_tag_name(int32_t i) { return (i >= 0 && i < TAG_COUNT) ? kTagNames[i] : ""; }
+
+// ---- stand-alone operators ------------------------------------------------------------------
+int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
+                 int32_t K, int32_t act, void* stream) {
+  if (!a || !w || !y || M <= 0 || N <= 0 || K <= 0) return DA_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  LinearOut o; o.f32 = y; o.ldc = N;
+  cudaError_t ce;
+  if (mode == DA_GEMM_FP32_SIMT) {
+    ce = launch_linear_simt(a, K, w, K, bias, o, M, N, K, act, s);
+    return ce == cudaSuccess ? DA_OK : (ce == cudaErrorInvalidValue ? DA_ERR_UNSUPPORTED : DA_ERR_CUDA);
+  }
+  if (mode != DA_GEMM_BF16X3_UMMA) return DA_ERR_INVALID;
+  if (K % 64 || N % 16) return DA_ERR_UNSUPPORTED;
+  __nv_bfloat16 *ahi = nullptr, *alo = nullptr, *whi = nullptr, *wlo = nullptr;
+  const size_t b2 = sizeof(__nv_bfloat16);
+  int rc = DA_OK;
+  if (cudaMalloc(&ahi, (size_t)M * K * b2) != cudaSuccess || cudaMalloc(&alo, (size_t)M * K * b2) != cudaSuccess ||
+      cudaMalloc(&whi, (size_t)N * K * b2) != cudaSuccess || cudaMalloc(&wlo, (size_t)N * K * b2) != cudaSuccess) {
+    rc = DA_ERR_CUDA;
+  } else {
+    ce = launch_split_bf16(a, K, ahi, alo, K, M, K, s);
+    if (ce == cudaSuccess) ce = launch_split_bf16(w, K, whi, wlo, K, N, K, s);
+    if (ce == cudaSuccess) ce = launch_linear_umma(ahi, alo, K, whi, wlo, K, bias, o, M, N, K, act, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) rc = (ce == cudaErrorInvalidValue) ? DA_ERR_UNSUPPORTED : DA_ERR_CUDA;
+  }
+  cudaFree(ahi); cudaFree(alo); cudaFree(whi); cudaFree(wlo);
+  return rc;
+}
+
+int da_op_graph_attention(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n,
+                          int32_t H, int32_t C, float* y, float* alpha, void* stream) {
+  if (!qkvs || !y || n <= 0 || H <= 0 || C <= 0 || E < 0) return DA_ERR_INVALID;
+  if ((C + 31) / 32 > 13) return DA_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  CsrGraph g;
+  const char* why = "";
+  cudaError_t ce = build_csr(edge_src, edge_dst, E, n, &g, s, &why);
+  if (ce != cudaSuccess) return ce == cudaErrorInvalidValue ? DA_ERR_INVALID : DA_ERR_CUDA;
+  float *scores = nullptr, *stats = nullptr;
+  int rc = DA_OK;
+  if (alpha) {
+    if (cudaMalloc(&scores, sizeof(float) * (size_t)(E > 0 ? E : 1) * H) != cudaSuccess ||
+        cudaMalloc(&stats, sizeof(float) * (size_t)n * H * 2) != cudaSuccess) rc = DA_ERR_CUDA;
+  }
+  if (rc == DA_OK) {
+    AttnCsrArgs a{};
+    a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = g.rowptr; a.col = g.col; a.n_targets = n; a.H = H; a.C = C;
+    a.act = ACT_NONE; a.out.f32 = y; a.out.ldc = H * C; a.scores = scores; a.stats = stats;
+    ce = launch_attn_csr(a, s);
+    if (ce == cudaSuccess && alpha) ce = launch_alpha_normalize(scores, stats, g.rowptr, g.eid, n, H, alpha, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) rc = DA_ERR_CUDA;
+  }
+  cudaFree(scores); cudaFree(stats);
+  free_csr(&g);
+  return rc;
+}
+
+}  // extern "C"

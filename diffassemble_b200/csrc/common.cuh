@@ -1,0 +1,140 @@
+// Shared declarations for the diffassemble_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/diffassemble_b200.h"
+
+namespace da {
+
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // nn.GELU() / F.gelu default = exact erf form (efficient_gat.py:89,95,100; Transformer_GNN.py:36)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float lrelu02(float x) { return x > 0.f ? x : 0.2f * x; }
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == ACT_GELU) return gelu_erf(x);
+  if (ACT == ACT_LRELU) return lrelu02(x);
+  return x;
+}
+__device__ __forceinline__ float apply_act_rt(float x, int act) {
+  if (act == ACT_GELU) return gelu_erf(x);
+  if (act == ACT_LRELU) return lrelu02(x);
+  return x;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launch wrappers (each returns cudaError_t from the launch; all async on `stream`).
+// ---------------------------------------------------------------------------------------------
+
+// Destination of a linear layer's epilogue.  Any subset of the three outputs may be requested.
+struct LinearOut {
+  float* f32 = nullptr;          // [M, ldc] fp32
+  int ldc = 0;
+  __nv_bfloat16* hi = nullptr;   // split-bf16 planes [M, ld_split] (operand of the next tensor-core GEMM)
+  __nv_bfloat16* lo = nullptr;
+  int ld_split = 0;
+};
+
+// y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
+cudaError_t launch_linear_simt(const float* a, int lda, const float* w, int ldw, const float* bias,
+                               const LinearOut& out, int M, int N, int K, int act, cudaStream_t s);
+
+// fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)); rows x cols with row strides.
+cudaError_t launch_split_bf16(const float* x, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld,
+                              int rows, int cols, cudaStream_t s);
+
+// CSR-by-target multigraph attention (TransformerConv message/aggregate stage).
+struct AttnCsrArgs {
+  const float* qkvs;     // [n, ld] rows laid out [Q | K | V | skip], each H*C wide
+  int ld;                // row stride of qkvs (= 4*H*C)
+  const int32_t* rowptr; // [n_targets + 1] in-edge ranges per target
+  const int32_t* col;    // [E] source node per in-edge
+  int n_targets;         // targets processed (first n_targets rows)
+  int H, C;
+  const float* resid;    // optional [n_targets, ld_resid] added after skip (trunk residual), or null
+  int ld_resid;
+  int act;               // activation applied to (attn + skip [+ resid])
+  LinearOut out;         // [n_targets, H*C]
+  float* scores;         // optional [E, H] raw scaled scores at CSR positions (for alpha output)
+  float* stats;          // optional [n_targets, H, 2] (max, sum) for alpha output
+};
+cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s);
+
+// alpha[eid[p], h] = exp(scores[p,h] - max) / (sum + 1e-16)
+cudaError_t launch_alpha_normalize(const float* scores, const float* stats, const int32_t* rowptr,
+                                   const int32_t* eid, int n_targets, int H, float* alpha, cudaStream_t s);
+
+struct PrologueArgs {
+  const float* x;        // [M, C_in]
+  const int64_t* t;      // [M] or null -> t_uniform
+  int t_uniform;
+  const float* P;        // [M, Hm] hoisted feats @ W1[:, :Dv]^T + b1   (or null -> b1 only)
+  const float* b1;       // [Hm]
+  const float* pos_w0;   // [16, C_in]
+  const float* pos_b0;   // [16]
+  const float* pos_w2;   // [32, 16]
+  const float* pos_b2;   // [32]
+  const float* time_emb; // [T, 32]
+  const float* w1pt_T;   // [64, Hm]  transposed W1[:, Dv:Dv+64]
+  int M, C_in, Hm, T, act;
+  LinearOut out;         // [M, Hm]
+};
+cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s);
+
+// sampler update modes for the head epilogue
+enum StepMode : int { STEP_NONE = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
+
+struct HeadFinalArgs {
+  const float* u;        // [M, Nh] hidden of the head after GELU
+  int Nh;
+  const float* w_b;      // 2D: [C_out, 32];  SE3: mlp_t.2 [3,256]
+  const float* b_b;
+  const float* w_r;      // SE3: mlp_r.2 [3,256]
+  const float* b_r;
+  int M, C_out, head_kind;
+  int step_mode;
+  da_step_coef coef;
+  const float* x_in;     // [M, C] current sample (step modes)
+  const float* noise;    // [M, C] or null
+  float* out;            // [M, C_out] model output (STEP_NONE) or x_prev
+};
+cudaError_t launch_head_final(const HeadFinalArgs& a, cudaStream_t s);
+cudaError_t launch_sampler_update(const float* x_in, const float* model_out, float* x_out, int M, int C,
+                                  int head_kind, int step_mode, const da_step_coef& coef,
+                                  const float* noise, cudaStream_t s);
+
+// graph structure
+struct CsrGraph {
+  int32_t* rowptr = nullptr;  // [n + 1]
+  int32_t* col = nullptr;     // [E]
+  int32_t* eid = nullptr;     // [E] original edge index of each CSR slot
+  int64_t E = 0;
+  int n = 0;
+};
+// Builds CSR by target with a stable radix sort.  Allocates with cudaMallocAsync-free plain cudaMalloc.
+cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
+                      const char** err);
+void free_csr(CsrGraph* g);
+
+cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
+                             cudaStream_t s);
+
+}  // namespace da

@@ -1,0 +1,98 @@
+// Device-side graph preparation: edge list (PyG edge_index, int64) -> CSR by target.
+// Done once per batch (da_set_graph), never inside the step loop.  A stable radix sort on the
+// target id keeps the caller's edge order inside each segment, so the per-node summation order
+// is deterministic run to run.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace da {
+namespace {
+
+__global__ void narrow_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                    int n, int32_t* __restrict__ key, int32_t* __restrict__ val,
+                                    int32_t* __restrict__ bad) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t s = src[e], d = dst[e];
+  if (s < 0 || s >= n || d < 0 || d >= n) { atomicExch(bad, 1); d = 0; }
+  key[e] = (int32_t)d;
+  val[e] = (int32_t)e;
+}
+
+__global__ void gather_cols_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ eid, int64_t E,
+                                   int n, int32_t* __restrict__ col) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= E) return;
+  int64_t s = src[eid[p]];
+  col[p] = (int32_t)((s < 0 || s >= n) ? 0 : s);
+}
+
+// rowptr[i] = first CSR slot whose (sorted) target is >= i
+__global__ void rowptr_kernel(const int32_t* __restrict__ sorted_dst, int64_t E, int n, int32_t* __restrict__ rowptr) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int64_t lo = 0, hi = E;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (sorted_dst[mid] < i) lo = mid + 1; else hi = mid;
+  }
+  rowptr[i] = (int32_t)lo;
+}
+
+}  // namespace
+
+void free_csr(CsrGraph* g) {
+  if (!g) return;
+  cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->eid);
+  *g = CsrGraph();
+}
+
+cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
+                      const char** err) {
+  *err = "";
+  free_csr(g);
+  if (E >= (int64_t)1 << 31) { *err = "edge count exceeds int32 range"; return cudaErrorInvalidValue; }
+  cudaError_t ce;
+#define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
+  int32_t *key = nullptr, *val = nullptr, *key_sorted = nullptr, *bad = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int32_t bad_h = 0;
+  int bits = 1;
+  g->n = n; g->E = E;
+  DA_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1)));
+  DA_TRY(cudaMalloc(&g->col, sizeof(int32_t) * (size_t)(E > 0 ? E : 1)));
+  DA_TRY(cudaMalloc(&g->eid, sizeof(int32_t) * (size_t)(E > 0 ? E : 1)));
+  if (E == 0) {
+    DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
+    return cudaSuccess;
+  }
+  DA_TRY(cudaMalloc(&key, sizeof(int32_t) * (size_t)E));
+  DA_TRY(cudaMalloc(&val, sizeof(int32_t) * (size_t)E));
+  DA_TRY(cudaMalloc(&key_sorted, sizeof(int32_t) * (size_t)E));
+  DA_TRY(cudaMalloc(&bad, sizeof(int32_t)));
+  DA_TRY(cudaMemsetAsync(bad, 0, sizeof(int32_t), s));
+  narrow_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, n, key, val, bad);
+  DA_TRY(cudaGetLastError());
+  while ((1ll << bits) < (long long)n + 1 && bits < 31) ++bits;
+  DA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key_sorted, val, g->eid, (int)E, 0, bits, s));
+  DA_TRY(cudaMalloc(&tmp, tmp_bytes));
+  DA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_sorted, val, g->eid, (int)E, 0, bits, s));
+  gather_cols_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, g->eid, E, n, g->col);
+  DA_TRY(cudaGetLastError());
+  rowptr_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(key_sorted, E, n, g->rowptr);
+  DA_TRY(cudaGetLastError());
+  DA_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DA_TRY(cudaStreamSynchronize(s));
+  cudaFree(key); cudaFree(val); cudaFree(key_sorted); cudaFree(bad); cudaFree(tmp);
+  if (bad_h) { *err = "edge_index entry outside [0, num_total)"; free_csr(g); return cudaErrorInvalidValue; }
+  return cudaSuccess;
+fail:
+  cudaFree(key); cudaFree(val); cudaFree(key_sorted); cudaFree(bad); cudaFree(tmp);
+  free_csr(g);
+  return ce;
+#undef DA_TRY
+}
+
+}  // namespace da

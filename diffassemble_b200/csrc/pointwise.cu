@@ -1,0 +1,232 @@
+// Node-wise stages around the projections: embedding prologue, head epilogue, sampler update.
+#include "common.cuh"
+#include "se3.cuh"
+
+namespace da {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Prologue: time_emb(t) (+) pos_mlp(x) folded into the first trunk linear.
+//   reference: efficient_gat.py:131-135 (efficient_gat_3d.py:181-186)
+//     combined_in = cat([feats(Dv), pos_mlp(x)(32), time_emb[t](32)])
+//     h = act(W1 @ combined_in + b1)
+//   here: h = act(P + W1[:, Dv:Dv+64] @ [pos(32), temb(32)]) with P = feats @ W1[:, :Dv]^T + b1
+//   hoisted out of the step loop by da_set_features (it does not depend on x or t).
+// ---------------------------------------------------------------------------------------------
+constexpr int PRO_NB = 8;      // nodes per CTA
+constexpr int PRO_NT = 256;
+
+__global__ void __launch_bounds__(PRO_NT)
+prologue_kernel(PrologueArgs a) {
+  __shared__ float xs[PRO_NB][8];
+  __shared__ float hid[PRO_NB][16];
+  __shared__ float f64[PRO_NB][64];
+  __shared__ int ts[PRO_NB];
+  const int tid = threadIdx.x;
+  const int node0 = blockIdx.x * PRO_NB;
+  if (tid < PRO_NB * 8) {
+    int nb = tid / 8, c = tid % 8, node = node0 + nb;
+    xs[nb][c] = (node < a.M && c < a.C_in) ? a.x[(size_t)node * a.C_in + c] : 0.f;
+    if (c == 0) {
+      int tt = a.t_uniform;
+      if (a.t && node < a.M) tt = (int)a.t[node];
+      ts[nb] = min(max(tt, 0), a.T - 1);
+    }
+  }
+  __syncthreads();
+  if (tid < PRO_NB * 16) {  // pos_mlp[0] + GELU
+    int nb = tid / 16, u = tid % 16;
+    float s = a.pos_b0[u];
+    for (int c = 0; c < a.C_in; ++c) s = fmaf(a.pos_w0[u * a.C_in + c], xs[nb][c], s);
+    hid[nb][u] = gelu_erf(s);
+  }
+  __syncthreads();
+  {  // pos_mlp[2] and the embedding row: PRO_NB * 32 == PRO_NT threads
+    int nb = tid / 32, v = tid % 32;
+    float s = a.pos_b2[v];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s = fmaf(a.pos_w2[v * 16 + u], hid[nb][u], s);
+    f64[nb][v] = s;
+    f64[nb][32 + v] = a.time_emb[(size_t)ts[nb] * 32 + v];
+  }
+  __syncthreads();
+  const int Hm = a.Hm;
+  for (int idx = tid; idx < PRO_NB * Hm; idx += PRO_NT) {
+    int nb = idx / Hm, n = idx % Hm, node = node0 + nb;
+    if (node >= a.M) continue;
+    float s = a.P ? a.P[(size_t)node * Hm + n] : a.b1[n];
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) s = fmaf(a.w1pt_T[k * Hm + n], f64[nb][k], s);
+    s = apply_act_rt(s, a.act);
+    if (a.out.f32) a.out.f32[(size_t)node * a.out.ldc + n] = s;
+    if (a.out.hi) {
+      __nv_bfloat16 h = __float2bfloat16_rn(s);
+      a.out.hi[(size_t)node * a.out.ld_split + n] = h;
+      a.out.lo[(size_t)node * a.out.ld_split + n] = __float2bfloat16_rn(s - __bfloat162float(h));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sampler updates (one value per thread), evaluated op by op in the reference's order with
+// explicit round-to-nearest intrinsics so no FMA contraction changes the result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ddpm_update(float x, float out, float noise, const da_step_coef& c) {
+  // spatial_diffusion.py:495-510
+  float mean = __fmul_rn(c.sqrt_recip_alpha, __fsub_rn(x, __fdiv_rn(__fmul_rn(c.beta_t, out), c.sqrt_one_minus_acp)));
+  if (c.t_index == 0) return mean;
+  return __fadd_rn(mean, __fmul_rn(sqrtf(c.posterior_variance), noise));
+}
+
+__device__ __forceinline__ float ddim_x0(float x, float out, const da_step_coef& c) {
+  // spatial_diffusion.py:603-606
+  if (c.pred == DA_PRED_START_X) return out;
+  float beta = __fsub_rn(1.f, c.acp);
+  return __fdiv_rn(__fsub_rn(x, __fmul_rn(sqrtf(beta), out)), sqrtf(c.acp));
+}
+
+__device__ __forceinline__ float ddim_update(float x, float out, float noise, const da_step_coef& c) {
+  // spatial_diffusion.py:548-627 with _get_variance :528-546 and _predict_eps_from_xstart :629-632
+  float x0 = ddim_x0(x, out, c);
+  float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.sqrt_recip_acp, x), x0), c.sqrt_recipm1_acp);
+  float beta = __fsub_rn(1.f, c.acp), beta_prev = __fsub_rn(1.f, c.acp_prev);
+  float variance = __fmul_rn(__fdiv_rn(beta_prev, beta), __fsub_rn(1.f, __fdiv_rn(c.acp, c.acp_prev)));
+  float std_eta = __fmul_rn(c.eta, sqrtf(variance));
+  float dir = __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.f, c.acp_prev), __fmul_rn(std_eta, std_eta))), eps);
+  float prev = __fadd_rn(__fmul_rn(sqrtf(c.acp_prev), x0), dir);
+  if (c.eta > 0.f) prev = __fadd_rn(prev, __fmul_rn(std_eta, noise));
+  return prev;
+}
+
+__device__ __forceinline__ float step_update(int mode, float x, float out, float noise, const da_step_coef& c) {
+  if (mode == STEP_DDPM) return ddpm_update(x, out, noise, c);
+  if (mode == STEP_DDIM) return ddim_update(x, out, noise, c);
+  return out;
+}
+
+// 2D head: out = W_b @ u + b_b (final_mlp[2], efficient_gat.py:91), fused with the sampler update.
+__global__ void head_final_2d_kernel(HeadFinalArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.M * a.C_out) return;
+  const int node = idx / a.C_out, c = idx % a.C_out;
+  const float* u = a.u + (size_t)node * a.Nh;
+  float s = a.b_b[c];
+  for (int k = 0; k < a.Nh; ++k) s = fmaf(a.w_b[c * a.Nh + k], u[k], s);
+  float x = 0.f, nz = 0.f;
+  if (a.step_mode != STEP_NONE) {
+    x = a.x_in[idx];
+    if (a.noise) nz = a.noise[idx];
+  }
+  a.out[idx] = step_update(a.step_mode, x, s, nz, a.coef);
+}
+
+// SE(3) head: one warp per node.  t = mlp_t[2](u[:256]); r = mlp_r[2](u[256:]);
+// q = normalize(matrix_to_quaternion(exp(hat(r))))  (efficient_gat_3d.py:211-220), then the
+// R^3 + SO(3) DDIM update of spatial_diffusion_3d_test_double_diffusion.py:595-685.
+__global__ void head_final_se3_kernel(HeadFinalArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int node = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (node >= a.M) return;
+  const int half = a.Nh / 2;
+  const float* u = a.u + (size_t)node * a.Nh;
+  float o[6];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float st = 0.f, sr = 0.f;
+    for (int k = lane; k < half; k += 32) {
+      st = fmaf(a.w_b[c * half + k], u[k], st);
+      sr = fmaf(a.w_r[c * half + k], u[half + k], sr);
+    }
+    o[c] = warp_sum(st) + a.b_b[c];
+    o[3 + c] = warp_sum(sr) + a.b_r[c];
+  }
+  if (lane != 0) return;
+  float q[4];
+  se3::axis_angle_to_unit_quat(o[3], o[4], o[5], q);
+  float model_out[7] = {q[0], q[1], q[2], q[3], o[0], o[1], o[2]};
+  float* dst = a.out + (size_t)node * 7;
+  if (a.step_mode == STEP_NONE) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) dst[i] = model_out[i];
+    return;
+  }
+  float x[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x[i] = a.x_in[(size_t)node * 7 + i];
+  float y[7];
+  se3::ddim_update_se3(x, model_out, a.coef, y);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) dst[i] = y[i];
+}
+
+__global__ void sampler_update_kernel(const float* __restrict__ x_in, const float* __restrict__ model_out,
+                                      float* __restrict__ x_out, int total, int mode, da_step_coef c,
+                                      const float* __restrict__ noise) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  x_out[idx] = step_update(mode, x_in[idx], model_out[idx], noise ? noise[idx] : 0.f, c);
+}
+
+__global__ void sampler_update_se3_kernel(const float* __restrict__ x_in, const float* __restrict__ model_out,
+                                          float* __restrict__ x_out, int M, da_step_coef c) {
+  const int node = blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= M) return;
+  float x[7], o[7], y[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) { x[i] = x_in[(size_t)node * 7 + i]; o[i] = model_out[(size_t)node * 7 + i]; }
+  se3::ddim_update_se3(x, o, c, y);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) x_out[(size_t)node * 7 + i] = y[i];
+}
+
+__global__ void fill_rows_kernel(float* __restrict__ dst, int ld, const float* __restrict__ table,
+                                 const int32_t* __restrict__ ids, int rows, int cols) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * cols) return;
+  int r = (int)(idx / cols), c = (int)(idx % cols);
+  dst[(size_t)r * ld + c] = table[(size_t)ids[r] * cols + c];
+}
+
+}  // namespace
+
+cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
+  if (a.M <= 0) return cudaSuccess;
+  if (a.C_in > 8) return cudaErrorInvalidValue;
+  prologue_kernel<<<(a.M + PRO_NB - 1) / PRO_NB, PRO_NT, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_final(const HeadFinalArgs& a, cudaStream_t s) {
+  if (a.M <= 0) return cudaSuccess;
+  if (a.head_kind == DA_HEAD_2D) {
+    int total = a.M * a.C_out;
+    head_final_2d_kernel<<<(total + 255) / 256, 256, 0, s>>>(a);
+  } else {
+    long long threads = (long long)a.M * 32;
+    head_final_se3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sampler_update(const float* x_in, const float* model_out, float* x_out, int M, int C,
+                                  int head_kind, int step_mode, const da_step_coef& coef,
+                                  const float* noise, cudaStream_t s) {
+  if (M <= 0) return cudaSuccess;
+  if (head_kind == DA_HEAD_SE3) {
+    sampler_update_se3_kernel<<<(M + 127) / 128, 128, 0, s>>>(x_in, model_out, x_out, M, coef);
+  } else {
+    int total = M * C;
+    sampler_update_kernel<<<(total + 255) / 256, 256, 0, s>>>(x_in, model_out, x_out, total, step_mode, coef, noise);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
+                             cudaStream_t s) {
+  size_t total = (size_t)rows * cols;
+  if (total == 0) return cudaSuccess;
+  fill_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dst, ld, table, ids, rows, cols);
+  return cudaGetLastError();
+}
+
+}  // namespace da

@@ -1,0 +1,398 @@
+"""Host-side mirror of ``puzzle_diff/model/spatial_diffusion.py`` (``GNN_Diffusion``).
+
+Same constructor keywords, buffer names, method names and return shapes as the
+reference Lightning module (``spatial_diffusion.py:219-357, 371-430, 485-699``), so it
+drops into ``train_script.py`` / ``viz_script.py`` / ``app.py`` for the sampling path.
+Every denoiser evaluation and every sampler update inside ``p_sample_loop`` is ONE
+fused call into ``libdiffassemble_b200.so`` (``da_ddpm_step`` / ``da_ddim_step``);
+torch is used for buffers, RNG and streams only.  No CPU path exists.
+
+Deliberate differences from the shipped reference:
+* ``p_sample_ddpm`` returns ``(x_prev, attentions)`` like ``p_sample_ddim`` (the shipped
+  version returns a bare tensor that ``p_sample_loop`` cannot unpack);
+* attention weights are not materialised unless ``return_attentions=True`` is asked of
+  ``forward_with_feats`` (the reference keeps 4 x [E, 8] per step and never reads them);
+* ``cond`` may be the pre-computed ``[nodes, feat_dim]`` feature matrix (the CNN encoder
+  is upstream of the hot path); image patches need an attached ``visual_backbone``.
+"""
+import enum
+from functools import partial
+from typing import Any, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import _cabi
+from ._cabi import da_step_coef
+from .backbones import Eff_GAT
+
+try:  # Lightning is optional: the reference subclasses pl.LightningModule (spatial_diffusion.py:219)
+    import pytorch_lightning as pl
+
+    _Base = pl.LightningModule
+    _HAVE_PL = True
+except Exception:  # pragma: no cover - depends on the environment
+    _Base = nn.Module
+    _HAVE_PL = False
+
+
+class ModelMeanType(enum.Enum):  # spatial_diffusion.py:60-67
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelScheduler(enum.Enum):  # spatial_diffusion.py:70-77
+    LINEAR = enum.auto()
+    COSINE = enum.auto()
+    COSINE_DISCRETE = enum.auto()
+
+
+def cosine_discrete_beta_schedule(timesteps, s=0.08):
+    steps = timesteps + 1
+    t = torch.linspace(0, timesteps, steps)
+    acp = lambda t: torch.cos(((t / timesteps) + s) / (1 + s) + np.pi / 2)  # noqa: E731
+    return torch.clip(1 - acp(t + 1) / acp(t), 0.0001, 0.9999)
+
+
+def cosine_beta_schedule(timesteps, s=0.08):
+    steps = timesteps + 1
+    x = torch.linspace(0, timesteps, steps)
+    acp = torch.cos(((x / timesteps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    acp = acp / acp[0]
+    return torch.clip(1 - (acp[1:] / acp[:-1]), 0.0001, 0.9999)
+
+
+def linear_beta_schedule(timesteps):
+    return torch.linspace(0.0001, 0.02, timesteps)
+
+
+def extract(a, t, x_shape=None):
+    return a.gather(-1, t)[:, None]
+
+
+_SCHEDULE_BUFFERS = (
+    "betas", "alphas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas", "sqrt_alphas_cumprod",
+    "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "posterior_variance",
+)
+
+
+class DiffusionScheduleMixin:
+    """Schedule buffers (``spatial_diffusion.py:282-321``) + their host copies for the fused steps."""
+
+    def _register_schedule(self, steps, scheduler):
+        betas = {
+            ModelScheduler.LINEAR: linear_beta_schedule,
+            ModelScheduler.COSINE: cosine_beta_schedule,
+            ModelScheduler.COSINE_DISCRETE: cosine_discrete_beta_schedule,
+        }[scheduler](timesteps=steps)
+        self.register_buffer("betas", betas)
+        self.register_buffer("alphas", 1.0 - self.betas)
+        self.register_buffer("alphas_cumprod", torch.cumprod(self.alphas, axis=0))
+        self.register_buffer("alphas_cumprod_prev", F.pad(self.alphas_cumprod[:-1], (1, 0), value=1.0))
+        self.register_buffer("sqrt_recip_alphas", torch.sqrt(1.0 / self.alphas))
+        self.register_buffer("sqrt_alphas_cumprod", torch.sqrt(self.alphas_cumprod))
+        self.register_buffer("sqrt_recip_alphas_cumprod", torch.sqrt(1.0 / self.alphas_cumprod))
+        self.register_buffer("sqrt_recipm1_alphas_cumprod", torch.sqrt(1.0 / self.alphas_cumprod - 1))
+        self.register_buffer("sqrt_one_minus_alphas_cumprod", torch.sqrt(1.0 - self.alphas_cumprod))
+        self.register_buffer(
+            "posterior_variance", self.betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        )
+        self._host_sched = None
+        self._host_sched_key = None
+
+    def _schedule_host(self):
+        key = tuple((getattr(self, n).data_ptr(), getattr(self, n)._version) for n in _SCHEDULE_BUFFERS)
+        if self._host_sched is None or key != self._host_sched_key:
+            self._host_sched = {n: getattr(self, n).detach().float().cpu().tolist() for n in _SCHEDULE_BUFFERS}
+            self._host_sched_key = key
+        return self._host_sched
+
+    def _step_coef(self, t: int, pred: int) -> da_step_coef:
+        s = self._schedule_host()
+        c = da_step_coef()
+        c.t, c.t_index, c.pred = int(t), int(t), pred
+        prev = int(t) - int(self.inference_ratio)
+        c.has_prev = 1 if prev >= 0 else 0
+        c.beta_t = s["betas"][t]
+        c.sqrt_one_minus_acp = s["sqrt_one_minus_alphas_cumprod"][t]
+        c.sqrt_recip_alpha = s["sqrt_recip_alphas"][t]
+        c.posterior_variance = s["posterior_variance"][t]
+        c.acp = s["alphas_cumprod"][t]
+        c.acp_prev = s["alphas_cumprod"][prev] if prev >= 0 else 1.0
+        c.sqrt_recip_acp = s["sqrt_recip_alphas_cumprod"][t]
+        c.sqrt_recipm1_acp = s["sqrt_recipm1_alphas_cumprod"][t]
+        c.eta = float(self.eta)
+        c.cfg_w = float(getattr(self, "classifier_free_w", 0.0))
+        return c
+
+    def _pred_code(self) -> int:
+        if self.model_mean_type == ModelMeanType.START_X:
+            return _cabi.DA_PRED_START_X
+        if self.model_mean_type == ModelMeanType.EPSILON:
+            return _cabi.DA_PRED_EPSILON
+        raise NotImplementedError("PREVIOUS_X is not used by the reference samplers")
+
+    def _get_variance(self, timestep, prev_timestep):  # spatial_diffusion.py:528-546
+        alpha_prod_t = extract(self.alphas_cumprod, timestep)
+        alpha_prod_t_prev = (
+            extract(self.alphas_cumprod, prev_timestep) if (prev_timestep >= 0).all() else alpha_prod_t * 0 + 1
+        )
+        return ((1 - alpha_prod_t_prev) / (1 - alpha_prod_t)) * (1 - alpha_prod_t / alpha_prod_t_prev)
+
+    def _predict_eps_from_xstart(self, x_t, t, pred_xstart):  # :629-632
+        return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - pred_xstart) / extract(
+            self.sqrt_recipm1_alphas_cumprod, t, x_t.shape
+        )
+
+
+class GNN_Diffusion(_Base, DiffusionScheduleMixin):
+    def __init__(
+        self,
+        steps=600,
+        inference_ratio=1,
+        sampling="DDPM",
+        learning_rate=1e-4,
+        save_and_sample_every=1000,
+        bb=None,
+        classifier_free_prob=0,
+        classifier_free_w=0,
+        noise_weight=0.0,
+        rotation=False,
+        model_mean_type: ModelMeanType = ModelMeanType.EPSILON,
+        input_channels=2,
+        output_channels=2,
+        scheduler: ModelScheduler = ModelScheduler.LINEAR,
+        visual_pretrained: bool = True,
+        freeze_backbone: bool = True,
+        backbone: str = "efficientnet_b0",
+        n_layers: int = 4,
+        architecture: str = "transformer",
+        virt_nodes: int = 4,
+        all_equivariant=False,
+        gemm_mode: str = "bf16x3",
+        attn_mode: str = "auto",
+        *args,
+        **kwargs,
+    ) -> None:
+        super().__init__(*args, **kwargs)
+        self.visual_pretrained = visual_pretrained
+        self.free_backbone = freeze_backbone
+        self.model_mean_type = model_mean_type
+        self.learning_rate = learning_rate
+        self.save_and_sample_every = save_and_sample_every
+        self.classifier_free_prob = classifier_free_prob
+        self.classifier_free_w = classifier_free_w
+        self.noise_weight = noise_weight
+        self.rotation = rotation
+        self.virt_nodes = virt_nodes
+        self.all_equivariant = all_equivariant
+        self.save_eval_images = False
+        self.gemm_mode, self.attn_mode = gemm_mode, attn_mode
+        if sampling not in ("DDPM", "DDIM"):
+            raise ValueError(f"unknown sampling {sampling!r}")
+        self.sampling = sampling
+        self.inference_ratio = inference_ratio
+        # spatial_diffusion.py:264-278 binds p_sample to one of the two samplers
+        self.p_sample = partial(
+            self._p_sample, sampling_func=self.p_sample_ddpm if sampling == "DDPM" else self.p_sample_ddim
+        )
+        self.eta = 1 if sampling == "DDPM" else 0
+        self._register_schedule(steps, scheduler)
+        self.steps = steps
+        self.input_channels = input_channels
+        self.output_channels = output_channels
+        self.backbone = backbone
+        self.n_layers = n_layers
+        self.architecture = architecture
+        self.init_backbone()
+        if _HAVE_PL:
+            self.save_hyperparameters()
+
+    if not _HAVE_PL:
+
+        @property
+        def device(self):
+            return self.betas.device
+
+        local_rank = 0
+
+        def log(self, *a, **k):
+            pass
+
+        def log_dict(self, *a, **k):
+            pass
+
+    def init_backbone(self):  # spatial_diffusion.py:334-357
+        extra = 2 if self.rotation else 0
+        self.model = Eff_GAT(
+            steps=self.steps,
+            input_channels=self.input_channels + extra,
+            output_channels=self.output_channels + extra,
+            visual_pretrained=self.visual_pretrained,
+            freeze_backbone=self.free_backbone,
+            all_equivariant=self.all_equivariant,
+            model=self.backbone,
+            architecture=self.architecture,
+            n_layers=self.n_layers,
+            virt_nodes=self.virt_nodes,
+            gemm_mode=self.gemm_mode,
+            attn_mode=self.attn_mode,
+        )
+
+    def initialize_torchmetrics(self, n_patches):  # metrics are downstream of the hot path (scope row N2)
+        self.metric_sizes = list(n_patches)
+
+    # -- denoiser ----------------------------------------------------------------------------
+    def forward(self, xy_pos, time, patch_rgb, edge_index, batch) -> Any:
+        return self.model(xy_pos, time, patch_rgb, edge_index, batch)
+
+    def forward_with_feats(self, xy_pos: Tensor, time: Tensor, patch_rgb: Tensor, edge_index: Tensor,
+                           patch_feats: Tensor, batch, return_attentions=False) -> Any:
+        out, attentions = self.model.forward_with_feats(
+            xy_pos, time, patch_rgb, edge_index, patch_feats, batch, return_attention=return_attentions
+        )
+        if return_attentions:
+            return out, attentions
+        return out
+
+    def visual_features(self, patch_rgb):
+        return self.model.visual_features(patch_rgb)
+
+    def _features_from_cond(self, cond):
+        if cond is None:
+            raise ValueError("cond (patches or pre-computed node features) is required")
+        if cond.dim() == 2 and cond.shape[1] == self.model.combined_features_dim - 64:
+            return cond  # already encoder features
+        return self.visual_features(cond)
+
+    # -- forward diffusion (training-side helpers; forward only) -----------------------------------
+    def q_sample(self, x_start, t, noise=None):  # :421-430
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        return (
+            extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+            + extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
+        )
+
+    @torch.no_grad()
+    def p_losses(self, x_start, t, noise=None, loss_type="l1", cond=None, edge_index=None, batch=None):
+        """Loss VALUE of ``spatial_diffusion.py:432-483`` (no autograd: training is scope row N1)."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
+        if self.steps == 1:
+            x_noisy = torch.zeros_like(x_noisy)
+        patch_feats = self._features_from_cond(cond)
+        prediction = self.forward_with_feats(x_noisy, t, cond, edge_index, patch_feats=patch_feats, batch=batch)
+        target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
+        if loss_type == "l1":
+            return F.l1_loss(target, prediction)
+        if loss_type == "l2":
+            return F.mse_loss(target, prediction)
+        if loss_type == "huber":
+            return F.smooth_l1_loss(target, prediction)
+        raise NotImplementedError()
+
+    # -- reverse diffusion -------------------------------------------------------------------
+    def _uniform_t(self, t: Tensor, t_index: int) -> bool:
+        return bool((t == int(t_index)).all())
+
+    @torch.no_grad()
+    def p_sample_ddpm(self, x, t, t_index, cond, edge_index, patch_feats, batch, noise=None):
+        """``spatial_diffusion.py:485-510``: fused denoiser + posterior-mean update."""
+        if self.model_mean_type != ModelMeanType.EPSILON:
+            raise NotImplementedError("p_sample_ddpm treats the model output as epsilon (spatial_diffusion.py:495-502)")
+        if not self._uniform_t(t, t_index):
+            raise NotImplementedError("the fused DDPM step needs t == t_index for every node (spatial_diffusion.py:665)")
+        eng = self.model.engine_for(edge_index, patch_feats, batch)
+        if int(t_index) != 0 and noise is None:
+            noise = torch.randn_like(x)
+        coef = self._step_coef(int(t_index), _cabi.DA_PRED_EPSILON)
+        return eng.ddpm_step(x, coef, noise if int(t_index) != 0 else None), None
+
+    @torch.no_grad()
+    def p_sample_ddim(self, x, t, t_index, cond, edge_index, patch_feats, batch, noise=None):
+        """``spatial_diffusion.py:548-627`` (incl. classifier-free guidance :568-589)."""
+        if not self._uniform_t(t, t_index):
+            raise NotImplementedError("the fused DDIM step needs t == t_index for every node (spatial_diffusion.py:665)")
+        coef = self._step_coef(int(t_index), self._pred_code())
+        if self.eta > 0 and noise is None:
+            noise = torch.randn(x.shape, dtype=x.dtype, device=x.device)
+        if self.classifier_free_prob > 0.0:
+            eng = self.model.engine_for(edge_index, patch_feats, batch)
+            out_cond = eng.forward(x, t)
+            eng = self.model.engine_for(edge_index, None, batch)  # patch_feats = zeros (:578-586)
+            out_uncond = eng.forward(x, t)
+            model_output = (1 + self.classifier_free_w) * out_cond - self.classifier_free_w * out_uncond
+            return eng.ddim_update(x, model_output, coef, noise if self.eta > 0 else None), None
+        eng = self.model.engine_for(edge_index, patch_feats, batch)
+        return eng.ddim_step(x, coef, noise if self.eta > 0 else None), None
+
+    @torch.no_grad()
+    def _p_sample(self, x, t, t_index, cond, edge_index, sampling_func, patch_feats, batch, noise=None):
+        return sampling_func(x, t, t_index, cond, edge_index, patch_feats, batch, noise=noise)
+
+    @torch.no_grad()
+    def p_sample_loop(self, shape, cond, edge_index, batch, generator: Optional[torch.Generator] = None):
+        """``spatial_diffusion.py:635-676``: returns ``(list of x_t per step, list of attentions)``.
+
+        The graph, features and weights are bound once; each iteration is a single fused
+        library call (no per-step Python-side tensor math, no host sync)."""
+        device = edge_index.device
+        img = torch.randn(shape, device=device, generator=generator) * self.noise_weight
+        imgs, attentions = [], []
+        patch_feats = self._features_from_cond(cond)
+        eng = self.model.engine_for(edge_index, patch_feats, batch)
+        cfg = self.classifier_free_prob > 0.0
+        pred = _cabi.DA_PRED_EPSILON if self.sampling == "DDPM" else self._pred_code()
+        if self.sampling == "DDPM" and self.model_mean_type != ModelMeanType.EPSILON:
+            raise NotImplementedError("p_sample_ddpm treats the model output as epsilon")
+        for i in list(reversed(range(0, self.steps, self.inference_ratio))):
+            if cfg:
+                t = torch.full((shape[0],), i, device=device, dtype=torch.long)
+                img, atts = self.p_sample_ddim(img, t, i, cond, edge_index, patch_feats, batch)
+            else:
+                coef = self._step_coef(i, pred)
+                if self.sampling == "DDPM":
+                    noise = torch.randn(shape, device=device, generator=generator) if i != 0 else None
+                    img = eng.ddpm_step(img, coef, noise)
+                else:
+                    noise = torch.randn(shape, device=device, generator=generator) if self.eta > 0 else None
+                    img = eng.ddim_step(img, coef, noise)
+                atts = None
+            attentions.append(atts)
+            imgs.append(img)
+        return imgs, attentions
+
+    @torch.no_grad()
+    def sample(self, image_size, batch_size=16, channels=3, cond=None, edge_index=None, batch=None):
+        return self.p_sample_loop(shape=(batch_size, channels, image_size, image_size), cond=cond,
+                                  edge_index=edge_index, batch=batch)
+
+    # -- Lightning hooks on the sampling path ------------------------------------------------------
+    def configure_optimizers(self):  # spatial_diffusion.py:701-705
+        from transformers.optimization import Adafactor
+
+        return Adafactor(self.parameters())
+
+    @torch.no_grad()
+    def prediction_step(self, batch, batch_idx):  # :768-773
+        return self.p_sample_loop(batch.x.shape, batch.patches, batch.edge_index, batch=batch.batch)
+
+    def predict_step(self, batch, batch_idx, dataloader_idx=0):
+        return self.prediction_step(batch, batch_idx)
+
+    def validation_step(self, batch, batch_idx):
+        """Sampling half of ``spatial_diffusion.py:775-790``; the assignment metric that
+        follows (greedy_cost_assignment, :179-216) is scope row N2."""
+        imgs, _ = self.p_sample_loop(batch.x.shape, batch.patches, batch.edge_index, batch=batch.batch)
+        return imgs[-1]
+
+    def test_step(self, batch, batch_idx):
+        return self.validation_step(batch, batch_idx)
+
+    def training_step(self, batch, batch_idx):
+        raise NotImplementedError("training (backward + Adafactor) through the CUDA denoiser is scope row N1")

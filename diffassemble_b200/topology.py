@@ -1,0 +1,106 @@
+"""Piece-graph topology producers (the inputs of the hot path; scope rows a14 / N3).
+
+* ``dense_edge_index(n)``: the fully-connected graph with self loops the reference
+  builds with ``dense_to_sparse(ones(n, n))`` (``puzzle_dataset.py:279-284``): row-major
+  ``(src, dst)`` pairs.
+* ``random_regular_edges`` / ``expander_edge_index``: the Exphander d-regular random graph
+  of ``puzzle_dataset.py:33-152`` -- a random permutation joined to its ``d // 2`` cyclic
+  shifts (plus a perfect matching when ``d`` is odd), symmetrised.  The same
+  ``numpy.random.Generator`` calls are made in the same order, so a given seed yields the
+  reference's graph.  The optional spectral-gap retry (``eigsh`` on the Laplacian, up to 5
+  draws, keep the best lambda_2) is available with ``check_spectral_gap=True``; note that all
+  candidates are relabelled circulant graphs with identical spectra, so that retry only ever
+  selects among the first five draws by floating-point noise.
+* ``batch_graphs``: PyG ``DataLoader`` collation of topologies (node offsets + batch vector).
+"""
+import math
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+
+def dense_edge_index(num_nodes: int, device=None) -> torch.Tensor:
+    idx = torch.arange(num_nodes, device=device)
+    src = idx.repeat_interleave(num_nodes)
+    dst = idx.repeat(num_nodes)
+    return torch.stack([src, dst])
+
+
+def resolve_degree(num_nodes: int, degree: Union[int, str]) -> int:
+    """``"60%"`` -> round(60 * (n - 1) / 100)  (puzzle_dataset.py:46-47, train_script.py:41-46)."""
+    if isinstance(degree, str):
+        degree = round((int(degree[:-1]) * (num_nodes - 1)) / 100)
+    return int(degree)
+
+
+def random_regular_edges(num_nodes: int, degree: int, rng: Optional[np.random.Generator] = None) -> Tuple[np.ndarray, np.ndarray]:
+    if (num_nodes * degree) % 2 != 0:
+        raise TypeError("nodes * degree must be even")
+    if rng is None:
+        rng = np.random.default_rng()
+    if degree == 0:
+        return np.array([], dtype=np.int64), np.array([], dtype=np.int64)
+    perm = rng.permutation(np.arange(num_nodes))
+    half = degree // 2
+    # neighbour at cyclic distance s in the permuted ring: position p pairs with position p - s
+    pos = np.arange(num_nodes)
+    shifts = np.arange(1, half + 1)
+    a = np.tile(perm, half)
+    b = perm[(pos[None, :] - shifts[:, None]) % num_nodes].reshape(-1)
+    if degree % 2:
+        m = num_nodes // 2
+        a = np.concatenate([a, perm[:m]])
+        b = np.concatenate([b, perm[m:]])
+    return np.concatenate([a, b]), np.concatenate([b, a])
+
+
+def _lambda2(senders, receivers, num_nodes):
+    """lambda_2 of the unnormalised Laplacian, as ``get_eigenvalue`` (puzzle_dataset.py:106-112):
+    float32 weights, self loops dropped, duplicate edges summed, ARPACK ``which="SM"``."""
+    from scipy.sparse import csr_matrix, identity
+    from scipy.sparse.linalg import eigsh
+
+    keep = senders != receivers
+    s, r = senders[keep], receivers[keep]
+    adj = csr_matrix((np.ones(len(s), dtype=np.float32), (s, r)), shape=(num_nodes, num_nodes))
+    deg = np.bincount(s, minlength=num_nodes).astype(np.float32)
+    lap = identity(num_nodes, dtype=np.float32, format="csr").multiply(deg[:, None]).tocsr() - adj
+    vals = eigsh(lap.tocoo(), k=2, which="SM", return_eigenvectors=False)
+    return vals[0] if len(vals) else 0.0
+
+
+def expander_edge_index(num_nodes: int, degree: Union[int, str], rng: Optional[np.random.Generator] = None,
+                        max_num_iters: int = 5, check_spectral_gap: bool = False) -> torch.Tensor:
+    """Returns ``edge_index`` ``[2, E]`` (int64), E = n * d, symmetric, no self loops."""
+    degree = resolve_degree(num_nodes, degree)
+    if rng is None:
+        rng = np.random.default_rng()
+    if num_nodes <= degree:
+        degree = num_nodes - 1
+    if num_nodes <= 10:  # complete graph without self loops (puzzle_dataset.py:68-73)
+        idx = np.arange(num_nodes)
+        s, r = np.repeat(idx, num_nodes), np.tile(idx, num_nodes)
+        keep = s != r
+        return torch.from_numpy(np.stack([s[keep], r[keep]])).long()
+    bound = max(0, degree - 2 * math.sqrt(degree - 1) - 0.1) if degree > 0 else 0
+    best, best_val, val, it = None, -1.0, -1.0, 1
+    while val < bound and it <= max_num_iters:
+        s, r = random_regular_edges(num_nodes, degree, rng)
+        if not check_spectral_gap:
+            best = (s, r)
+            break
+        val = _lambda2(s, r, num_nodes)
+        if val > best_val:
+            best_val, best = val, (s, r)
+        it += 1
+    return torch.from_numpy(np.stack(best)).long()
+
+
+def batch_graphs(edge_indices: Sequence[torch.Tensor], num_nodes: Sequence[int]):
+    offs, eis, batch = 0, [], []
+    for g, (ei, n) in enumerate(zip(edge_indices, num_nodes)):
+        eis.append(ei + offs)
+        batch.append(torch.full((n,), g, dtype=torch.long, device=ei.device))
+        offs += n
+    return torch.cat(eis, dim=1).contiguous(), torch.cat(batch)

@@ -1,0 +1,205 @@
+/*
+ * diffassemble_b200.h -- C ABI of the B200-native DiffAssemble denoiser + sampler step.
+ *
+ * This is the drop-in boundary for ONE hot path of IIT-PAVIS/DiffAssemble: the
+ * per-timestep graph-transformer denoiser and the DDPM/DDIM update that drives it.
+ * The reference has no FFI of its own (pure Python); each entry
+ * point below cites the reference Python interface it replaces (paths relative to
+ * the reference checkout).  The Python mirror of those interfaces lives in
+ * diffassemble_b200/ and binds this header with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (DA_OK) or a negative da_status;
+ *     nothing throws across the ABI.  da_last_error() gives a human-readable reason.
+ *   - "device pointer" = CUDA device memory of the handle's device, contiguous,
+ *     16-byte aligned, owned by the caller.  The library owns packed weights,
+ *     graph structure (CSR by target) and all workspace.
+ *   - every compute call is asynchronous on the cudaStream_t passed as `stream`
+ *     (as void*; NULL = legacy default stream).  One handle per (device, stream);
+ *     handles are not thread-safe.
+ *   - random numbers stay with the caller (noise is passed in) so seeds match the
+ *     reference call for call.
+ *   - there is NO CPU fallback: every entry point fails with DA_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef DIFFASSEMBLE_B200_H
+#define DIFFASSEMBLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DA_ABI_VERSION 1
+
+typedef enum da_status {
+  DA_OK = 0,
+  DA_ERR_INVALID = -1,     /* bad argument / shape / state (e.g. forward before set_graph) */
+  DA_ERR_CUDA = -2,        /* CUDA runtime / driver error, or no usable sm_100 device       */
+  DA_ERR_UNSUPPORTED = -3, /* configuration outside what the kernels implement              */
+  DA_ERR_MISSING = -4      /* a required weight was not loaded                              */
+} da_status;
+
+/* head_kind */
+#define DA_HEAD_2D 0  /* Eff_GAT.final_mlp:  D -> 32 -> C_out          (efficient_gat.py:88-92,144)   */
+#define DA_HEAD_SE3 1 /* Eff_GAT_3d.mlp_t / mlp_r -> [quat(4), t(3)]    (efficient_gat_3d.py:142-151,211-220) */
+/* arch */
+#define DA_ARCH_TRANSFORMER 0 /* Transformer_GNN: GELU after every layer but the last (Transformer_GNN.py:29-46) */
+#define DA_ARCH_EXOPHORMER 1  /* Exophormer_GNN: no activation, virtual nodes       (exophormer_gnn.py:161-215) */
+/* gemm_mode */
+#define DA_GEMM_FP32_SIMT 0  /* exact fp32 FMA on CUDA cores (debug / anchor mode)                         */
+#define DA_GEMM_BF16X3_UMMA 1 /* tcgen05 tensor cores, 3-pass split-bf16 (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), fp32 accumulate in TMEM */
+/* attn_mode */
+#define DA_ATTN_CSR 0  /* every edge through the CSR-by-target warp kernel                    */
+#define DA_ATTN_AUTO 1 /* per-graph dense bitmap tiles where the graph is dense enough, CSR for the rest */
+/* model_mean_type (spatial_diffusion.py:60-67) */
+#define DA_PRED_START_X 0
+#define DA_PRED_EPSILON 1
+
+typedef struct da_config {
+  int32_t abi_version;  /* must be DA_ABI_VERSION */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t feat_dim;     /* Dv: per-node encoder feature width (1088 for efficientnet_b0; 128 for pointnet) */
+  int32_t in_channels;  /* C_in : pose width fed to pos_mlp (2, 4 with rotation, 7 in 3D) */
+  int32_t out_channels; /* C_out: 2 / 4 (2D); 7 for the SE(3) head */
+  int32_t heads;        /* H = 8 */
+  int32_t hidden;       /* H*C of the inner layers = 256 */
+  int32_t n_layers;     /* 4 */
+  int32_t steps;        /* T, rows of time_emb */
+  int32_t mlp_hidden;   /* 128 (Eff_GAT.mlp) / 256 (Eff_GAT_3d.mlp) */
+  int32_t head_kind;    /* DA_HEAD_* */
+  int32_t arch;         /* DA_ARCH_* */
+  int32_t virt_nodes;   /* V (exophormer only; 0 = none) */
+  int32_t gemm_mode;    /* DA_GEMM_* */
+  int32_t attn_mode;    /* DA_ATTN_* */
+  int32_t reserved[8];  /* zero */
+} da_config;
+
+typedef struct da_handle da_handle;
+
+/* One named parameter tensor, fp32, row-major, in host OR device memory (UVA copy).
+ * Names are the reference state_dict keys of the denoiser (prefix "model." stripped),
+ * e.g. "time_emb.weight", "pos_mlp.0.weight", "mlp.2.bias",
+ * "gnn_backbone.module_list.3.lin_key.weight", "gnn_backbone.virt_node_embedding.weight",
+ * "final_mlp.0.weight", "mlp_t.2.bias" (SURVEY.md section 2.3f). */
+typedef struct da_weight_desc {
+  const char* name;
+  const float* data;
+  int64_t rows; /* weight: out_features (embedding: num_embeddings); bias: length */
+  int64_t cols; /* weight: in_features  (embedding: dim);            bias: 1      */
+} da_weight_desc;
+
+/* Replaces Eff_GAT.__init__ / Eff_GAT_3d.__init__ (efficient_gat.py:23-112,
+ * efficient_gat_3d.py:57-151): allocates the handle, no weights yet. */
+int da_create(da_handle** out, const da_config* cfg);
+void da_destroy(da_handle* h);
+const char* da_last_error(const da_handle* h); /* h may be NULL: last da_create error */
+
+/* Replaces nn.Module.load_state_dict for the denoiser (checkpoint -> packed device
+ * weights).  May be called repeatedly; every call re-packs (QKV+skip concatenated per
+ * layer, split-bf16 planes for the tensor-core path). */
+int da_load_weights(da_handle* h, const da_weight_desc* w, int32_t n);
+
+/* Replaces the (edge_index, batch) arguments of Eff_GAT.forward_with_feats
+ * (efficient_gat.py:121-129) and, for arch=EXOPHORMER, consumes the extended
+ * multigraph that exophormer_gnn.py:164-200 builds (the host mirror builds it once
+ * per batch instead of once per step).
+ *   edge_src/edge_dst : int64 device pointers, E entries: message j=src[e] -> i=dst[e];
+ *                       a multiset (duplicates count twice in the softmax)
+ *   batch             : int64 device pointer, num_real entries, non-decreasing graph ids
+ *   num_real          : real nodes (rows of x / out)
+ *   num_total         : num_real + virtual rows appended after the real ones
+ *   virt_ids          : int32 device pointer, (num_total-num_real) rows of
+ *                       virt_node_embedding to place in the virtual rows (NULL if none)
+ * Builds CSR-by-target on the device (stable sort: deterministic summation order). */
+int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
+                 const int64_t* batch, int32_t num_real, int32_t num_total,
+                 const int32_t* virt_ids, void* stream);
+
+/* Replaces the patch_feats / pcd_feats argument (efficient_gat.py:127,
+ * efficient_gat_3d.py:178): feats is fp32 [num_real, feat_dim] on the device, or NULL
+ * for all-zero features (classifier-free "unconditional" pass,
+ * spatial_diffusion.py:578-586).  Runs the step-invariant part of mlp[0] once
+ * (feats @ W1[:, :Dv]^T + b1) so the per-step cost is the 64 pose+time columns only. */
+int da_set_features(da_handle* h, const float* feats, void* stream);
+
+/* Replaces Eff_GAT.forward_with_feats / Eff_GAT_3d.forward_with_feats
+ * (efficient_gat.py:121-146, efficient_gat_3d.py:173-220).
+ *   x   : fp32 [num_real, C_in]     t : int64 [num_real] (per node, as the reference)
+ *   out : fp32 [num_real, C_out]
+ *   alpha_last : NULL, or fp32 [E, H] attention weights of the LAST layer in the
+ *                caller's edge order (exophormer_gnn.py:205-207); DA_ATTN_CSR only. */
+int da_forward(da_handle* h, const float* x, const int64_t* t, float* out, float* alpha_last,
+               void* stream);
+
+/* Scalar schedule coefficients of one sampler step, computed by the caller in fp32
+ * exactly as the reference does from its registered buffers
+ * (spatial_diffusion.py:289-321). */
+typedef struct da_step_coef {
+  int32_t t;                 /* timestep index (uniform over nodes in sampling, spatial_diffusion.py:665) */
+  int32_t t_index;           /* == t in the reference loop; DDPM adds no noise when 0 */
+  int32_t pred;              /* DA_PRED_* */
+  int32_t has_prev;          /* DDIM: (t - inference_ratio) >= 0 */
+  float beta_t;              /* betas[t] */
+  float sqrt_one_minus_acp;  /* sqrt_one_minus_alphas_cumprod[t] */
+  float sqrt_recip_alpha;    /* sqrt_recip_alphas[t] */
+  float posterior_variance;  /* posterior_variance[t] */
+  float acp;                 /* alphas_cumprod[t] */
+  float acp_prev;            /* alphas_cumprod[t - ratio], or 1 when !has_prev */
+  float sqrt_recip_acp;      /* sqrt_recip_alphas_cumprod[t] */
+  float sqrt_recipm1_acp;    /* sqrt_recipm1_alphas_cumprod[t] */
+  float eta;                 /* 0 (DDIM) or 1 */
+  float cfg_w;               /* classifier_free_w (unused unless x_uncond given) */
+} da_step_coef;
+
+/* Replaces GNN_Diffusion.p_sample_ddpm (spatial_diffusion.py:485-510): one denoiser
+ * forward fused with the posterior-mean update.  x_in / x_out fp32 [num_real, C]
+ * (may alias); noise fp32 [num_real, C] or NULL when t_index == 0. */
+int da_ddpm_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c,
+                 const float* noise, void* stream);
+
+/* Replaces GNN_Diffusion.p_sample_ddim (spatial_diffusion.py:548-627) for
+ * classifier_free_prob == 0: denoiser forward fused with the DDIM update; noise is
+ * only read when eta > 0.  For head_kind == DA_HEAD_SE3 this is the R^3 + SO(3)
+ * update of spatial_diffusion_3d_test_double_diffusion.py:595-685. */
+int da_ddim_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c,
+                 const float* noise, void* stream);
+
+/* Sampler update alone on a given model output (used for classifier-free guidance,
+ * where two forwards are blended first, spatial_diffusion.py:568-589). */
+int da_ddim_update(da_handle* h, const float* x_in, const float* model_out, float* x_out,
+                   const da_step_coef* c, const float* noise, void* stream);
+
+/* Introspection for tests, roofline accounting and gpu_launches. */
+size_t da_workspace_bytes(const da_handle* h);
+int64_t da_launch_count(const da_handle* h); /* kernels launched by this handle so far */
+int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_edges,
+                   int32_t* n_dense_graphs);
+/* Built-in CUDA-event profiler: with da_set_profiling(h, 1) every kernel launch is bracketed
+ * by events on its own stream and accumulated per launch site ("tag").  da_get_profile fills
+ * up to n_classes entries (ms and launch counts per tag), optionally resets, and returns the
+ * number of tags; da_profile_tag_name(i) names tag i ("qkvs_gemm_first", "attn_last", ...). */
+int da_set_profiling(da_handle* h, int32_t enable);
+int da_get_profile(da_handle* h, double* ms_out, int64_t* launches_out, int32_t n_classes, int32_t reset);
+const char* da_profile_tag_name(int32_t i);
+
+/* Stand-alone operator entry points (unit-level parity tests and micro-benchmarks).
+ * y[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]); act: 0 none, 1 GELU(erf), 2 LeakyReLU(0.2).
+ * mode = DA_GEMM_*; all pointers device fp32. */
+int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y,
+                 int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* TransformerConv attention stage on precomputed projections (section 2.3c of SURVEY.md):
+ * qkvs fp32 [n, 4*H*C] laid out [Q | K | V | skip]; edges as in da_set_graph;
+ * y[n, H*C] = softmax-aggregate + skip. */
+int da_op_graph_attention(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst,
+                          int64_t E, int32_t n, int32_t H, int32_t C, float* y, float* alpha,
+                          void* stream);
+
+int da_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFASSEMBLE_B200_H */

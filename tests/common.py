@@ -1,0 +1,67 @@
+"""Shared helpers for the parity tests (test infrastructure; may import the oracle)."""
+import torch
+
+import oracle
+
+TOL = 1e-4  # BASELINE.json north_star: per-step poses within 1e-4 relative of the fp32 oracle
+
+
+def rel_err(y, ref):
+    """max|y - ref| / max|ref|  (SURVEY.md section 8d parity metric)."""
+    y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
+    return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+def quat_rel_err(y, ref):
+    """Quaternion block compared up to sign (pytorch3d releases differ on standardisation)."""
+    y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
+    sign = torch.where((y[:, :4] * ref[:, :4]).sum(-1, keepdim=True) < 0, -1.0, 1.0)
+    y = torch.cat([y[:, :4] * sign, y[:, 4:]], 1)
+    return ((y - ref).abs().max() / ref.abs().max()).item()
+
+
+def make_pair_2d(seed=0, steps=300, sampling="DDPM", architecture="transformer", virt_nodes=4, rotation=True,
+                 model_mean_type="EPSILON", inference_ratio=1, gemm_mode="fp32", attn_mode="csr", **extra):
+    """Oracle module + product module sharing one seeded state_dict."""
+    import diffassemble_b200 as dab
+
+    torch.manual_seed(seed)
+    ref = oracle.GNNDiffusionRef(
+        steps=steps, sampling=sampling, rotation=rotation, architecture=architecture, virt_nodes=virt_nodes,
+        model_mean_type=oracle.ModelMeanType[model_mean_type], inference_ratio=inference_ratio, **extra)
+    ref.eval()
+    mod = dab.GNN_Diffusion(
+        steps=steps, sampling=sampling, rotation=rotation, architecture=architecture, virt_nodes=virt_nodes,
+        model_mean_type=dab.ModelMeanType[model_mean_type], inference_ratio=inference_ratio, gemm_mode=gemm_mode,
+        attn_mode=attn_mode, **extra)
+    missing = mod.load_state_dict(ref.state_dict(), strict=True)
+    return ref, mod
+
+
+def make_pair_3d(seed=0, steps=300, backbone="pointnet", inference_ratio=10, model_mean_type="START_X",
+                 gemm_mode="fp32", attn_mode="csr"):
+    import diffassemble_b200 as dab
+
+    torch.manual_seed(seed)
+    ref = oracle.GNNDiffusion3dRef(steps=steps, backbone=backbone, inference_ratio=inference_ratio,
+                                   model_mean_type=oracle.ModelMeanType[model_mean_type])
+    ref.eval()
+    mod = dab.GNN_Diffusion_3d(steps=steps, sampling="DDIM", backbone=backbone, inference_ratio=inference_ratio,
+                               model_mean_type=dab.ModelMeanType[model_mean_type], gemm_mode=gemm_mode,
+                               attn_mode=attn_mode)
+    mod.load_state_dict(ref.state_dict(), strict=False)
+    return ref, mod
+
+
+def synth_graph_batch(sizes, kind="dense", degree="60%", seed=0):
+    """edge_index / batch for a list of graph sizes (dense incl. self loops, or Exphander)."""
+    import numpy as np
+
+    eis = []
+    for g, n in enumerate(sizes):
+        if kind == "dense":
+            eis.append(oracle.dense_edge_index(n))
+        else:
+            rng = np.random.default_rng(seed + g)
+            eis.append(oracle.generate_random_expander(n, degree, rng=rng, check_spectral_gap=False).t().contiguous())
+    return oracle.batch_graphs(eis, sizes)

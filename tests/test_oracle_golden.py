@@ -1,0 +1,46 @@
+"""The oracle must reproduce the committed golden fixtures (drift detector for the restatement)."""
+from pathlib import Path
+
+import pytest
+import torch
+
+import oracle
+from common import rel_err
+
+G = Path(__file__).resolve().parent / "golden"
+
+
+def _checksum(module):
+    return float(sum(v.double().abs().sum() for k, v in sorted(module.state_dict().items()) if v.is_floating_point()))
+
+
+@pytest.mark.parametrize("name", ["c1_dense36_ddpm", "dense_ragged_ddim", "exph_2x64_ddim"])
+def test_oracle_matches_golden_2d(name):
+    d = torch.load(G / f"{name}.pt")
+    torch.manual_seed(0)
+    ref = oracle.GNNDiffusionRef(steps=d["T"], sampling=d["sampling"], rotation=True, architecture=d["architecture"],
+                                 virt_nodes=d["virt_nodes"], model_mean_type=oracle.ModelMeanType[d["mean_type"]],
+                                 inference_ratio=d["ratio"]).eval()
+    if abs(_checksum(ref) - d["weight_checksum"]) > 1e-6 * d["weight_checksum"]:
+        pytest.skip("torch's default initialisers produced different weights than when the fixture was made")
+    with torch.no_grad():
+        out, atts = ref.model.forward_with_feats(d["x"], d["t"], None, d["edge_index"], d["feats"], d["batch"])
+        tt = torch.full_like(d["t"], d["step_t"])
+        step, _ = ref.p_sample(d["x"], tt, d["step_t"], edge_index=d["edge_index"], patch_feats=d["feats"],
+                               batch=d["batch"], noise=d["step_noise"])
+    assert rel_err(out, d["out"]) < 1e-5
+    assert rel_err(atts[-1][1], d["alpha_last"]) < 1e-5
+    assert rel_err(step, d["step_out"]) < 1e-5
+
+
+def test_oracle_matches_golden_3d():
+    d = torch.load(G / "se3_ragged.pt")
+    torch.manual_seed(0)
+    ref = oracle.GNNDiffusion3dRef(steps=d["T"], backbone="pointnet", inference_ratio=d["ratio"],
+                                   model_mean_type=oracle.ModelMeanType.START_X).eval()
+    if abs(_checksum(ref) - d["weight_checksum"]) > 1e-6 * d["weight_checksum"]:
+        pytest.skip("initialiser drift")
+    with torch.no_grad():
+        out, _ = ref.model.forward_with_feats(d["x"], d["t"], d["edge_index"], d["feats"], d["batch"])
+    assert rel_err(out, d["out"]) < 1e-5
+    assert torch.allclose(out[:, :4].norm(dim=-1), torch.ones(out.shape[0]), atol=1e-5)

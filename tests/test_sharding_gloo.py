@@ -1,0 +1,42 @@
+"""world_size-2 gloo test of the N>1 host path: shard by graph, one all-gather at the end."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from diffassemble_b200 import sharding
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sizes = [4, 6, 3, 5, 2]
+    ei, batch = oracle.batch_graphs([oracle.dense_edge_index(n) for n in sizes], sizes)
+    x = torch.arange(float(sum(sizes)) * 4).reshape(-1, 4)
+    _, _, (x_r,), (n0, n1) = sharding.shard_batch(ei, batch, [x], world, rank)
+    counts = []
+    for r in range(world):
+        g0, g1 = sharding.shard_bounds(len(sizes), world, r)
+        counts.append(sum(sizes[g0:g1]))
+    poses = x_r * 2.0  # stand-in for the per-rank sampling loop (no collective inside it)
+    full = sharding.gather_poses(poses, counts)
+    q.put((rank, torch.equal(full, x * 2.0)))
+    dist.destroy_process_group()
+
+
+def test_shard_then_single_gather_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
