@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: denoising steps/sec on 900-node (30x30) puzzle graphs.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" is one pass of the hot path over one batch: one denoiser forward fused
+with the sampler update for every graph of the per-GPU batch.  `value` counts graph-steps
+(denoising steps x graphs) per second over all ranks, inputs resident in HBM; `e2e` is the same
+metric through the public `GNN_Diffusion.p_sample_loop` API with pinned HOST buffers (uploads of
+features / topology / state and the per-step device->host read of x_t inside the timed region).
+
+Workload (default, BASELINE.json configs[2]): 30x30 puzzles (900 nodes), Exphander 60 % sparse
+edges (d = 539), architecture="exophormer" with 8 virtual nodes, 32 graphs per GPU, DDIM with
+x0-prediction, T = 300, inference_ratio = 10 (the shipped launch-script setting), fp32 state,
+synthetic N(0,1) patch features and seeded random-init weights.
+
+`--impl reference` times the reference formulation on the host cores: the pure-torch edge-list
+oracle (PyG / the reference package cannot be installed in this image), on a
+bounded sample (one 900-node graph per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "denoising-steps/sec on 900-node (30x30) puzzle graphs"
+UNIT = "graph-steps/s"
+
+WORKLOADS = {
+    # name: (nodes per graph, graphs per GPU, topology, architecture, virt_nodes)
+    "c3_exphander60_v8": dict(n=900, B=32, kind="expander", degree="60%", arch="exophormer", V=8),
+    "c3_exphander60_v0": dict(n=900, B=32, kind="expander", degree="60%", arch="exophormer", V=0),
+    "c3_exphander20_v8": dict(n=900, B=32, kind="expander", degree="20%", arch="exophormer", V=8),
+    "c3_dense": dict(n=900, B=32, kind="dense", degree=None, arch="transformer", V=0),
+    "c2_dense144": dict(n=144, B=1, kind="dense", degree=None, arch="transformer", V=0),
+}
+T_STEPS, RATIO = 300, 10
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---- work accounting (SURVEY.md section 8d / BASELINE.md section 2) -------------------------------------------
+def flops_per_node(D=1152, C=4, Hm=128, hid=256):
+    return 2 * (C * 16 + 16 * 32 + D * Hm + Hm * D + 4 * D * hid + 2 * (4 * hid * hid) + 4 * hid * D + D * 32 + 32 * C)
+
+
+def flops_per_edge(D=1152, hid=256):
+    return 4 * (3 * hid + D)
+
+
+def bytes_per_node(D=1152, Dv=1088, C=4, hid=256):
+    shc = 3 * hid + D
+    return 4 * (Dv + C + C + 3 * D + 4 * shc + 2 * 3 * hid)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_topology(w, device, seed, module):
+    """Host-side topology of one per-GPU batch (pinned), as the dataloader would deliver it."""
+    from diffassemble_b200 import topology
+
+    eis = []
+    for g in range(w["B"]):
+        if w["kind"] == "dense":
+            eis.append(topology.dense_edge_index(w["n"]))
+        else:
+            eis.append(topology.expander_edge_index(w["n"], w["degree"], rng=np.random.default_rng(seed + g)))
+    ei, batch = topology.batch_graphs(eis, [w["n"]] * w["B"])
+    return ei, batch
+
+
+def make_module(w, gemm_mode, attn_mode, device):
+    import diffassemble_b200 as dab
+
+    torch.manual_seed(0)
+    mod = dab.GNN_Diffusion(steps=T_STEPS, sampling="DDIM", inference_ratio=RATIO, rotation=True, noise_weight=1.0,
+                            model_mean_type=dab.ModelMeanType.START_X, architecture=w["arch"], virt_nodes=w["V"],
+                            gemm_mode=gemm_mode, attn_mode=attn_mode)
+    return mod.to(device)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"warning: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    w = WORKLOADS[args.workload]
+    from diffassemble_b200 import _cabi, sharding
+
+    mod = make_module(w, args.gemm, args.attn, device)
+    M = w["n"] * w["B"]
+    ei_h, batch_h = build_topology(w, device, seed=1000 * rank, module=mod)
+    g = torch.Generator().manual_seed(1 + rank)
+    feats_h = torch.randn(M, 1088, generator=g).pin_memory()
+    x_h = torch.randn(M, 4, generator=g).pin_memory()
+    ei_h, batch_h = ei_h.pin_memory(), batch_h.pin_memory()
+
+    # ---------------- device-resident arm: inputs already in HBM -----------------------------------
+    ei, batch, feats, x0 = ei_h.to(device), batch_h.to(device), feats_h.to(device), x_h.to(device)
+    eng = mod.model.engine_for(ei, feats, batch)
+    pred = mod._pred_code()
+    sched = list(reversed(range(0, T_STEPS, RATIO)))
+    coefs = [mod._step_coef(i, pred) for i in sched]
+    xa, xb = x0.clone(), torch.empty_like(x0)
+
+    def one_step(k, xin, xout):
+        eng.ddim_step(xin, coefs[k % len(coefs)], None, out=xout)
+
+    for k in range(args.warmup):
+        one_step(k, xa, xb); xa, xb = xb, xa
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize()
+        ev0.record()
+        for k in range(args.steps):
+            one_step(k, xa, xb); xa, xb = xb, xa
+        if world > 1:  # the ONE collective of the sampling path: gather of the predicted poses
+            full = sharding.gather_poses(xa, [M] * world)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    if world > 1:
+        tms = torch.tensor([ms], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = w["B"] * world * args.steps / (ms / 1e3)
+
+    # ---------------- per-kernel times (CUDA events inside the library, same stream) -----------------
+    eng.set_profiling(True)
+    eng.get_profile(reset=True)
+    for k in range(min(args.steps, 10)):
+        one_step(k, xa, xb); xa, xb = xb, xa
+    torch.cuda.synchronize()
+    prof = eng.get_profile(reset=True)
+    eng.set_profiling(False)
+    nprof = min(args.steps, 10)
+    stats = eng.graph_stats()
+
+    # ---------------- end-to-end arm: public API, pinned host buffers -------------------------------
+    e2e = None
+    if args.e2e_loops > 0:
+        mod.model.invalidate()
+        loops = args.e2e_loops
+        host_out = torch.empty((len(sched), M, 4), dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(loops):
+            ei_d = ei_h.to(device, non_blocking=True)
+            batch_d = batch_h.to(device, non_blocking=True)
+            feats_d = feats_h.to(device, non_blocking=True)
+            imgs, _ = mod.p_sample_loop((M, 4), feats_d, ei_d, batch_d)
+            for s, img in enumerate(imgs):
+                host_out[s].copy_(img, non_blocking=True)
+            if world > 1:
+                sharding.gather_poses(imgs[-1], [M] * world)
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tdt = torch.tensor([dt], device=device)
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            dt = float(tdt.item())
+        nsteps = loops * len(sched)
+        h2d = (ei_h.numel() * 8 + batch_h.numel() * 8 + feats_h.numel() * 4) / len(sched)
+        e2e = {"value": w["B"] * world * nsteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(M * 4 * 4), "api": "GNN_Diffusion.p_sample_loop (DDIM, 30 steps/loop), pinned host inputs",
+               "loops": loops}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel -----------------------------------------------
+    pk = peaks()
+    E = ei.shape[1]
+    Mt = eng.num_total
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    dom_name, dom_ms = dom[0], dom[1]["ms"] / max(1, dom[1]["launches"])
+    step_ms_prof = sum(v["ms"] for v in prof.values()) / nprof
+    E_tot = eng.num_edges
+    hid, D = 256, 1152
+    if "gemm" in dom_name:
+        shapes = {"hoist_gemm": (M, 128, 1088), "mlp2_gemm": (M, D, 128), "qkvs_gemm_first": (Mt, 4 * hid, D),
+                  "qkvs_gemm_mid": (Mt, 4 * hid, hid), "qkvs_gemm_last": (Mt, 4 * D, hid), "head_gemm": (M, 32, D)}[dom_name]
+        fl = 2.0 * shapes[0] * shapes[1] * shapes[2]
+        ach = fl / (dom_ms * 1e-3) / 1e12
+        peak = pk["tensor_sustained"]
+        roof = {"bound": "tensor", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "peak_source": pk["source"] + ", sustained (timed inside a long step)",
+                "note": "algorithmic 2*M*N*K flops; the tensor-core path issues 3 bf16 passes per product for fp32 parity"
+                        if args.gemm == "bf16x3" else "fp32 CUDA-core GEMM (exact mode) measured against the bf16 tensor peak"}
+    else:
+        HC = D if dom_name == "attn_last" else hid
+        ntgt = M if dom_name == "attn_last" else Mt
+        # compulsory bytes: Q,K,V,skip read once, output written once, one int32 column index per edge
+        by = 4.0 * (4 * HC * Mt + HC * ntgt + (HC * M if dom_name == "attn_last" else 0)) + 4.0 * E_tot
+        ach = by / (dom_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                "traffic": None, "peak_source": pk["source"],
+                "attn_tflops": 4.0 * E_tot * HC / (dom_ms * 1e-3) / 1e12,
+                "note": "algorithmic (compulsory) bytes of the layer: QKV+skip read once, output once, 4 B/edge of indices"}
+    roof["share_of_step"] = dom[1]["ms"] / nprof / step_ms_prof if step_ms_prof else None
+    roof["per_kernel_ms_per_step"] = {k: round(v["ms"] / nprof, 4) for k, v in prof.items() if v["launches"]}
+    ncu = ROOT / "profiles" / "ncu_traffic.json"
+    if ncu.exists():
+        try:
+            roof["traffic"] = json.loads(ncu.read_text()).get(dom_name)
+        except Exception:
+            pass
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "nodes_per_graph": w["n"], "graphs_per_gpu": w["B"], "edges_per_gpu": int(E),
+                   "edges_per_gpu_with_virtual": int(E_tot), "topology": w["kind"] + (f" {w['degree']}" if w["degree"] else ""),
+                   "architecture": w["arch"], "virt_nodes": w["V"], "sampler": "DDIM x0-pred T=300 ratio=10",
+                   "gemm_mode": args.gemm, "attn_mode": args.attn, "parallelism": f"graph-shard x{world}",
+                   "batch_steps_per_s": args.steps / (ms / 1e3),
+                   "l2_policy": "per-step working set ~%.1f GB >> 126 MB L2 (no flush needed)" % (bytes_per_node() * M / 1e9),
+                   "graph_stats": stats, "workspace_gb": eng.workspace_bytes() / 1e9},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "e2e": e2e,
+        "roofline": roof,
+        "work": {"gflop_per_step": (M * flops_per_node() + E_tot * flops_per_edge()) / 1e9,
+                 "compulsory_gb_per_step": (bytes_per_node() * M + 16 * E_tot) / 1e9,
+                 "achieved_tflops_total": (M * flops_per_node() + E_tot * flops_per_edge()) / (ms_per_step * 1e-3) / 1e12},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(w, steps=args.cpu_steps)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(w, steps=2):
+    """The oracle (edge-list restatement of the reference formulation) timed on the host cores on a
+    bounded sample: ONE graph of the workload per step (B=32 would need >100 GB of per-edge tensors)."""
+    import oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    ref = oracle.GNNDiffusionRef(steps=T_STEPS, sampling="DDIM", rotation=True, architecture=w["arch"], virt_nodes=w["V"],
+                                 model_mean_type=oracle.ModelMeanType.START_X, inference_ratio=RATIO).eval()
+    n = w["n"]
+    if w["kind"] == "dense":
+        ei = oracle.dense_edge_index(n)
+    else:
+        ei = oracle.generate_random_expander(n, w["degree"], rng=np.random.default_rng(0), check_spectral_gap=False).t().contiguous()
+    batch = torch.zeros(n, dtype=torch.long)
+    g = torch.Generator().manual_seed(0)
+    feats, x = torch.randn(n, 1088, generator=g), torch.randn(n, 4, generator=g)
+    sched = list(reversed(range(0, T_STEPS, RATIO)))
+    with torch.no_grad():
+        t = torch.full((n,), sched[0], dtype=torch.long)
+        x, _ = ref.p_sample(x, t, sched[0], edge_index=ei, patch_feats=feats, batch=batch)  # warm-up
+        t0 = time.perf_counter()
+        for k in range(steps):
+            i = sched[(k + 1) % len(sched)]
+            t = torch.full((n,), i, dtype=torch.long)
+            x, _ = ref.p_sample(x, t, i, edge_index=ei, patch_feats=feats, batch=batch)
+        dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} DDIM steps of ONE {n}-node graph ({ei.shape[1]} edges) of the workload, torch-cpu edge-list oracle "
+                      f"(PyG absent: reference formulation restated), {cores} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    steps = max(1, min(args.steps, 3))
+    for _ in range(0):
+        pass
+    cb = cpu_baseline(w, steps=steps)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": steps, "warmup": 1, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "nodes_per_graph": w["n"], "graphs_per_step": 1,
+                      "note": "bounded sample: one graph per step on the host cores"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_exphander60_v8", choices=sorted(WORKLOADS))
+    ap.add_argument("--gemm", default="bf16x3", choices=["fp32", "bf16x3"])
+    ap.add_argument("--attn", default="auto", choices=["csr", "auto"])
+    ap.add_argument("--e2e-loops", type=int, default=1)
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
