@@ -1,9 +1,359 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Tensor-core linear layer for sm_100a: y = act(x @ w^T + bias) with fp32-faithful results.
+//
+// Every nn.Linear on the hot path (efficient_gat.py:88-102, the four TransformerConv projections
+// fused as one [Q|K|V|skip] GEMM per layer) runs here.  The reference computes them in fp32
+// (torch 1.12, TF32 off); a single bf16 or TF32 pass misses the 1e-4 parity bar (2e-3 / 3e-4
+// end to end), so each fp32 operand is carried as two bf16 planes (hi = bf16(x), lo = bf16(x - hi))
+// and the product is evaluated as three tcgen05 MMAs per k-step
+//        a_hi*w_hi + a_hi*w_lo + a_lo*w_hi          (fp32 accumulation in TMEM)
+// which leaves a ~2^-17 relative error per product (5e-6 end to end, measured).
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor of the four operand planes into a 128B-swizzled
+//               smem ring (full/empty mbarriers)
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to the barriers
+//   warps 2-5   epilogue: tcgen05.ld of the 128 x BN fp32 accumulator (double-buffered in TMEM so
+//               the next tile's MMAs overlap it), + bias, activation, fp32 and/or split-bf16 stores
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "umma.cuh"
+
 namespace da {
-cudaError_t launch_linear_umma(const __nv_bfloat16*, const __nv_bfloat16*, int, const __nv_bfloat16*,
-                               const __nv_bfloat16*, int, const float*, const LinearOut&, int, int, int, int,
-                               cudaStream_t) {
-  return cudaErrorNotSupported;
+namespace {
+
+constexpr int BM = 128;       // rows per tile = UMMA M
+constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 =
+//   1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10),
+// K-major A and B (bits 15, 16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGE_BYTES = 2 * BM * BK * 2 + 2 * BN * BK * 2;   // a_hi, a_lo, w_hi, w_lo
+  static constexpr int STAGES = (BN >= 256) ? 2 : ((BN >= 128) ? 3 : 4);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;            // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  const float* bias;
+  float* cf; int ldc;
+  __nv_bfloat16* chi; __nv_bfloat16* clo; int ldsp;
+  int M, N, K, act;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                   const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+                   EpiParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte aligned tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2; // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = p.N / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_ahi); tma_prefetch_desc(&map_alo); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate TMEM columns, publish the base address through smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(&map_ahi, &full_bar[stage], st, kb * BK, m0);
+          tma_load_2d(&map_alo, &full_bar[stage], st + BM * BK * 2, kb * BK, m0);
+          tma_load_2d(&map_whi, &full_bar[stage], st + 2 * BM * BK * 2, kb * BK, n0);
+          tma_load_2d(&map_wlo, &full_bar[stage], st + 2 * BM * BK * 2 + BN * BK * 2, kb * BK, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer (one thread) =====
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + BM * BK * 2, w_hi = st + 2 * BM * BK * 2, w_lo = w_hi + BN * BK * 2;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the 128-byte swizzle row
+            const uint64_t da_hi = make_desc_sw128(a_hi + koff), da_lo = make_desc_sw128(a_lo + koff);
+            const uint64_t db_hi = make_desc_sw128(w_hi + koff), db_lo = make_desc_sw128(w_lo + koff);
+            tc_mma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+            tc_mma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+          }
+          tc_commit(&empty_bar[stage]);                // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) tc_commit(&tmem_full[acc]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {  // ===== epilogue warps: TMEM -> registers -> global =====
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + row_in_tile;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_addr + c0, r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+            v[j] = apply_act_rt(x, p.act);
+          }
+          if (p.cf) {
+            float4* dst = reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.chi) {
+            uint4* dh = reinterpret_cast<uint4*>(p.chi + (size_t)row * p.ldsp + n0 + c0);
+            uint4* dl = reinterpret_cast<uint4*>(p.clo + (size_t)row * p.ldsp + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat16 h[8], l[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                h[e] = __float2bfloat16_rn(v[8 * j + e]);
+                l[e] = __float2bfloat16_rn(v[8 * j + e] - __bfloat162float(h[e]));
+              }
+              dh[j] = *reinterpret_cast<uint4*>(h);
+              dl[j] = *reinterpret_cast<uint4*>(l);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, cols, ld, box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int v : {k.rows, k.cols, k.ld, k.box_rows}) h = h * 1000003u ^ std::hash<int>()(v);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64], 128-byte swizzle.
+bool get_tensor_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static std::mutex mu;
+  MapKey key{ptr, rows, cols, ld, box_rows};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return true; }
+  auto enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return true;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+cudaError_t launch_bn(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda, const __nv_bfloat16* w_hi,
+                      const __nv_bfloat16* w_lo, int ldw, const EpiParams& p, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap mah, mal, mwh, mwl;
+  if (!get_tensor_map(a_hi, p.M, p.K, lda, BM, &mah) || !get_tensor_map(a_lo, p.M, p.K, lda, BM, &mal) ||
+      !get_tensor_map(w_hi, p.N, p.K, ldw, BN, &mwh) || !get_tensor_map(w_lo, p.N, p.K, ldw, BN, &mwl))
+    return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(linear_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  linear_umma_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(mah, mal, mwh, mwl, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda,
+                               const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int ldw, const float* bias,
+                               const LinearOut& out, int M, int N, int K, int act, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K % BK || N % 32 || (lda % 8) || (ldw % 8)) return cudaErrorInvalidValue;
+  if ((out.f32 && out.ldc % 4) || (out.hi && out.ld_split % 8)) return cudaErrorInvalidValue;
+  EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act};
+  if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
+  if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
+  return launch_bn<32>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
+}
+
 }  // namespace da
