@@ -17,10 +17,12 @@ thread_local std::string g_create_error;
 // launch-site tags for the built-in CUDA-event profiler
 enum Tag : int {
   TAG_HOIST_GEMM = 0, TAG_PROLOGUE, TAG_MLP2_GEMM, TAG_QKVS_GEMM_FIRST, TAG_QKVS_GEMM_MID, TAG_QKVS_GEMM_LAST,
-  TAG_ATTN_HIDDEN, TAG_ATTN_LAST, TAG_HEAD_GEMM, TAG_HEAD_FINAL, TAG_OTHER, TAG_COUNT
+  TAG_ATTN_HIDDEN, TAG_ATTN_LAST, TAG_HEAD_GEMM, TAG_HEAD_FINAL, TAG_OTHER, TAG_PACK_HIDDEN, TAG_PACK_LAST,
+  TAG_ATTN_DENSE_HIDDEN, TAG_ATTN_DENSE_LAST, TAG_COUNT
 };
 const char* kTagNames[TAG_COUNT] = {"hoist_gemm", "prologue", "mlp2_gemm", "qkvs_gemm_first", "qkvs_gemm_mid",
-                                    "qkvs_gemm_last", "attn_hidden", "attn_last", "head_gemm", "head_final", "other"};
+                                    "qkvs_gemm_last", "attn_hidden", "attn_last", "head_gemm", "head_final", "other",
+                                    "pack_hidden", "pack_last", "attn_dense_hidden", "attn_dense_last"};
 
 struct DevBuf {
   void* p = nullptr;
@@ -57,8 +59,11 @@ struct da_handle {
   std::vector<Linear> layer;
   DevBuf pos_w0, pos_b0, pos_w2, pos_b2, time_emb, w1pt_T, b1, headb_w, headb_b, headr_w, headr_b, virt_emb;
   // graph
-  CsrGraph csr;
+  CsrGraph csr;        // every edge (attn_mode = CSR)
+  DensePlan plan;      // bitmap tiles + residual CSR (attn_mode = AUTO)
+  bool use_plan = false;
   int num_real = 0, num_total = 0;
+  DevBuf qimg, kimg, vimg, dacc, dstats;
   // activations / workspace
   DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
   // split-bf16 operand planes for the tensor-core path
@@ -75,7 +80,8 @@ struct da_handle {
     return (int)DA_ERR_CUDA;
   }
   size_t workspace_bytes() const {
-    const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats,
+    const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats, &qimg, &kimg, &vimg,
+                           &dacc, &dstats,
                            &feats_sp_hi, &feats_sp_lo, &h_hi, &h_lo, &comb_hi, &comb_lo, &xa_hi, &xa_lo,
                            &xb_hi, &xb_lo, &r_hi, &r_lo};
     size_t s = 0;
@@ -186,9 +192,32 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
       DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
+    const bool dense = h->use_plan && h->plan.n_tiles > 0;
+    const CsrGraph& csr = h->use_plan ? h->plan.residual : h->csr;
+    if (dense) {  // bitmap edges on the tensor cores; the CSR kernel below continues with the residual edges
+      const int Cpad = (C + 15) / 16 * 16;
+      PackArgs pa{};
+      pa.qkvs = h->qkvs.as<float>(); pa.ld = 4 * HC; pa.node_slot = h->plan.node_slot; pa.n = Mr;
+      pa.H = c.heads; pa.C = C; pa.Cpad = Cpad;
+      pa.qimg = h->qimg.as<__nv_bfloat16>(); pa.kimg = h->kimg.as<__nv_bfloat16>(); pa.vimg = h->vimg.as<__nv_bfloat16>();
+      {
+        Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
+        DA_CK(launch_pack_images(pa, s), "pack images");
+      }
+      AttnDenseArgs da_{};
+      da_.qimg = pa.qimg; da_.kimg = pa.kimg; da_.vimg = pa.vimg;
+      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
+      da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
+      da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
+      {
+        Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
+        DA_CK(launch_attn_dense(da_, s), "dense attention");
+      }
+    }
     AttnCsrArgs a{};
     a.qkvs = h->qkvs.as<float>(); a.ld = 4 * HC;
-    a.rowptr = h->csr.rowptr; a.col = h->csr.col;
+    a.rowptr = csr.rowptr; a.col = csr.col;
+    if (dense) { a.init_acc = h->dacc.as<float>(); a.init_stats = h->dstats.as<float>(); a.init_slot = h->plan.node_slot; }
     a.H = c.heads; a.C = C;
     a.act = (!last && c.arch == DA_ARCH_TRANSFORMER) ? ACT_GELU : ACT_NONE;
     if (last) {
@@ -311,9 +340,10 @@ void da_destroy(da_handle* h) {
                    &h->headb_b, &h->headr_w, &h->headr_b, &h->virt_emb, &h->P, &h->hbuf, &h->combined, &h->qkvs,
                    &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
                    &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
-                   &h->xb_lo, &h->r_hi, &h->r_lo};
+                   &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->dacc, &h->dstats};
   for (auto* b : all) b->release();
   free_csr(&h->csr);
+  free_plan(&h->plan);
   delete h;
 }
 
@@ -456,16 +486,23 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
     return h->fail(DA_ERR_INVALID, "virtual rows need arch = EXOPHORMER and virt_ids");
   if (num_total > num_real && !h->weights_loaded)
     return h->fail(DA_ERR_MISSING, "load weights before da_set_graph when virtual nodes are used");
-  (void)batch;  // graph membership is only needed by the dense-tile attention planner
+  const da_config& c = h->cfg;
+  const int D = h->D, Hm = c.mlp_hidden, hid = c.hidden;
   const char* why = "";
-  cudaError_t ce = build_csr(edge_src, edge_dst, E, num_total, &h->csr, s, &why);
+  cudaError_t ce;
+  // dense tensor-core tiles need head dims that are multiples of 8 and small enough for shared memory
+  const int c_hid = hid / c.heads, c_last = D / c.heads;
+  const int cpad_max = ((c_hid > c_last ? c_hid : c_last) + 15) / 16 * 16;
+  h->use_plan = (c.attn_mode == DA_ATTN_AUTO) && batch != nullptr && (c_hid % 8 == 0) && (c_last % 8 == 0) && cpad_max <= 144;
+  free_csr(&h->csr);
+  free_plan(&h->plan);
+  if (h->use_plan) ce = build_dense_plan(edge_src, edge_dst, E, batch, num_real, num_total, &h->plan, s, &why);
+  else ce = build_csr(edge_src, edge_dst, E, num_total, &h->csr, s, &why);
   if (ce != cudaSuccess) {
     if (ce == cudaErrorInvalidValue && why[0]) return h->fail(DA_ERR_INVALID, why);
     return h->cuda_fail(ce, why);
   }
   h->num_real = num_real; h->num_total = num_total;
-  const da_config& c = h->cfg;
-  const int D = h->D, Hm = c.mlp_hidden, hid = c.hidden;
   const size_t Mt = num_total, Mr = num_real;
   const bool umma = use_umma(h);
 #define DA_CK(call) do { ce = (call); if (ce != cudaSuccess) return h->cuda_fail(ce, "da_set_graph alloc"); } while (0)
@@ -486,6 +523,18 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
     DA_CK(h->xa.ensure(Mt * hid * sizeof(float)));
     DA_CK(h->xb.ensure(Mt * hid * sizeof(float)));
     DA_CK(h->r.ensure(Mt * D * sizeof(float)));
+  }
+  if (h->use_plan && h->plan.n_tiles > 0) {
+    const size_t img = dense_image_elems(h->plan.n_tiles, c.heads, cpad_max) * sizeof(__nv_bfloat16);
+    const bool fresh = img > h->vimg.bytes;
+    DA_CK(h->qimg.ensure(img)); DA_CK(h->kimg.ensure(img)); DA_CK(h->vimg.ensure(img));
+    if (fresh || true) {  // padded rows / channels must read as finite zeros
+      DA_CK(cudaMemsetAsync(h->qimg.p, 0, h->qimg.bytes, s));
+      DA_CK(cudaMemsetAsync(h->kimg.p, 0, h->kimg.bytes, s));
+      DA_CK(cudaMemsetAsync(h->vimg.p, 0, h->vimg.bytes, s));
+    }
+    DA_CK(h->dacc.ensure(Mr * (size_t)(D > hid ? D : hid) * sizeof(float)));
+    DA_CK(h->dstats.ensure(Mr * (size_t)c.heads * 2 * sizeof(float)));
   }
   if (num_total > num_real) {  // virtual rows: constant embeddings appended after the real nodes (exophormer_gnn.py:169-178)
     const int nv = num_total - num_real;
@@ -574,9 +623,9 @@ int64_t da_launch_count(const da_handle* h) { return h ? h->launches : 0; }
 
 int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_edges, int32_t* n_dense_graphs) {
   if (!h || !h->graph_set) return DA_ERR_INVALID;
-  if (n_dense_edges) *n_dense_edges = 0;
-  if (n_csr_edges) *n_csr_edges = h->csr.E;
-  if (n_dense_graphs) *n_dense_graphs = 0;
+  if (n_dense_edges) *n_dense_edges = h->use_plan ? h->plan.n_dense_edges : 0;
+  if (n_csr_edges) *n_csr_edges = h->use_plan ? h->plan.residual.E : h->csr.E;
+  if (n_dense_graphs) *n_dense_graphs = h->use_plan ? h->plan.n_dense_graphs : 0;
   return DA_OK;
 }
 
@@ -658,6 +707,51 @@ int da_op_graph_attention(const float* qkvs, const int64_t* edge_src, const int6
   }
   cudaFree(scores); cudaFree(stats);
   free_csr(&g);
+  return rc;
+}
+
+int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
+                                const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
+                                void* stream) {
+  if (!qkvs || !y || !batch || n <= 0 || H <= 0 || C <= 0 || E < 0) return DA_ERR_INVALID;
+  const int Cpad = (C + 15) / 16 * 16;
+  if (C % 8 || Cpad > 144) return DA_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  DensePlan plan;
+  const char* why = "";
+  cudaError_t ce = build_dense_plan(edge_src, edge_dst, E, batch, n, n, &plan, s, &why);
+  if (ce != cudaSuccess) return ce == cudaErrorInvalidValue ? DA_ERR_INVALID : DA_ERR_CUDA;
+  if (n_dense_edges) *n_dense_edges = plan.n_dense_edges;
+  __nv_bfloat16 *qi = nullptr, *ki = nullptr, *vi = nullptr;
+  float *acc = nullptr, *st = nullptr;
+  int rc = DA_OK;
+  const size_t img = dense_image_elems(plan.n_tiles > 0 ? plan.n_tiles : 1, H, Cpad) * sizeof(__nv_bfloat16);
+  if (cudaMalloc(&qi, img) != cudaSuccess || cudaMalloc(&ki, img) != cudaSuccess || cudaMalloc(&vi, img) != cudaSuccess ||
+      cudaMalloc(&acc, sizeof(float) * (size_t)n * H * C) != cudaSuccess || cudaMalloc(&st, sizeof(float) * (size_t)n * H * 2) != cudaSuccess) {
+    rc = DA_ERR_CUDA;
+  } else {
+    cudaMemsetAsync(qi, 0, img, s); cudaMemsetAsync(ki, 0, img, s); cudaMemsetAsync(vi, 0, img, s);
+    ce = cudaSuccess;
+    if (plan.n_tiles > 0) {
+      PackArgs pa{qkvs, 4 * H * C, plan.node_slot, n, H, C, Cpad, qi, ki, vi};
+      ce = launch_pack_images(pa, s);
+      if (ce == cudaSuccess) {
+        AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st};
+        ce = launch_attn_dense(da_, s);
+      }
+    }
+    if (ce == cudaSuccess) {
+      AttnCsrArgs a{};
+      a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = plan.residual.rowptr; a.col = plan.residual.col; a.n_targets = n;
+      a.H = H; a.C = C; a.act = ACT_NONE; a.out.f32 = y; a.out.ldc = H * C;
+      if (plan.n_tiles > 0) { a.init_acc = acc; a.init_stats = st; a.init_slot = plan.node_slot; }
+      ce = launch_attn_csr(a, s);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (ce != cudaSuccess) rc = DA_ERR_CUDA;
+  }
+  cudaFree(qi); cudaFree(ki); cudaFree(vi); cudaFree(acc); cudaFree(st);
+  free_plan(&plan);
   return rc;
 }
 

@@ -24,8 +24,9 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
                 const int32_t* __restrict__ col, int n_targets, int H, int C, float scale,
                 const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                 __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
-                float* __restrict__ scores, float* __restrict__ stats) {
-  extern __shared__ float q_sm[];  // [WARPS_PER_CTA][C]
+                float* __restrict__ scores, float* __restrict__ stats, const float* __restrict__ init_acc,
+                const float* __restrict__ init_stats, const int32_t* __restrict__ init_slot) {
+  extern __shared__ __align__(16) float q_sm[];  // [WARPS_PER_CTA][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + warp;
   if (gw >= (long long)n_targets * H) return;  // whole warp exits together
@@ -44,6 +45,16 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
   float acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (init_slot != nullptr && init_slot[node] >= 0) {
+    // continue the online softmax the dense-tile kernel started on this node's bitmap edges
+    m = init_stats[((size_t)node * H + head) * 2 + 0];
+    l = init_stats[((size_t)node * H + head) * 2 + 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = lane + 32 * r;
+      if (c < C) acc[r] = init_acc[(size_t)node * HC + head * C + c];
+    }
+  }
 
   for (int base = beg; base < end; base += 32) {
     const int e = base + lane;
@@ -138,7 +149,7 @@ cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s) {
 #define DA_LAUNCH(RR)                                                                                       \
   attn_csr_kernel<RR><<<grid, WARPS_PER_CTA * 32, smem, s>>>(                                               \
       a.qkvs, a.ld, a.rowptr, a.col, a.n_targets, a.H, a.C, scale, a.resid, a.ld_resid, a.act, a.out.f32,   \
-      a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.scores, a.stats)
+      a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.scores, a.stats, a.init_acc, a.init_stats, a.init_slot)
   if (R <= 1) DA_LAUNCH(1);
   else if (R <= 2) DA_LAUNCH(2);
   else if (R <= 5) DA_LAUNCH(5);

@@ -1,0 +1,431 @@
+// Masked dense graph attention on tcgen05 tensor cores (attn_mode = DA_ATTN_AUTO).
+//
+// For the graphs selected by the planner (plan.cu) the TransformerConv message/softmax/aggregate
+// stage is evaluated as flash-style tiled attention restricted by the
+// graph's adjacency bitmap:
+//     S = Q K^T               128 targets x 64 sources per tile, fp32 accumulators in TMEM
+//     P = exp(scale*S - m)    only where bitmap(i, j) = 1 (online running max / sum per target row)
+//     O += P V                fp32 accumulator in TMEM, rescaled when the running max moves
+// Both products use the 3-pass split-bf16 scheme of gemm_umma.cu (hi*hi + hi*lo + lo*hi) so the
+// result stays within ~1e-5 of fp32.  The operands come from "images" written by pack_images_kernel:
+// per (tile, head) contiguous blocks already in the canonical no-swizzle K-major core-matrix layout
+// of tcgen05.mma (8 rows x 16 bytes per core matrix), so a K or V^T block is ONE cp.async.bulk.
+//
+// CTA = (128-row target tile, head).  Warp roles:
+//   warp 0     bulk-copy producer (Q image once, then K / V^T blocks through mbarrier rings)
+//   warp 1     TMEM allocation, single-thread tcgen05.mma issue (S_{j+1} is issued before P_j V_j
+//              so the tensor core works while the softmax warps are busy)
+//   warps 2-5  softmax: thread == target row (TMEM lane), so the row max / sum need no shuffles;
+//              two passes over the S tile in TMEM (max, then exp + P store), O correction in TMEM
+// The un-normalised O and the (m, l) statistics go to global memory; attn_csr.cu then continues the
+// same online softmax over the residual edges and applies skip / residual / activation.
+#include "common.cuh"
+
+namespace da {
+namespace {
+
+constexpr int TM = 128;   // targets per tile (UMMA M)
+constexpr int TS = 64;    // sources per block (UMMA N of S, K of PV)
+constexpr int NT = 192;
+constexpr int KST = 2;    // K ring depth
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// No-swizzle K-major operand descriptor: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// SBO = byte distance between 8-row groups, LBO = byte distance between the two 8-element k-chunks
+// of one UMMA_K = 16 step (cute::UMMA::SmemDescriptor, layout_type 0, version 1).
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+         (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- image layout ---------------------------------------------------------------------------------
+// Q image of (tile t, head h):   [plane 2][k-chunk Cpad/8][row 128][8]            bf16
+// K image of (block b, head h):  [plane 2][k-chunk Cpad/8][row 64][8]
+// V^T image of (block b, head h):[plane 2][src-chunk 8][channel Cpad][8 sources]
+__host__ __device__ inline size_t q_block_elems(int Cpad) { return (size_t)2 * TM * Cpad; }
+__host__ __device__ inline size_t kv_block_elems(int Cpad) { return (size_t)2 * TS * Cpad; }
+
+__global__ void pack_images_kernel(PackArgs a) {
+  // one warp = 32 consecutive nodes (lane = node) x a strided set of (part, head, 8-channel chunk)
+  const int lane = threadIdx.x & 31;
+  const int node = blockIdx.x * 32 + lane;
+  const int HC = a.H * a.C;
+  const int chunks = a.Cpad / 8;                 // per head, including zero padding up to Cpad
+  const int items_per_part = a.H * chunks;
+  const int warp_in_cta = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const int slot = node < a.n ? a.node_slot[node] : -1;
+  if (slot < 0) return;
+  const int tile = slot >> 7, r = slot & 127;
+  const int blk = slot >> 6, rb = slot & 63;
+  const float* row = a.qkvs + (size_t)node * a.ld;
+  for (int it = warp_in_cta + blockIdx.y * warps; it < 3 * items_per_part; it += warps * gridDim.y) {
+    const int part = it / items_per_part, rem = it % items_per_part;
+    const int h = rem / chunks, ch = rem % chunks;
+    const int c = ch * 8;
+    __nv_bfloat16 hi[8], lo[8];
+    if (c < a.C) {  // C % 8 == 0: a chunk is entirely data or entirely padding
+      const float* src = row + part * HC + h * a.C + c;
+      const float4 v0 = *reinterpret_cast<const float4*>(src);
+      const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hi[e] = __float2bfloat16_rn(v[e]);
+        lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { hi[e] = __float2bfloat16_rn(0.f); lo[e] = hi[e]; }
+    }
+    if (part == 0) {
+      __nv_bfloat16* base = a.qimg + ((size_t)tile * a.H + h) * q_block_elems(a.Cpad);
+      const size_t off = (size_t)ch * (TM * 8) + (size_t)r * 8;
+      *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(base + (size_t)TM * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
+    } else if (part == 1) {
+      __nv_bfloat16* base = a.kimg + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
+      const size_t off = (size_t)ch * (TS * 8) + (size_t)rb * 8;
+      *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(base + (size_t)TS * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
+    } else {
+      __nv_bfloat16* base = a.vimg + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
+      const size_t off0 = (size_t)(rb >> 3) * (a.Cpad * 8) + (rb & 7);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const size_t off = off0 + (size_t)(c + e) * 8;
+        base[off] = hi[e];
+        base[(size_t)TS * a.Cpad + off] = lo[e];
+      }
+    }
+  }
+}
+
+struct DenseSmem {
+  uint64_t q_full;
+  uint64_t k_full[KST], k_empty[KST];
+  uint64_t v_full, v_empty;
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_full, pv_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NT)
+attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int Cpad = a.Cpad;
+  const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2, p_plane = TM * TS * 2;  // bytes
+  uint8_t* q_sm = smem;                                   // 2 planes
+  uint8_t* k_sm = q_sm + 2 * q_plane;                     // KST stages x 2 planes
+  uint8_t* v_sm = k_sm + KST * 2 * kv_plane;              // 1 stage x 2 planes
+  uint8_t* p_sm = v_sm + 2 * kv_plane;                    // 2 planes
+  DenseSmem* sh = reinterpret_cast<DenseSmem*>(p_sm + 2 * p_plane);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / a.H, head = blockIdx.x % a.H;
+  const TileInfo ti = a.tiles[tile];
+  const int nblk = (ti.gn + TS - 1) / TS;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sh->q_full, 1);
+    for (int i = 0; i < KST; ++i) { mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1); }
+    mbar_init(&sh->v_full, 1); mbar_init(&sh->v_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->s_empty[i], 4); }
+    mbar_init(&sh->p_full, 4); mbar_init(&sh->pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const uint32_t tmem_s = tmem_base;             // 2 x TS columns
+  const uint32_t tmem_o = tmem_base + 2 * TS;    // Cpad columns
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== bulk-copy producer =====
+      const __nv_bfloat16* qsrc = a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cpad);
+      mbar_expect_tx(&sh->q_full, 2 * q_plane);
+      bulk_load(q_sm, qsrc, 2 * q_plane, &sh->q_full);
+      uint32_t kph = 0, vph = 0;
+      int ks = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const size_t boff = ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad);
+        mbar_wait(&sh->k_empty[ks], kph ^ 1);
+        mbar_expect_tx(&sh->k_full[ks], 2 * kv_plane);
+        bulk_load(k_sm + ks * 2 * kv_plane, a.kimg + boff, 2 * kv_plane, &sh->k_full[ks]);
+        if (++ks == KST) { ks = 0; kph ^= 1; }
+        mbar_wait(&sh->v_empty, vph ^ 1);
+        mbar_expect_tx(&sh->v_full, 2 * kv_plane);
+        bulk_load(v_sm, a.vimg + boff, 2 * kv_plane, &sh->v_full);
+        vph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad);
+      const uint32_t q_hi = smem_u32(q_sm), q_lo = q_hi + q_plane;
+      const uint32_t p_hi = smem_u32(p_sm), p_lo = p_hi + p_plane;
+      const uint32_t v_hi = smem_u32(v_sm), v_lo = v_hi + kv_plane;
+      const int ksteps = Cpad / 16;
+      auto issue_s = [&](int j, int ks) {
+        const uint32_t k_hi = smem_u32(k_sm + ks * 2 * kv_plane), k_lo = k_hi + kv_plane;
+        const uint32_t d = tmem_s + (uint32_t)((j & 1) * TS);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          // one k-step = 16 channels = 2 chunks; Q chunk stride TM*16 B, K chunk stride TS*16 B
+          const uint64_t aq_hi = make_desc_nosw(q_hi + kk * 2 * (TM * 16), TM * 16, 128);
+          const uint64_t aq_lo = make_desc_nosw(q_lo + kk * 2 * (TM * 16), TM * 16, 128);
+          const uint64_t bk_hi = make_desc_nosw(k_hi + kk * 2 * (TS * 16), TS * 16, 128);
+          const uint64_t bk_lo = make_desc_nosw(k_lo + kk * 2 * (TS * 16), TS * 16, 128);
+          tc_mma_bf16(d, aq_hi, bk_hi, idesc_s, kk ? 1u : 0u);
+          tc_mma_bf16(d, aq_hi, bk_lo, idesc_s, 1u);
+          tc_mma_bf16(d, aq_lo, bk_hi, idesc_s, 1u);
+        }
+      };
+      mbar_wait(&sh->q_full, 0);
+      uint32_t kph = 0;
+      int ks = 0;
+      // S_0
+      mbar_wait(&sh->k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      tc_commit(&sh->s_full[0]);
+      tc_commit(&sh->k_empty[0]);
+      ks = 1 % KST; if (ks == 0) kph ^= 1;
+      uint32_t sph[2] = {0, 0};  // parity of the NEXT s_empty wait per buffer
+      for (int j = 0; j < nblk; ++j) {
+        if (j + 1 < nblk) {
+          const int b = (j + 1) & 1;
+          mbar_wait(&sh->k_full[ks], kph);
+          if (j + 1 >= 2) { mbar_wait(&sh->s_empty[b], sph[b]); sph[b] ^= 1; }  // softmax released this S buffer
+          tc_fence_after();
+          issue_s(j + 1, ks);
+          tc_commit(&sh->s_full[b]);
+          tc_commit(&sh->k_empty[ks]);
+          if (++ks == KST) { ks = 0; kph ^= 1; }
+        }
+        mbar_wait(&sh->p_full, j & 1);   // P_j in smem, O corrected
+        mbar_wait(&sh->v_full, j & 1);
+        tc_fence_after();
+        for (int kk = 0; kk < TS / 16; ++kk) {
+          const uint64_t ap_hi = make_desc_nosw(p_hi + kk * 2 * (TM * 16), TM * 16, 128);
+          const uint64_t ap_lo = make_desc_nosw(p_lo + kk * 2 * (TM * 16), TM * 16, 128);
+          const uint64_t bv_hi = make_desc_nosw(v_hi + kk * 2 * (Cpad * 16), Cpad * 16, 128);
+          const uint64_t bv_lo = make_desc_nosw(v_lo + kk * 2 * (Cpad * 16), Cpad * 16, 128);
+          tc_mma_bf16(tmem_o, ap_hi, bv_hi, idesc_o, (j | kk) ? 1u : 0u);
+          tc_mma_bf16(tmem_o, ap_hi, bv_lo, idesc_o, 1u);
+          tc_mma_bf16(tmem_o, ap_lo, bv_hi, idesc_o, 1u);
+        }
+        tc_commit(&sh->pv_done);
+        tc_commit(&sh->v_empty);
+      }
+    }
+  } else {  // ===== softmax warps =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;           // row in tile == TMEM lane
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool row_valid = r < ti.rows;
+    const float c_log2 = 1.4426950408889634f / sqrtf((float)a.C);  // scale * log2(e)
+    const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
+    float m = -INFINITY, l = 0.f;  // m in raw-score units
+    uint8_t* p_hi = p_sm;
+    uint8_t* p_lo = p_sm + p_plane;
+    for (int j = 0; j < nblk; ++j) {
+      const int b = j & 1;
+      const uint2 bits = row_valid ? *reinterpret_cast<const uint2*>(bm_row + j * 2) : make_uint2(0u, 0u);
+      mbar_wait(&sh->s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
+      // pass 1: row max over the unmasked sources of this block
+      float m_new = m;
+#pragma unroll
+      for (int c0 = 0; c0 < TS; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(s_addr + c0, v);
+        tmem_ld_wait();
+        const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if ((w >> e) & 1u) m_new = fmaxf(m_new, __uint_as_float(v[e]));
+      }
+      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * c_log2);
+      const float m_sub = (m_new == -INFINITY) ? 0.f : m_new * c_log2;
+      if (j > 0) {
+        mbar_wait(&sh->pv_done, (j - 1) & 1);   // P buffer free, O holds blocks < j
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // O correction (rows whose running max moved)
+          for (int c0 = 0; c0 < Cpad; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_o + lane_off + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st16(tmem_o + lane_off + c0, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: P = exp2(s*c - m*c) on the bitmap, split to bf16 hi/lo, store in the A-operand layout
+      float lsum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < TS; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(s_addr + c0, v);
+        tmem_ld_wait();
+        const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
+        __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float p = 0.f;
+          if ((w >> e) & 1u) p = exp2f(fmaf(__uint_as_float(v[e]), c_log2, -m_sub));
+          lsum += p;
+          hi[e] = __float2bfloat16_rn(p);
+          lo[e] = __float2bfloat16_rn(p - __bfloat162float(hi[e]));
+        }
+        // source chunk sc = (c0 / 8) and sc + 1: 16 bytes each at [sc][r][8]
+        const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(p_hi + o0) = *reinterpret_cast<uint4*>(&hi[0]);
+        *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = *reinterpret_cast<uint4*>(&hi[8]);
+        *reinterpret_cast<uint4*>(p_lo + o0) = *reinterpret_cast<uint4*>(&lo[0]);
+        *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = *reinterpret_cast<uint4*>(&lo[8]);
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy P stores -> async proxy (MMA)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&sh->p_full); mbar_arrive(&sh->s_empty[b]); }
+    }
+    // epilogue: un-normalised O and (m, l) to global
+    mbar_wait(&sh->pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    const int node = ti.node0 + r;
+    const int HC = a.H * a.C;
+    for (int c0 = 0; c0 < Cpad; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_o + lane_off + c0, v);
+      tmem_ld_wait();
+      if (row_valid) {
+        float* dst = a.acc + (size_t)node * HC + head * a.C + c0;
+        if (c0 + 16 <= a.C && (a.C & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4)
+            *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        } else {
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < a.C) dst[e] = __uint_as_float(v[e]);
+        }
+      }
+    }
+    if (row_valid) {
+      float* st = a.stats + ((size_t)node * a.H + head) * 2;
+      st[0] = (m == -INFINITY) ? -INFINITY : m / sqrtf((float)a.C);  // natural-log units of the scaled score
+      st[1] = l;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
+  if (a.n <= 0) return cudaSuccess;
+  if ((a.C % 8) || (a.ld % 4)) return cudaErrorInvalidValue;
+  if (a.Cpad % 16 || a.Cpad < a.C) return cudaErrorInvalidValue;
+  const int groups = 3 * a.H * a.Cpad / 8;
+  int gy = (groups + 8 * 8 - 1) / (8 * 8);  // ~8 items per warp
+  if (gy < 1) gy = 1;
+  dim3 grid((a.n + 31) / 32, gy);
+  pack_images_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
+  if (a.n_tiles <= 0) return cudaSuccess;
+  const int Cpad = a.Cpad;
+  if (Cpad % 16 || Cpad > 256 || Cpad < 16) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)2 * TM * Cpad * 2 + (size_t)(KST + 1) * 2 * TS * Cpad * 2 + (size_t)2 * TM * TS * 2 + sizeof(DenseSmem) + 128;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  int need = 2 * TS + Cpad, cols = 32;
+  while (cols < need) cols <<= 1;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  attn_dense_kernel<<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
+  return cudaGetLastError();
+}
+
+}  // namespace da

@@ -75,6 +75,10 @@ struct AttnCsrArgs {
   LinearOut out;         // [n_targets, H*C]
   float* scores;         // optional [E, H] raw scaled scores at CSR positions (for alpha output)
   float* stats;          // optional [n_targets, H, 2] (max, sum) for alpha output
+  // continuation of an online softmax started by the dense-tile kernel (null = start fresh):
+  const float* init_acc;      // [n, H*C] un-normalised accumulator
+  const float* init_stats;    // [n, H, 2] (m, l)
+  const int32_t* init_slot;   // [n] >= 0 where the init state is valid
 };
 cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s);
 
@@ -136,5 +140,65 @@ void free_csr(CsrGraph* g);
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);
+
+}  // namespace da
+
+// ---------------------------------------------------------------------------------------------
+// Dense-tile attention plan (attn_mode = DA_ATTN_AUTO).
+//
+// Graphs that are large and dense enough are processed as masked dense attention on the tensor
+// cores: their nodes are grouped in 128-row target tiles / 64-row source blocks, their in-graph
+// edges (multiplicity one) become an adjacency bitmap, and Q / K / V^T are repacked per layer into
+// split-bf16 "operand images" (the exact shared-memory layout tcgen05.mma consumes, so a tile is
+// one contiguous bulk copy).  Every other edge (virtual-node wiring, duplicates, cross-graph
+// edges, small or very sparse graphs) stays in a residual CSR that continues the same online
+// softmax, so the union is exactly the reference's segment softmax over ALL in-edges.
+// ---------------------------------------------------------------------------------------------
+namespace da {
+
+struct TileInfo {
+  int32_t node0;     // first global node id of this 128-row target tile
+  int32_t rows;      // valid rows (<= 128)
+  int32_t gblock0;   // global index of the graph's first 64-row source block
+  int32_t gn;        // nodes in the graph
+  int32_t bm_words;  // uint32 words per bitmap row of this graph (multiple of 2)
+  int32_t row0;      // local index (within the graph) of the tile's first row
+  int64_t bm_off;    // word offset of the graph's bitmap
+};
+
+struct DensePlan {
+  int n_tiles = 0;           // 128-row tiles (image rows = n_tiles * 128)
+  int n_dense_graphs = 0;
+  int64_t n_dense_edges = 0;
+  TileInfo* tiles = nullptr;       // [n_tiles] device
+  int32_t* node_slot = nullptr;    // [n_total] device: image row (tile * 128 + r) of each node, -1 if not dense
+  uint32_t* bitmap = nullptr;      // device
+  size_t bitmap_words = 0;
+  CsrGraph residual;               // CSR by target over the edges not in the bitmap
+};
+void free_plan(DensePlan* p);
+// Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.
+cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
+                             int num_total, DensePlan* plan, cudaStream_t s, const char** err);
+
+// fp32 [Q | K | V | skip] rows -> split-bf16 operand images of the dense tiles
+struct PackArgs {
+  const float* qkvs; int ld;       // [n, 4*H*C]
+  const int32_t* node_slot; int n;
+  int H, C, Cpad;
+  __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
+};
+cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s);
+
+struct AttnDenseArgs {
+  const __nv_bfloat16* qimg; const __nv_bfloat16* kimg; const __nv_bfloat16* vimg;
+  const TileInfo* tiles; int n_tiles;
+  const uint32_t* bitmap;
+  int H, C, Cpad;
+  float* acc;    // [n, H*C] un-normalised sum_e exp(a_e - m) v_e of the bitmap edges
+  float* stats;  // [n, H, 2] (m, l) of the bitmap edges, natural-log units
+};
+cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s);
+size_t dense_image_elems(int n_tiles, int H, int Cpad);  // elements of ONE of the q / k / v image buffers
 
 }  // namespace da

@@ -1,0 +1,200 @@
+// Dense-tile attention planner (runs once per batch inside da_set_graph).
+//
+// Splits the edge multiset of the PyG-style batch into
+//   (1) per-graph adjacency bitmaps for graphs that are big and dense enough to be worth running
+//       as masked dense attention on the tensor cores, and
+//   (2) a residual CSR (duplicates, virtual-node wiring, cross-graph edges, small / sparse graphs).
+// The two parts partition the multiset exactly, so dense + residual == the reference's segment
+// softmax over all in-edges (exophormer_gnn.py:198-200 wiring included).
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace da {
+namespace {
+
+constexpr int MIN_DENSE_NODES = 48;   // smaller graphs stay on the CSR warp kernel
+constexpr int DENSITY_DIV = 16;       // dense if in-graph edges >= n^2 / 16
+
+__global__ void count_ingraph_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                           const int64_t* __restrict__ batch, int num_real,
+                                           unsigned long long* __restrict__ cnt) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t s = src[e], d = dst[e];
+  if (s < 0 || d < 0 || s >= num_real || d >= num_real) return;
+  int64_t g = batch[d];
+  if (batch[s] == g) atomicAdd(&cnt[g], 1ull);
+}
+
+// flag[e] = 1 -> residual edge (goes to the CSR), 0 -> recorded in the bitmap
+__global__ void classify_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
+                                      const int64_t* __restrict__ batch, int num_real,
+                                      const int32_t* __restrict__ g_node0, const int64_t* __restrict__ g_bm_off,
+                                      const int32_t* __restrict__ g_bm_words, uint32_t* __restrict__ bitmap,
+                                      uint8_t* __restrict__ flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t s = src[e], d = dst[e];
+  uint8_t residual = 1;
+  if (s >= 0 && d >= 0 && s < num_real && d < num_real) {
+    int64_t g = batch[d];
+    if (batch[s] == g && g_bm_off[g] >= 0) {
+      const int i = (int)(d - g_node0[g]), j = (int)(s - g_node0[g]);
+      uint32_t* w = bitmap + g_bm_off[g] + (int64_t)i * g_bm_words[g] + (j >> 5);
+      const uint32_t bit = 1u << (j & 31);
+      const uint32_t old = atomicOr(w, bit);
+      residual = (old & bit) ? 1 : 0;  // a duplicate of an edge already in the bitmap stays in the CSR
+    }
+  }
+  flag[e] = residual;
+}
+
+__global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, int32_t* __restrict__ bad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < n && batch[i + 1] < batch[i]) atomicExch(bad, 1);
+  if (i < n && batch[i] < 0) atomicExch(bad, 1);
+}
+
+}  // namespace
+
+void free_plan(DensePlan* p) {
+  if (!p) return;
+  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap);
+  free_csr(&p->residual);
+  *p = DensePlan();
+}
+
+size_t dense_image_elems(int n_tiles, int H, int Cpad) { return (size_t)n_tiles * 128 * H * Cpad * 2; }
+
+cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
+                             int num_total, DensePlan* plan, cudaStream_t s, const char** err) {
+  *err = "";
+  free_plan(plan);
+  cudaError_t ce = cudaSuccess;
+#define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
+  std::vector<int64_t> hbatch(num_real);
+  std::vector<unsigned long long> hcnt;
+  std::vector<int32_t> g_node0, g_n, g_bm_words, node_slot(num_total, -1);
+  std::vector<int64_t> g_bm_off;
+  std::vector<TileInfo> tiles;
+  unsigned long long* dcnt = nullptr;
+  int32_t *d_g_node0 = nullptr, *d_g_bm_words = nullptr, *d_bad = nullptr;
+  int64_t *d_g_bm_off = nullptr, *res_src = nullptr, *res_dst = nullptr, *d_nsel = nullptr;
+  uint8_t* flag = nullptr;
+  void* tmp = nullptr;
+  size_t tmp_bytes = 0, tb2 = 0;
+  int32_t bad_h = 0;
+  int64_t nsel = 0, n_res = 0;
+  int B = 0;
+  size_t words = 0;
+  int block64 = 0;
+
+  DA_TRY(cudaMalloc(&d_bad, sizeof(int32_t)));
+  DA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), s));
+  check_sorted_kernel<<<(num_real + 255) / 256, 256, 0, s>>>(batch, num_real, d_bad);
+  DA_TRY(cudaGetLastError());
+  DA_TRY(cudaMemcpyAsync(hbatch.data(), batch, sizeof(int64_t) * num_real, cudaMemcpyDeviceToHost, s));
+  DA_TRY(cudaMemcpyAsync(&bad_h, d_bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DA_TRY(cudaStreamSynchronize(s));
+  if (bad_h) {  // not PyG collation order: no dense graphs, everything through the CSR
+    B = 0;
+  } else {
+    B = (int)hbatch[num_real - 1] + 1;
+  }
+  g_node0.assign(B, 0); g_n.assign(B, 0); g_bm_words.assign(B, 0); g_bm_off.assign(B, -1);
+  for (int i = 0; i < num_real && B > 0; ++i) g_n[hbatch[i]]++;
+  for (int g = 1; g < B; ++g) g_node0[g] = g_node0[g - 1] + g_n[g - 1];
+  if (B > 0 && E > 0) {
+    DA_TRY(cudaMalloc(&dcnt, sizeof(unsigned long long) * B));
+    DA_TRY(cudaMemsetAsync(dcnt, 0, sizeof(unsigned long long) * B, s));
+    count_ingraph_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, dcnt);
+    DA_TRY(cudaGetLastError());
+    hcnt.resize(B);
+    DA_TRY(cudaMemcpyAsync(hcnt.data(), dcnt, sizeof(unsigned long long) * B, cudaMemcpyDeviceToHost, s));
+    DA_TRY(cudaStreamSynchronize(s));
+  } else {
+    hcnt.assign(B, 0);
+  }
+  // host decisions: which graphs go dense, tile table, bitmap offsets
+  for (int g = 0; g < B; ++g) {
+    const long long n = g_n[g];
+    if (n < MIN_DENSE_NODES || (long long)hcnt[g] * DENSITY_DIV < n * n) continue;
+    const int ntile = (int)((n + 127) / 128);
+    const int nblk64 = (int)((n + 63) / 64);
+    g_bm_words[g] = nblk64 * 2;
+    g_bm_off[g] = (int64_t)words;
+    words += (size_t)ntile * 128 * g_bm_words[g];
+    for (int t = 0; t < ntile; ++t) {
+      TileInfo ti;
+      ti.node0 = g_node0[g] + t * 128;
+      ti.rows = (int)std::min<long long>(128, n - t * 128);
+      ti.gblock0 = block64;
+      ti.gn = (int)n;
+      ti.bm_words = g_bm_words[g];
+      ti.row0 = t * 128;
+      ti.bm_off = g_bm_off[g];
+      const int tile_idx = (int)tiles.size();
+      for (int r = 0; r < ti.rows; ++r) node_slot[ti.node0 + r] = tile_idx * 128 + r;
+      tiles.push_back(ti);
+    }
+    block64 += ntile * 2;  // source blocks are laid out at image-row granularity: 2 per 128-row tile
+    plan->n_dense_graphs++;
+    plan->n_dense_edges += 0;
+  }
+  plan->n_tiles = (int)tiles.size();
+  plan->bitmap_words = words;
+  DA_TRY(cudaMalloc(&plan->node_slot, sizeof(int32_t) * (size_t)num_total));
+  DA_TRY(cudaMemcpyAsync(plan->node_slot, node_slot.data(), sizeof(int32_t) * (size_t)num_total, cudaMemcpyHostToDevice, s));
+  if (plan->n_tiles > 0) {
+    DA_TRY(cudaMalloc(&plan->tiles, sizeof(TileInfo) * tiles.size()));
+    DA_TRY(cudaMemcpyAsync(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, s));
+    DA_TRY(cudaMalloc(&plan->bitmap, sizeof(uint32_t) * words));
+    DA_TRY(cudaMemsetAsync(plan->bitmap, 0, sizeof(uint32_t) * words, s));
+    DA_TRY(cudaMalloc(&d_g_node0, sizeof(int32_t) * B));
+    DA_TRY(cudaMalloc(&d_g_bm_words, sizeof(int32_t) * B));
+    DA_TRY(cudaMalloc(&d_g_bm_off, sizeof(int64_t) * B));
+    DA_TRY(cudaMemcpyAsync(d_g_node0, g_node0.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    DA_TRY(cudaMemcpyAsync(d_g_bm_words, g_bm_words.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    DA_TRY(cudaMemcpyAsync(d_g_bm_off, g_bm_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
+  }
+  if (plan->n_tiles > 0 && E > 0) {
+    DA_TRY(cudaMalloc(&flag, (size_t)E));
+    classify_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, d_g_node0, d_g_bm_off,
+                                                                     d_g_bm_words, plan->bitmap, flag);
+    DA_TRY(cudaGetLastError());
+    DA_TRY(cudaMalloc(&res_src, sizeof(int64_t) * (size_t)E));
+    DA_TRY(cudaMalloc(&res_dst, sizeof(int64_t) * (size_t)E));
+    DA_TRY(cudaMalloc(&d_nsel, sizeof(int64_t)));
+    DA_TRY(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, src, flag, res_src, d_nsel, (int)E, s));
+    DA_TRY(cub::DeviceSelect::Flagged(nullptr, tb2, dst, flag, res_dst, d_nsel, (int)E, s));
+    if (tb2 > tmp_bytes) tmp_bytes = tb2;
+    DA_TRY(cudaMalloc(&tmp, tmp_bytes));
+    DA_TRY(cub::DeviceSelect::Flagged(tmp, tmp_bytes, src, flag, res_src, d_nsel, (int)E, s));
+    DA_TRY(cub::DeviceSelect::Flagged(tmp, tmp_bytes, dst, flag, res_dst, d_nsel, (int)E, s));
+    DA_TRY(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    DA_TRY(cudaStreamSynchronize(s));
+    n_res = nsel;
+    plan->n_dense_edges = E - n_res;
+    ce = build_csr(res_src, res_dst, n_res, num_total, &plan->residual, s, err);
+    if (ce != cudaSuccess) goto fail;
+  } else {
+    plan->n_dense_edges = 0;
+    ce = build_csr(src, dst, E, num_total, &plan->residual, s, err);
+    if (ce != cudaSuccess) goto fail;
+  }
+  DA_TRY(cudaStreamSynchronize(s));
+  cudaFree(dcnt); cudaFree(d_g_node0); cudaFree(d_g_bm_words); cudaFree(d_bad); cudaFree(d_g_bm_off);
+  cudaFree(res_src); cudaFree(res_dst); cudaFree(d_nsel); cudaFree(flag); cudaFree(tmp);
+  return cudaSuccess;
+fail:
+  cudaFree(dcnt); cudaFree(d_g_node0); cudaFree(d_g_bm_words); cudaFree(d_bad); cudaFree(d_g_bm_off);
+  cudaFree(res_src); cudaFree(res_dst); cudaFree(d_nsel); cudaFree(flag); cudaFree(tmp);
+  free_plan(plan);
+  return ce;
+#undef DA_TRY
+}
+
+}  // namespace da

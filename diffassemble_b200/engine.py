@@ -212,3 +212,22 @@ def op_graph_attention(qkvs, edge_index, heads, return_alpha=False):
     if st != _cabi.DA_OK:
         raise DiffAssembleError(st, "da_op_graph_attention failed")
     return (y, alpha) if return_alpha else y
+
+
+def op_graph_attention_dense(qkvs, edge_index, batch, heads):
+    """Tensor-core dense-tile path + residual CSR; returns ``(y, n_dense_edges)``."""
+    lib = _cabi.load_library()
+    _require_cuda(qkvs, "qkvs")
+    qkvs = qkvs.float().contiguous()
+    n = qkvs.shape[0]
+    HC = qkvs.shape[1] // 4
+    ei = edge_index.to(device=qkvs.device, dtype=torch.int64).contiguous()
+    b = batch.to(device=qkvs.device, dtype=torch.int64).contiguous()
+    y = torch.empty((n, HC), dtype=torch.float32, device=qkvs.device)
+    nd = C.c_int64(0)
+    with torch.cuda.device(qkvs.device):
+        st = lib.da_op_graph_attention_dense(_ptr(qkvs), _ptr(ei[0]), _ptr(ei[1]), ei.shape[1], _ptr(b), n, heads,
+                                             HC // heads, _ptr(y), C.byref(nd), _stream(qkvs.device))
+    if st != _cabi.DA_OK:
+        raise DiffAssembleError(st, "da_op_graph_attention_dense failed")
+    return y, nd.value

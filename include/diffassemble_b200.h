@@ -197,6 +197,14 @@ int da_op_graph_attention(const float* qkvs, const int64_t* edge_src, const int6
                           int64_t E, int32_t n, int32_t H, int32_t C, float* y, float* alpha,
                           void* stream);
 
+/* Same stage through the tensor-core dense-tile path (DA_ATTN_AUTO): `batch` (int64 [n], PyG
+ * collation order) selects the per-graph bitmap tiles; edges the bitmap cannot hold (duplicates,
+ * cross-graph, small or sparse graphs) run through the residual CSR.  *n_dense_edges (optional)
+ * receives how many edges took the tensor-core path. */
+int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst,
+                                int64_t E, const int64_t* batch, int32_t n, int32_t H, int32_t C,
+                                float* y, int64_t* n_dense_edges, void* stream);
+
 int da_abi_version(void);
 
 #ifdef __cplusplus

@@ -66,6 +66,30 @@ def test_op_graph_attention(n, H, C, kind):
         assert rel_err(al, alpha) < 1e-5
 
 
+@pytest.mark.parametrize("sizes,H,C,kind", [
+    ([200], 8, 32, "dense"), ([130], 8, 32, "expander"), ([100, 150], 8, 144, "expander"), ([64, 64, 300], 4, 24, "dense"),
+    ([900], 8, 32, "expander"), ([257, 20, 128], 8, 32, "mixed"), ([70, 90], 2, 144, "mixed")])
+def test_op_graph_attention_dense(sizes, H, C, kind):
+    """Tensor-core bitmap tiles + residual CSR == the edge-list formulation on the whole multiset."""
+    from diffassemble_b200 import op_graph_attention_dense
+    from oracle.transformer_conv import segment_softmax
+
+    n = sum(sizes)
+    g = torch.Generator().manual_seed(n + C)
+    qkvs = torch.randn(n, 4 * H * C, generator=g)
+    ei, batch = synth_graph_batch(sizes, kind="dense" if kind == "dense" else "expander", degree="60%")
+    if kind == "mixed":  # duplicates, cross-graph edges and self loops on top of the in-graph edges
+        extra = torch.randint(0, n, (2, 3 * n), generator=g)
+        ei = torch.cat([ei, extra, ei[:, :50]], 1)
+    q, k, v, s = [t.reshape(n, H, C) for t in qkvs.double().split(H * C, dim=1)]
+    a = (q[ei[1]] * k[ei[0]]).sum(-1) / C ** 0.5
+    alpha = segment_softmax(a, ei[1], n)
+    ref = torch.zeros(n, H, C, dtype=torch.float64).index_add_(0, ei[1], v[ei[0]] * alpha[..., None]) + s
+    y, n_dense = op_graph_attention_dense(qkvs.to(DEV), ei.to(DEV), batch.to(DEV), H)
+    assert n_dense > 0.5 * ei.shape[1] * (max(sizes) >= 48)
+    assert rel_err(y, ref.reshape(n, H * C)) < 2e-5
+
+
 # ---- model level, against the golden fixtures ------------------------------------------------------
 @pytest.mark.parametrize("mode", GEMM_MODES)
 @pytest.mark.parametrize("name", ["c1_dense36_ddpm", "dense_ragged_ddim", "exph_2x64_ddim"])
@@ -142,10 +166,11 @@ def test_golden_3d(mode):
 
 
 # ---- BASELINE configs against the live oracle ------------------------------------------------------
+@pytest.mark.parametrize("attn", ["csr", "auto"])
 @pytest.mark.parametrize("mode", GEMM_MODES)
-def test_c2_12x12_dense_ddpm_steps(mode):
+def test_c2_12x12_dense_ddpm_steps(mode, attn):
     """configs[1]: 144-node dense graph, DDPM eps-prediction, T=300: teacher-forced steps."""
-    ref, mod = make_pair_2d(seed=1, steps=300, sampling="DDPM", gemm_mode=mode)
+    ref, mod = make_pair_2d(seed=1, steps=300, sampling="DDPM", gemm_mode=mode, attn_mode=attn)
     mod = mod.to(DEV)
     ei, batch = synth_graph_batch([144])
     g = torch.Generator().manual_seed(0)
@@ -162,12 +187,13 @@ def test_c2_12x12_dense_ddpm_steps(mode):
         x = want  # teacher forcing on the oracle's trajectory
 
 
+@pytest.mark.parametrize("attn", ["csr", "auto"])
 @pytest.mark.parametrize("mode", GEMM_MODES)
 @pytest.mark.parametrize("V", [0, 8])
-def test_c3_shape_exphander_small_batch(mode, V):
+def test_c3_shape_exphander_small_batch(mode, V, attn):
     """configs[2] at oracle-sized scale: 2 x 100-node Exphander 60% graphs, exophormer, DDIM x0."""
     ref, mod = make_pair_2d(seed=2, steps=300, sampling="DDIM", architecture="exophormer", virt_nodes=V,
-                            model_mean_type="START_X", inference_ratio=10, gemm_mode=mode)
+                            model_mean_type="START_X", inference_ratio=10, gemm_mode=mode, attn_mode=attn)
     mod = mod.to(DEV)
     ei, batch = synth_graph_batch([100, 100], kind="expander", degree="60%")
     M = 200
@@ -206,6 +232,13 @@ def test_full_size_900_node_graph_properties():
     out_p = mods["fp32"].forward_with_feats(x[perm], t, None, inv[ei], feats[perm], batch)
     assert rel_err(out_p, base[perm]) < 1e-5
     assert rel_err(mods["bf16x3"].forward_with_feats(x, t, None, ei, feats, batch), base) < TOL
+    auto = dab.GNN_Diffusion(steps=300, sampling="DDIM", rotation=True, inference_ratio=10,
+                             model_mean_type=dab.ModelMeanType.START_X, gemm_mode="bf16x3", attn_mode="auto")
+    auto.load_state_dict(mods["fp32"].state_dict())
+    auto.to(DEV)
+    out_auto = auto.forward_with_feats(x, t, None, ei, feats, batch)
+    assert auto.model._engine.graph_stats()["dense_edges"] == ei.shape[1]
+    assert rel_err(out_auto, base) < TOL
     t0 = torch.zeros_like(t)
     last, _ = mods["fp32"].p_sample(x, t0, 0, cond=None, edge_index=ei, patch_feats=feats, batch=batch)
     assert rel_err(last, mods["fp32"].forward_with_feats(x, t0, None, ei, feats, batch)) < 1e-5
