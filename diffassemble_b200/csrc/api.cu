@@ -216,7 +216,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     }
     AttnCsrArgs a{};
     a.qkvs = h->qkvs.as<float>(); a.ld = 4 * HC;
-    a.rowptr = csr.rowptr; a.col = csr.col;
+    a.rowptr = csr.rowptr; a.col = csr.col; a.weight = csr.weight;
     if (dense) { a.init_acc = h->dacc.as<float>(); a.init_stats = h->dstats.as<float>(); a.init_slot = h->plan.node_slot; }
     a.H = c.heads; a.C = C;
     a.act = (!last && c.arch == DA_ARCH_TRANSFORMER) ? ACT_GELU : ACT_NONE;
@@ -239,7 +239,21 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
       xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
     }
-    {
+    if (h->use_plan && attn_csr_rows_supported(c.heads, C) && !a.scores) {
+      // residual edges: low-degree rows on the warp-per-node kernel, heavy rows (virtual nodes) edge-parallel
+      const DensePlan& pl = h->plan;
+      AttnCsrArgs hv = a, lt = a;
+      hv.node_list = pl.heavy; hv.n_targets = last ? pl.n_heavy_real : pl.n_heavy;
+      lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light;
+      if (hv.n_targets > 0) {
+        Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
+        DA_CK(launch_attn_csr_heavy(hv, s), "graph attention (heavy rows)");
+      }
+      if (lt.n_targets > 0) {
+        Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
+        DA_CK(launch_attn_csr_rows(lt, s), "graph attention (light rows)");
+      }
+    } else {
       Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
       DA_CK(launch_attn_csr(a, s), "graph attention");
     }
@@ -742,10 +756,18 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
     }
     if (ce == cudaSuccess) {
       AttnCsrArgs a{};
-      a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = plan.residual.rowptr; a.col = plan.residual.col; a.n_targets = n;
+      a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = plan.residual.rowptr; a.col = plan.residual.col; a.weight = plan.residual.weight; a.n_targets = n;
       a.H = H; a.C = C; a.act = ACT_NONE; a.out.f32 = y; a.out.ldc = H * C;
       if (plan.n_tiles > 0) { a.init_acc = acc; a.init_stats = st; a.init_slot = plan.node_slot; }
-      ce = launch_attn_csr(a, s);
+      if (attn_csr_rows_supported(H, C)) {
+        AttnCsrArgs hv = a, lt = a;
+        hv.node_list = plan.heavy; hv.n_targets = plan.n_heavy;
+        lt.node_list = plan.light; lt.n_targets = plan.n_light;
+        ce = launch_attn_csr_heavy(hv, s);
+        if (ce == cudaSuccess) ce = launch_attn_csr_rows(lt, s);
+      } else {
+        ce = launch_attn_csr(a, s);
+      }
     }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
     if (ce != cudaSuccess) rc = DA_ERR_CUDA;

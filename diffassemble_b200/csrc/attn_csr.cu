@@ -21,16 +21,18 @@ constexpr int WARPS_PER_CTA = 8;
 template <int R>  // R = ceil(C / 32) channel accumulators per lane
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
-                const int32_t* __restrict__ col, int n_targets, int H, int C, float scale,
+                const int32_t* __restrict__ col, const float* __restrict__ weight, int n_targets, int H, int C, float scale,
                 const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                 __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
                 float* __restrict__ scores, float* __restrict__ stats, const float* __restrict__ init_acc,
-                const float* __restrict__ init_stats, const int32_t* __restrict__ init_slot) {
+                const float* __restrict__ init_stats, const int32_t* __restrict__ init_slot,
+                const int32_t* __restrict__ node_list) {
   extern __shared__ __align__(16) float q_sm[];  // [WARPS_PER_CTA][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * WARPS_PER_CTA + warp;
   if (gw >= (long long)n_targets * H) return;  // whole warp exits together
-  const int node = (int)(gw / H), head = (int)(gw % H);
+  const int node = node_list ? node_list[gw / H] : (int)(gw / H);
+  const int head = (int)(gw % H);
   const int HC = H * C;
   float* q = q_sm + warp * C;
   const float* qrow = qkvs + (size_t)node * ld + head * C;
@@ -78,7 +80,8 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
       if (scores) scores[(size_t)e * H + head] = s;
     }
     const float m_new = fmaxf(m, warp_max(s));
-    const float p = valid ? expf(s - m_new) : 0.f;
+    float p = valid ? expf(s - m_new) : 0.f;
+    if (weight != nullptr && valid) p *= weight[e];
     const float rescale = (m == -INFINITY) ? 0.f : expf(m - m_new);
     l = l * rescale + warp_sum(p);
 #pragma unroll
@@ -120,6 +123,232 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
   }
 }
 
+// Heavy rows (hundreds of in-edges: the virtual nodes of the Exphander wiring): one CTA owns one
+// (target node, head); its 8 warps take interleaved 32-edge chunks with the same online softmax as
+// attn_csr_kernel, then the 8 partial states (m, l, acc) are merged through shared memory.
+template <int R>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
+                      const int32_t* __restrict__ col, const float* __restrict__ weight,
+                      const int32_t* __restrict__ node_list, int H, int C, float scale,
+                      const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
+                      __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
+                      const float* __restrict__ init_acc, const float* __restrict__ init_stats,
+                      const int32_t* __restrict__ init_slot) {
+  extern __shared__ __align__(16) float sm[];  // q[C] | acc[WARPS][C] | m[WARPS] | l[WARPS]
+  float* q = sm;
+  float* acc_s = sm + C;
+  float* m_s = acc_s + WARPS_PER_CTA * C;
+  float* l_s = m_s + WARPS_PER_CTA;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int node = node_list[blockIdx.x / H], head = blockIdx.x % H;
+  const int HC = H * C;
+  const float* qrow = qkvs + (size_t)node * ld + head * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) q[c] = qrow[c] * scale;
+  __syncthreads();
+  const float* Kbase = qkvs + HC + head * C;
+  const float* Vbase = qkvs + 2 * HC + head * C;
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  float m = -INFINITY, l = 0.f;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (warp == 0 && init_slot != nullptr && init_slot[node] >= 0) {
+    m = init_stats[((size_t)node * H + head) * 2 + 0];
+    l = init_stats[((size_t)node * H + head) * 2 + 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = lane + 32 * r;
+      if (c < C) acc[r] = init_acc[(size_t)node * HC + head * C + c];
+    }
+  }
+  for (int base = beg + warp * 32; base < end; base += 32 * WARPS_PER_CTA) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const int j = valid ? col[e] : 0;
+    float s = -INFINITY;
+    if (valid) {
+      const float* kr = Kbase + (size_t)j * ld;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      if ((C & 3) == 0) {
+        for (int c = 0; c < C; c += 4) {
+          float4 kk = __ldg(reinterpret_cast<const float4*>(kr + c));
+          float4 qq = *reinterpret_cast<const float4*>(q + c);
+          d0 = fmaf(kk.x, qq.x, d0); d1 = fmaf(kk.y, qq.y, d1);
+          d2 = fmaf(kk.z, qq.z, d2); d3 = fmaf(kk.w, qq.w, d3);
+        }
+      } else {
+        for (int c = 0; c < C; ++c) d0 = fmaf(__ldg(kr + c), q[c], d0);
+      }
+      s = (d0 + d1) + (d2 + d3);
+    }
+    const float m_new = fmaxf(m, warp_max(s));
+    float p = valid ? expf(s - m_new) : 0.f;
+    if (weight != nullptr && valid) p *= weight[e];
+    const float rescale = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    l = l * rescale + warp_sum(p);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] *= rescale;
+    m = m_new;
+    // aggregate: 4 V rows in flight per step (invalid lanes carry p = 0 and row 0)
+#pragma unroll 1
+    for (int t = 0; t < 32; t += 4) {
+      float pt[4]; const float* vr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pt[u] = __shfl_sync(0xffffffffu, p, t + u);
+        vr[u] = Vbase + (size_t)__shfl_sync(0xffffffffu, j, t + u) * ld;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int c = lane + 32 * r;
+        if (c < C) {
+          float v0 = __ldg(vr[0] + c), v1 = __ldg(vr[1] + c), v2 = __ldg(vr[2] + c), v3 = __ldg(vr[3] + c);
+          acc[r] = fmaf(pt[0], v0, acc[r]); acc[r] = fmaf(pt[1], v1, acc[r]);
+          acc[r] = fmaf(pt[2], v2, acc[r]); acc[r] = fmaf(pt[3], v3, acc[r]);
+        }
+      }
+    }
+  }
+  if (lane == 0) { m_s[warp] = m; l_s[warp] = l; }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) acc_s[warp * C + c] = acc[r];
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  float M = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < WARPS_PER_CTA; ++w) M = fmaxf(M, m_s[w]);
+  float L = 0.f;
+  float f[WARPS_PER_CTA];
+#pragma unroll
+  for (int w = 0; w < WARPS_PER_CTA; ++w) {
+    f[w] = (m_s[w] == -INFINITY) ? 0.f : expf(m_s[w] - M);
+    L += l_s[w] * f[w];
+  }
+  const float inv = 1.f / (L + 1e-16f);
+  const float* srow = qkvs + (size_t)node * ld + 3 * HC + head * C;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS_PER_CTA; ++w) a = fmaf(acc_s[w * C + c], f[w], a);
+      float v = a * inv + srow[c];
+      if (resid) v += resid[(size_t)node * ld_resid + head * C + c];
+      v = apply_act_rt(v, act);
+      const size_t o = (size_t)head * C + c;
+      if (yf) yf[(size_t)node * ldc + o] = v;
+      if (yhi) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        yhi[(size_t)node * ldsp + o] = h;
+        ylo[(size_t)node * ldsp + o] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+  }
+}
+
+// Row-parallel variant for low-degree targets (the residual edges of a dense-tile plan: typically one
+// virtual->real edge per node).  One warp owns one target node and ALL heads: lane l holds the VPL =
+// H*C/32 contiguous channels [l*VPL, (l+1)*VPL) of the row, which belong to head l / (32/H); every
+// row access (Q, K_j, V_j, skip, residual, dense accumulator, output) is a fully coalesced H*C-wide
+// read or write, and the per-head score is a shuffle reduction over the 32/H lanes of that head.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+attn_csr_rows_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
+                     const int32_t* __restrict__ col, const float* __restrict__ weight,
+                     const int32_t* __restrict__ node_list, int n_list, int H, int C, float scale,
+                     const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
+                     __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
+                     const float* __restrict__ init_acc, const float* __restrict__ init_stats,
+                     const int32_t* __restrict__ init_slot) {
+  constexpr int W = (VPL % 4 == 0) ? 4 : ((VPL % 2 == 0) ? 2 : 1);
+  const int lane = threadIdx.x & 31;
+  const int wg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (wg >= n_list) return;
+  const int node = node_list ? node_list[wg] : wg;
+  const int HC = H * C, lph = 32 / H, head = lane / lph;
+  const int c0 = lane * VPL;  // first channel (within the H*C row) owned by this lane
+
+  auto load_row = [&](const float* p, float* dst) {
+#pragma unroll
+    for (int i = 0; i < VPL; i += W) {
+      if (W == 4) { float4 t = __ldg(reinterpret_cast<const float4*>(p + i)); dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w; }
+      else if (W == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p + i)); dst[i] = t.x; dst[i + 1] = t.y; }
+      else dst[i] = __ldg(p + i);
+    }
+  };
+  float q[VPL], acc[VPL];
+  load_row(qkvs + (size_t)node * ld + c0, q);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) q[i] *= scale;
+  float m = -INFINITY, l = 0.f;
+  if (init_slot != nullptr && init_slot[node] >= 0) {
+    m = init_stats[((size_t)node * H + head) * 2 + 0];
+    l = init_stats[((size_t)node * H + head) * 2 + 1];
+    load_row(init_acc + (size_t)node * HC + c0, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+  }
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  for (int e = beg; e < end; ++e) {
+    const int j = col[e];
+    const float w = weight ? weight[e] : 1.f;
+    float kv[VPL];
+    load_row(qkvs + (size_t)j * ld + HC + c0, kv);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) d = fmaf(q[i], kv[i], d);
+    for (int o = lph >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    load_row(qkvs + (size_t)j * ld + 2 * HC + c0, kv);
+    const float m_new = fmaxf(m, d);
+    const float sc = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    const float p = w * expf(d - m_new);
+    l = l * sc + p;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i] = fmaf(p, kv[i], acc[i] * sc);
+    m = m_new;
+  }
+  const float inv = 1.f / (l + 1e-16f);
+  float sk[VPL];
+  load_row(qkvs + (size_t)node * ld + 3 * HC + c0, sk);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) sk[i] = fmaf(acc[i], inv, sk[i]);
+  if (resid) {
+    float rr[VPL];
+    load_row(resid + (size_t)node * ld_resid + c0, rr);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sk[i] += rr[i];
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) sk[i] = apply_act_rt(sk[i], act);
+  if (yf) {
+    float* dst = yf + (size_t)node * ldc + c0;
+#pragma unroll
+    for (int i = 0; i < VPL; i += W) {
+      if (W == 4) *reinterpret_cast<float4*>(dst + i) = make_float4(sk[i], sk[i + 1], sk[i + 2], sk[i + 3]);
+      else if (W == 2) *reinterpret_cast<float2*>(dst + i) = make_float2(sk[i], sk[i + 1]);
+      else dst[i] = sk[i];
+    }
+  }
+  if (yhi) {
+    __nv_bfloat16* dh = yhi + (size_t)node * ldsp + c0;
+    __nv_bfloat16* dl = ylo + (size_t)node * ldsp + c0;
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+      __nv_bfloat162 h2, l2;
+      h2.x = __float2bfloat16_rn(sk[i]); h2.y = __float2bfloat16_rn(sk[i + 1]);
+      l2.x = __float2bfloat16_rn(sk[i] - __bfloat162float(h2.x)); l2.y = __float2bfloat16_rn(sk[i + 1] - __bfloat162float(h2.y));
+      *reinterpret_cast<__nv_bfloat162*>(dh + i) = h2;
+      *reinterpret_cast<__nv_bfloat162*>(dl + i) = l2;
+    }
+  }
+}
+
 __global__ void alpha_normalize_kernel(const float* __restrict__ scores, const float* __restrict__ stats,
                                        const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid,
                                        int n_targets, int H, float* __restrict__ alpha) {
@@ -148,13 +377,57 @@ cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s) {
   const int R = (a.C + 31) / 32;
 #define DA_LAUNCH(RR)                                                                                       \
   attn_csr_kernel<RR><<<grid, WARPS_PER_CTA * 32, smem, s>>>(                                               \
-      a.qkvs, a.ld, a.rowptr, a.col, a.n_targets, a.H, a.C, scale, a.resid, a.ld_resid, a.act, a.out.f32,   \
-      a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.scores, a.stats, a.init_acc, a.init_stats, a.init_slot)
+      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.n_targets, a.H, a.C, scale, a.resid, a.ld_resid, a.act, a.out.f32,   \
+      a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.scores, a.stats, a.init_acc, a.init_stats, a.init_slot,   \
+      a.node_list)
   if (R <= 1) DA_LAUNCH(1);
   else if (R <= 2) DA_LAUNCH(2);
   else if (R <= 5) DA_LAUNCH(5);
   else if (R <= 13) DA_LAUNCH(13);
   else return cudaErrorInvalidValue;  // head dims above 416 (resnet50 trunk) are not built
+#undef DA_LAUNCH
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s) {
+  if (a.n_targets <= 0) return cudaSuccess;
+  if (!a.node_list || a.scores || a.stats) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(a.C + WARPS_PER_CTA * a.C + 2 * WARPS_PER_CTA) * sizeof(float);
+  const float scale = 1.0f / sqrtf((float)a.C);
+  const int R = (a.C + 31) / 32;
+  const unsigned grid = (unsigned)a.n_targets * a.H;
+#define DA_LAUNCH(RR)                                                                                          \
+  attn_csr_heavy_kernel<RR><<<grid, WARPS_PER_CTA * 32, smem, s>>>(                                            \
+      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.H, a.C, scale, a.resid, a.ld_resid, a.act,       \
+      a.out.f32, a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot)
+  if (R <= 1) DA_LAUNCH(1);
+  else if (R <= 2) DA_LAUNCH(2);
+  else if (R <= 5) DA_LAUNCH(5);
+  else if (R <= 13) DA_LAUNCH(13);
+  else return cudaErrorInvalidValue;
+#undef DA_LAUNCH
+  return cudaGetLastError();
+}
+
+bool attn_csr_rows_supported(int H, int C) {
+  if (H <= 0 || 32 % H) return false;
+  const int vpl = H * C / 32;
+  return (H * C) % 32 == 0 && (vpl == 8 || vpl == 36 || vpl == 6);
+}
+
+cudaError_t launch_attn_csr_rows(const AttnCsrArgs& a, cudaStream_t s) {
+  if (a.n_targets <= 0) return cudaSuccess;
+  if (!attn_csr_rows_supported(a.H, a.C) || a.scores || a.stats) return cudaErrorInvalidValue;
+  const int vpl = a.H * a.C / 32;
+  const unsigned grid = (unsigned)(((long long)a.n_targets * 32 + 255) / 256);
+  const float scale = 1.0f / sqrtf((float)a.C);
+#define DA_LAUNCH(V)                                                                                              \
+  attn_csr_rows_kernel<V><<<grid, 256, 0, s>>>(a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, a.H, \
+                                               a.C, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc, a.out.hi, \
+                                               a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot)
+  if (vpl == 8) DA_LAUNCH(8);
+  else if (vpl == 36) DA_LAUNCH(36);
+  else DA_LAUNCH(6);
 #undef DA_LAUNCH
   return cudaGetLastError();
 }

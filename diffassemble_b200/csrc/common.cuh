@@ -67,6 +67,7 @@ struct AttnCsrArgs {
   int ld;                // row stride of qkvs (= 4*H*C)
   const int32_t* rowptr; // [n_targets + 1] in-edge ranges per target
   const int32_t* col;    // [E] source node per in-edge
+  const float* weight;   // optional [E] multiplicity of each in-edge (null = 1)
   int n_targets;         // targets processed (first n_targets rows)
   int H, C;
   const float* resid;    // optional [n_targets, ld_resid] added after skip (trunk residual), or null
@@ -79,8 +80,14 @@ struct AttnCsrArgs {
   const float* init_acc;      // [n, H*C] un-normalised accumulator
   const float* init_stats;    // [n, H, 2] (m, l)
   const int32_t* init_slot;   // [n] >= 0 where the init state is valid
+  const int32_t* node_list;   // optional: the n_targets target ids to process (null = 0 .. n_targets-1)
 };
 cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s);
+// warp-per-node variant for low-degree targets (all heads at once, fully coalesced rows)
+bool attn_csr_rows_supported(int H, int C);
+cudaError_t launch_attn_csr_rows(const AttnCsrArgs& a, cudaStream_t s);
+// CTA-per-(node, head) variant for rows with hundreds of in-edges (needs node_list)
+cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s);
 
 // alpha[eid[p], h] = exp(scores[p,h] - max) / (sum + 1e-16)
 cudaError_t launch_alpha_normalize(const float* scores, const float* stats, const int32_t* rowptr,
@@ -129,13 +136,16 @@ cudaError_t launch_sampler_update(const float* x_in, const float* model_out, flo
 struct CsrGraph {
   int32_t* rowptr = nullptr;  // [n + 1]
   int32_t* col = nullptr;     // [E]
-  int32_t* eid = nullptr;     // [E] original edge index of each CSR slot
+  int32_t* eid = nullptr;     // [E] original edge index of each CSR slot (uncompressed build only)
+  float* weight = nullptr;    // [E] multiplicity of each (target, source) pair (compressed build only)
   int64_t E = 0;
   int n = 0;
 };
 // Builds CSR by target with a stable radix sort.  Allocates with cudaMallocAsync-free plain cudaMalloc.
 cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
                       const char** err);
+cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
+                                 const char** err);
 void free_csr(CsrGraph* g);
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
@@ -175,6 +185,10 @@ struct DensePlan {
   uint32_t* bitmap = nullptr;      // device
   size_t bitmap_words = 0;
   CsrGraph residual;               // CSR by target over the edges not in the bitmap
+  // targets split by residual in-degree: "light" rows (<= 16 edges) take the warp-per-node kernel,
+  // "heavy" rows (virtual nodes with hundreds of in-edges) the edge-parallel one.  Real nodes first.
+  int32_t* light = nullptr; int n_light = 0, n_light_real = 0;
+  int32_t* heavy = nullptr; int n_heavy = 0, n_heavy_real = 0;
 };
 void free_plan(DensePlan* p);
 // Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.

@@ -44,8 +44,90 @@ __global__ void rowptr_kernel(const int32_t* __restrict__ sorted_dst, int64_t E,
 
 void free_csr(CsrGraph* g) {
   if (!g) return;
-  cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->eid);
+  cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->eid); cudaFree(g->weight);
   *g = CsrGraph();
+}
+
+namespace {
+__global__ void pack_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E, int n,
+                                 unsigned long long* __restrict__ key, int32_t* __restrict__ bad) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int64_t s = src[e], d = dst[e];
+  if (s < 0 || s >= n || d < 0 || d >= n) { atomicExch(bad, 1); s = 0; d = 0; }
+  key[e] = ((unsigned long long)d << 32) | (unsigned long long)s;
+}
+__global__ void unpack_runs_kernel(const unsigned long long* __restrict__ ukey, const int32_t* __restrict__ cnt,
+                                   const int32_t* __restrict__ nruns, int32_t* __restrict__ col,
+                                   float* __restrict__ weight, int32_t* __restrict__ udst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *nruns) return;
+  col[i] = (int32_t)(ukey[i] & 0xffffffffull);
+  udst[i] = (int32_t)(ukey[i] >> 32);
+  weight[i] = (float)cnt[i];
+}
+}  // namespace
+
+// CSR by target with duplicate edges collapsed into (source, multiplicity) pairs: a duplicate edge
+// contributes a second identical term to the segment softmax, i.e. weight * exp(score).
+cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
+                                 const char** err) {
+  *err = "";
+  free_csr(g);
+  if (E >= (int64_t)1 << 31) { *err = "edge count exceeds int32 range"; return cudaErrorInvalidValue; }
+  cudaError_t ce;
+#define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
+  unsigned long long *key = nullptr, *key_sorted = nullptr, *ukey = nullptr;
+  int32_t *cnt = nullptr, *nruns = nullptr, *bad = nullptr, *udst = nullptr;
+  void* tmp = nullptr;
+  size_t tb1 = 0, tb2 = 0;
+  int32_t bad_h = 0, nruns_h = 0;
+  int bits = 1;
+  g->n = n;
+  DA_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1)));
+  if (E == 0) {
+    g->E = 0;
+    DA_TRY(cudaMalloc(&g->col, sizeof(int32_t)));
+    DA_TRY(cudaMalloc(&g->weight, sizeof(float)));
+    DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
+    return cudaSuccess;
+  }
+  DA_TRY(cudaMalloc(&key, sizeof(unsigned long long) * (size_t)E));
+  DA_TRY(cudaMalloc(&key_sorted, sizeof(unsigned long long) * (size_t)E));
+  DA_TRY(cudaMalloc(&ukey, sizeof(unsigned long long) * (size_t)E));
+  DA_TRY(cudaMalloc(&cnt, sizeof(int32_t) * (size_t)E));
+  DA_TRY(cudaMalloc(&udst, sizeof(int32_t) * (size_t)E));
+  DA_TRY(cudaMalloc(&nruns, sizeof(int32_t)));
+  DA_TRY(cudaMalloc(&bad, sizeof(int32_t)));
+  DA_TRY(cudaMemsetAsync(bad, 0, sizeof(int32_t), s));
+  pack_keys_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, n, key, bad);
+  DA_TRY(cudaGetLastError());
+  while ((1ll << bits) < (long long)n + 1 && bits < 31) ++bits;
+  DA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb1, key, key_sorted, (int)E, 0, 32 + bits, s));
+  DA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tb2, key_sorted, ukey, cnt, nruns, (int)E, s));
+  if (tb2 > tb1) tb1 = tb2;
+  DA_TRY(cudaMalloc(&tmp, tb1));
+  DA_TRY(cub::DeviceRadixSort::SortKeys(tmp, tb1, key, key_sorted, (int)E, 0, 32 + bits, s));
+  DA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tb1, key_sorted, ukey, cnt, nruns, (int)E, s));
+  DA_TRY(cudaMemcpyAsync(&nruns_h, nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DA_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DA_TRY(cudaStreamSynchronize(s));
+  if (bad_h) { *err = "edge_index entry outside [0, num_total)"; ce = cudaErrorInvalidValue; goto fail; }
+  g->E = nruns_h;
+  DA_TRY(cudaMalloc(&g->col, sizeof(int32_t) * (size_t)nruns_h));
+  DA_TRY(cudaMalloc(&g->weight, sizeof(float) * (size_t)nruns_h));
+  unpack_runs_kernel<<<(nruns_h + 255) / 256, 256, 0, s>>>(ukey, cnt, nruns, g->col, g->weight, udst);
+  DA_TRY(cudaGetLastError());
+  rowptr_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(udst, nruns_h, n, g->rowptr);
+  DA_TRY(cudaGetLastError());
+  DA_TRY(cudaStreamSynchronize(s));
+  cudaFree(key); cudaFree(key_sorted); cudaFree(ukey); cudaFree(cnt); cudaFree(udst); cudaFree(nruns); cudaFree(bad); cudaFree(tmp);
+  return cudaSuccess;
+fail:
+  cudaFree(key); cudaFree(key_sorted); cudaFree(ukey); cudaFree(cnt); cudaFree(udst); cudaFree(nruns); cudaFree(bad); cudaFree(tmp);
+  free_csr(g);
+  return ce;
+#undef DA_TRY
 }
 
 cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,

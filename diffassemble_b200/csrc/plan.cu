@@ -62,7 +62,7 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 
 void free_plan(DensePlan* p) {
   if (!p) return;
-  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap);
+  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy);
   free_csr(&p->residual);
   *p = DensePlan();
 }
@@ -178,14 +178,28 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     DA_TRY(cudaStreamSynchronize(s));
     n_res = nsel;
     plan->n_dense_edges = E - n_res;
-    ce = build_csr(res_src, res_dst, n_res, num_total, &plan->residual, s, err);
+    ce = build_csr_compressed(res_src, res_dst, n_res, num_total, &plan->residual, s, err);
     if (ce != cudaSuccess) goto fail;
   } else {
     plan->n_dense_edges = 0;
-    ce = build_csr(src, dst, E, num_total, &plan->residual, s, err);
+    ce = build_csr_compressed(src, dst, E, num_total, &plan->residual, s, err);
     if (ce != cudaSuccess) goto fail;
   }
   DA_TRY(cudaStreamSynchronize(s));
+  {  // degree classes of the residual CSR (node order kept, real nodes before virtual rows)
+    std::vector<int32_t> rp((size_t)num_total + 1), light, heavy;
+    DA_TRY(cudaMemcpy(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < num_total; ++i) {
+      if (i == num_real) { plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size(); }
+      (rp[i + 1] - rp[i] <= 16 ? light : heavy).push_back(i);
+    }
+    if (num_total == num_real) { plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size(); }
+    plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size();
+    DA_TRY(cudaMalloc(&plan->light, sizeof(int32_t) * (light.size() + 1)));
+    DA_TRY(cudaMalloc(&plan->heavy, sizeof(int32_t) * (heavy.size() + 1)));
+    DA_TRY(cudaMemcpy(plan->light, light.data(), sizeof(int32_t) * light.size(), cudaMemcpyHostToDevice));
+    DA_TRY(cudaMemcpy(plan->heavy, heavy.data(), sizeof(int32_t) * heavy.size(), cudaMemcpyHostToDevice));
+  }
   cudaFree(dcnt); cudaFree(d_g_node0); cudaFree(d_g_bm_words); cudaFree(d_bad); cudaFree(d_g_bm_off);
   cudaFree(res_src); cudaFree(res_dst); cudaFree(d_nsel); cudaFree(flag); cudaFree(tmp);
   return cudaSuccess;
