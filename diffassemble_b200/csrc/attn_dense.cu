@@ -44,11 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW instead of spinning
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -85,6 +85,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two fp32 -> packed bf16x2 (round to nearest even); low half = a, high half = b
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -312,7 +323,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         for (int e = 0; e < 16; ++e)
           if ((w >> e) & 1u) m_new = fmaxf(m_new, __uint_as_float(v[e]));
       }
-      const float alpha = (m == -INFINITY) ? 0.f : exp2f((m - m_new) * c_log2);
+      const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
       const float m_sub = (m_new == -INFINITY) ? 0.f : m_new * c_log2;
       if (j > 0) {
         mbar_wait(&sh->pv_done, (j - 1) & 1);   // P buffer free, O holds blocks < j
@@ -337,21 +348,24 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         tmem_ld16(s_addr + c0, v);
         tmem_ld_wait();
         const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
-        __nv_bfloat16 hi[16], lo[16];
+        uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float p = 0.f;
-          if ((w >> e) & 1u) p = exp2f(fmaf(__uint_as_float(v[e]), c_log2, -m_sub));
-          lsum += p;
-          hi[e] = __float2bfloat16_rn(p);
-          lo[e] = __float2bfloat16_rn(p - __bfloat162float(hi[e]));
+        for (int e = 0; e < 16; e += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), c_log2, -m_sub));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), c_log2, -m_sub));
+          p0 = ((w >> e) & 1u) ? p0 : 0.f;
+          p1 = ((w >> (e + 1)) & 1u) ? p1 : 0.f;
+          lsum += p0 + p1;
+          const uint32_t h2 = pack_bf16x2(p0, p1);
+          hi[e >> 1] = h2;
+          lo[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
         }
         // source chunk sc = (c0 / 8) and sc + 1: 16 bytes each at [sc][r][8]
         const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
-        *reinterpret_cast<uint4*>(p_hi + o0) = *reinterpret_cast<uint4*>(&hi[0]);
-        *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = *reinterpret_cast<uint4*>(&hi[8]);
-        *reinterpret_cast<uint4*>(p_lo + o0) = *reinterpret_cast<uint4*>(&lo[0]);
-        *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = *reinterpret_cast<uint4*>(&lo[8]);
+        *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
       l = l * alpha + lsum;
       m = m_new;

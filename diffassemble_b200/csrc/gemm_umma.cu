@@ -29,7 +29,7 @@ constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
+constexpr int EPI_PITCH = 36;   // floats per staged row (32 + 4 pad: float4-aligned, conflict-free enough)
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,11 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW instead of spinning
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -108,7 +108,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * BM * BK * 2 + 2 * BN * BK * 2;   // a_hi, a_lo, w_hi, w_lo
   static constexpr int STAGES = (BN >= 256) ? 2 : ((BN >= 128) ? 3 : 4);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;            // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * EPI_PITCH * 4 /*epilogue staging*/;
 };
 
 struct EpiParams {
@@ -202,13 +202,15 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {  // ===== epilogue warps: TMEM -> registers -> global =====
+  } else {  // ===== epilogue warps: TMEM -> registers -> smem (transpose) -> coalesced global stores =====
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int row_in_tile = q * 32 + lane;
+    float* stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + q * (32 * EPI_PITCH);
+    const int sub_row = lane >> 3;             // read-back mapping: 4 rows x 8 float4 per instruction
+    const int sub_col = (lane & 7) * 4;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-      const int row = m0 + row_in_tile;
+      const int row_base = m0 + q * 32;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -217,34 +219,39 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
-        if (row < p.M) {
-          float v[32];
+        // thread == row: park the 32 columns of this row in the staging tile
+        float4* srow = reinterpret_cast<float4*>(stage + lane * EPI_PITCH);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
-            v[j] = apply_act_rt(x, p.act);
-          }
-          if (p.cf) {
-            float4* dst = reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + n0 + c0);
+        for (int j = 0; j < 8; ++j)
+          srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + sub_col;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.chi) {
-            uint4* dh = reinterpret_cast<uint4*>(p.chi + (size_t)row * p.ldsp + n0 + c0);
-            uint4* dl = reinterpret_cast<uint4*>(p.clo + (size_t)row * p.ldsp + n0 + c0);
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + sub_row;
+          const int row = row_base + rr;
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + sub_col);
+          v.x = apply_act_rt(v.x + b4.x, p.act); v.y = apply_act_rt(v.y + b4.y, p.act);
+          v.z = apply_act_rt(v.z + b4.z, p.act); v.w = apply_act_rt(v.w + b4.w, p.act);
+          if (row < p.M) {
+            if (p.cf) *reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + col) = v;
+            if (p.chi) {
+              __nv_bfloat16 h[4], l[4];
+              const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat16 h[8], l[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                h[e] = __float2bfloat16_rn(v[8 * j + e]);
-                l[e] = __float2bfloat16_rn(v[8 * j + e] - __bfloat162float(h[e]));
+              for (int e = 0; e < 4; ++e) {
+                h[e] = __float2bfloat16_rn(vv[e]);
+                l[e] = __float2bfloat16_rn(vv[e] - __bfloat162float(h[e]));
               }
-              dh[j] = *reinterpret_cast<uint4*>(h);
-              dl[j] = *reinterpret_cast<uint4*>(l);
+              *reinterpret_cast<uint2*>(p.chi + (size_t)row * p.ldsp + col) = *reinterpret_cast<uint2*>(h);
+              *reinterpret_cast<uint2*>(p.clo + (size_t)row * p.ldsp + col) = *reinterpret_cast<uint2*>(l);
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
