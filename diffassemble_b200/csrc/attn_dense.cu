@@ -176,12 +176,19 @@ __global__ void pack_images_kernel(PackArgs a) {
 struct DenseSmem {
   uint64_t q_full;
   uint64_t k_full[KST], k_empty[KST];
-  uint64_t v_full, v_empty;
+  uint64_t v_full[2], v_empty[2];
   uint64_t s_full[2], s_empty[2];
-  uint64_t p_full, pv_done;
+  uint64_t p_full[2], pv_done[2];
   uint32_t tmem_base;
 };
 
+// Reference point of the online softmax is only raised when a block's max exceeds it by more than
+// 2^LAZY_LOG2 (lazy rescaling): exp2 arguments stay <= LAZY_LOG2, the O correction in TMEM becomes
+// rare, and the result is mathematically identical (any reference point cancels in acc / l).
+constexpr float LAZY_LOG2 = 8.0f;
+
+// NPB = number of P buffers in shared memory, VST = number of V^T stages (both 2 when they fit).
+template <int NPB, int VST>
 __global__ void __launch_bounds__(NT)
 attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -189,9 +196,9 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2, p_plane = TM * TS * 2;  // bytes
   uint8_t* q_sm = smem;                                   // 2 planes
   uint8_t* k_sm = q_sm + 2 * q_plane;                     // KST stages x 2 planes
-  uint8_t* v_sm = k_sm + KST * 2 * kv_plane;              // 1 stage x 2 planes
-  uint8_t* p_sm = v_sm + 2 * kv_plane;                    // 2 planes
-  DenseSmem* sh = reinterpret_cast<DenseSmem*>(p_sm + 2 * p_plane);
+  uint8_t* v_sm = k_sm + KST * 2 * kv_plane;              // VST stages x 2 planes
+  uint8_t* p_sm = v_sm + VST * 2 * kv_plane;              // NPB buffers x 2 planes
+  DenseSmem* sh = reinterpret_cast<DenseSmem*>(p_sm + NPB * 2 * p_plane);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / a.H, head = blockIdx.x % a.H;
@@ -201,9 +208,11 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   if (threadIdx.x == 0) {
     mbar_init(&sh->q_full, 1);
     for (int i = 0; i < KST; ++i) { mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1); }
-    mbar_init(&sh->v_full, 1); mbar_init(&sh->v_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->s_empty[i], 4); }
-    mbar_init(&sh->p_full, 4); mbar_init(&sh->pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
+      mbar_init(&sh->s_full[i], 1); mbar_init(&sh->s_empty[i], 4);
+      mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -218,33 +227,41 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   const uint32_t tmem_o = tmem_base + 2 * TS;    // Cpad columns
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== bulk-copy producer =====
+    if (lane == 0) {  // ===== bulk-copy producer: K runs two blocks ahead, V^T VST blocks ahead =====
       const __nv_bfloat16* qsrc = a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cpad);
       mbar_expect_tx(&sh->q_full, 2 * q_plane);
       bulk_load(q_sm, qsrc, 2 * q_plane, &sh->q_full);
-      uint32_t kph = 0, vph = 0;
-      int ks = 0;
+      auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad); };
+      auto load_k = [&](int j) {
+        const int st = j % KST;
+        mbar_expect_tx(&sh->k_full[st], 2 * kv_plane);
+        bulk_load(k_sm + st * 2 * kv_plane, a.kimg + blk_off(j), 2 * kv_plane, &sh->k_full[st]);
+      };
+      auto load_v = [&](int j) {
+        const int st = j % VST;
+        mbar_expect_tx(&sh->v_full[st], 2 * kv_plane);
+        bulk_load(v_sm + st * 2 * kv_plane, a.vimg + blk_off(j), 2 * kv_plane, &sh->v_full[st]);
+      };
+      for (int j = 0; j < KST && j < nblk; ++j) load_k(j);
+      for (int j = 0; j < VST && j < nblk; ++j) load_v(j);
       for (int j = 0; j < nblk; ++j) {
-        const size_t boff = ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad);
-        mbar_wait(&sh->k_empty[ks], kph ^ 1);
-        mbar_expect_tx(&sh->k_full[ks], 2 * kv_plane);
-        bulk_load(k_sm + ks * 2 * kv_plane, a.kimg + boff, 2 * kv_plane, &sh->k_full[ks]);
-        if (++ks == KST) { ks = 0; kph ^= 1; }
-        mbar_wait(&sh->v_empty, vph ^ 1);
-        mbar_expect_tx(&sh->v_full, 2 * kv_plane);
-        bulk_load(v_sm, a.vimg + boff, 2 * kv_plane, &sh->v_full);
-        vph ^= 1;
+        if (j + KST < nblk) {  // slot j % KST is free once S_j (its (j / KST)-th user) has retired
+          mbar_wait(&sh->k_empty[j % KST], (j / KST) & 1);
+          load_k(j + KST);
+        }
+        if (j + VST < nblk) {
+          mbar_wait(&sh->v_empty[j % VST], (j / VST) & 1);
+          load_v(j + VST);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad);
       const uint32_t q_hi = smem_u32(q_sm), q_lo = q_hi + q_plane;
-      const uint32_t p_hi = smem_u32(p_sm), p_lo = p_hi + p_plane;
-      const uint32_t v_hi = smem_u32(v_sm), v_lo = v_hi + kv_plane;
       const int ksteps = Cpad / 16;
-      auto issue_s = [&](int j, int ks) {
-        const uint32_t k_hi = smem_u32(k_sm + ks * 2 * kv_plane), k_lo = k_hi + kv_plane;
+      auto issue_s = [&](int j) {
+        const uint32_t k_hi = smem_u32(k_sm + (j % KST) * 2 * kv_plane), k_lo = k_hi + kv_plane;
         const uint32_t d = tmem_s + (uint32_t)((j & 1) * TS);
         for (int kk = 0; kk < ksteps; ++kk) {
           // one k-step = 16 channels = 2 chunks; Q chunk stride TM*16 B, K chunk stride TS*16 B
@@ -256,32 +273,27 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
           tc_mma_bf16(d, aq_hi, bk_lo, idesc_s, 1u);
           tc_mma_bf16(d, aq_lo, bk_hi, idesc_s, 1u);
         }
+        tc_commit(&sh->s_full[j & 1]);
+        tc_commit(&sh->k_empty[j % KST]);
       };
       mbar_wait(&sh->q_full, 0);
-      uint32_t kph = 0;
-      int ks = 0;
-      // S_0
       mbar_wait(&sh->k_full[0], 0);
       tc_fence_after();
-      issue_s(0, 0);
-      tc_commit(&sh->s_full[0]);
-      tc_commit(&sh->k_empty[0]);
-      ks = 1 % KST; if (ks == 0) kph ^= 1;
-      uint32_t sph[2] = {0, 0};  // parity of the NEXT s_empty wait per buffer
+      issue_s(0);
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
-          const int b = (j + 1) & 1;
-          mbar_wait(&sh->k_full[ks], kph);
-          if (j + 1 >= 2) { mbar_wait(&sh->s_empty[b], sph[b]); sph[b] ^= 1; }  // softmax released this S buffer
+          const int jn = j + 1;
+          mbar_wait(&sh->k_full[jn % KST], (jn / KST) & 1);
+          if (jn >= 2) mbar_wait(&sh->s_empty[jn & 1], ((jn >> 1) - 1) & 1);  // softmax released this S buffer
           tc_fence_after();
-          issue_s(j + 1, ks);
-          tc_commit(&sh->s_full[b]);
-          tc_commit(&sh->k_empty[ks]);
-          if (++ks == KST) { ks = 0; kph ^= 1; }
+          issue_s(jn);
         }
-        mbar_wait(&sh->p_full, j & 1);   // P_j in smem, O corrected
-        mbar_wait(&sh->v_full, j & 1);
+        const int pb = j % NPB, vs = j % VST;
+        mbar_wait(&sh->p_full[pb], (j / NPB) & 1);   // P_j in smem (and O corrected if needed)
+        mbar_wait(&sh->v_full[vs], (j / VST) & 1);
         tc_fence_after();
+        const uint32_t p_hi = smem_u32(p_sm + pb * 2 * p_plane), p_lo = p_hi + p_plane;
+        const uint32_t v_hi = smem_u32(v_sm + vs * 2 * kv_plane), v_lo = v_hi + kv_plane;
         for (int kk = 0; kk < TS / 16; ++kk) {
           const uint64_t ap_hi = make_desc_nosw(p_hi + kk * 2 * (TM * 16), TM * 16, 128);
           const uint64_t ap_lo = make_desc_nosw(p_lo + kk * 2 * (TM * 16), TM * 16, 128);
@@ -291,8 +303,8 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
           tc_mma_bf16(tmem_o, ap_hi, bv_lo, idesc_o, 1u);
           tc_mma_bf16(tmem_o, ap_lo, bv_hi, idesc_o, 1u);
         }
-        tc_commit(&sh->pv_done);
-        tc_commit(&sh->v_empty);
+        tc_commit(&sh->pv_done[pb]);
+        tc_commit(&sh->v_empty[vs]);
       }
     }
   } else {  // ===== softmax warps =====
@@ -301,81 +313,117 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const bool row_valid = r < ti.rows;
     const float c_log2 = 1.4426950408889634f / sqrtf((float)a.C);  // scale * log2(e)
+    const float tau_raw = LAZY_LOG2 / c_log2;
     const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
-    float m = -INFINITY, l = 0.f;  // m in raw-score units
-    uint8_t* p_hi = p_sm;
-    uint8_t* p_lo = p_sm + p_plane;
+    float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
+    uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
       const int b = j & 1;
-      const uint2 bits = row_valid ? *reinterpret_cast<const uint2*>(bm_row + j * 2) : make_uint2(0u, 0u);
+      const uint2 bits = bits_next;
+      if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (j + 1) * 2);
+      const int pb = j % NPB;
+      uint8_t* p_hi = p_sm + pb * 2 * p_plane;
+      uint8_t* p_lo = p_hi + p_plane;
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
-      // pass 1: row max over the unmasked sources of this block
-      float m_new = m;
+      if (j == 0) {  // first block: take its masked max as the reference point
+        uint32_t v[TS];
 #pragma unroll
-      for (int c0 = 0; c0 < TS; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(s_addr + c0, v);
+        for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
         tmem_ld_wait();
-        const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if ((w >> e) & 1u) m_new = fmaxf(m_new, __uint_as_float(v[e]));
+        for (int e = 0; e < TS; ++e) {
+          const uint32_t w = (e < 32) ? bits.x : bits.y;
+          if ((w >> (e & 31)) & 1u) m = fmaxf(m, __uint_as_float(v[e]));
+        }
       }
-      const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
-      const float m_sub = (m_new == -INFINITY) ? 0.f : m_new * c_log2;
-      if (j > 0) {
-        mbar_wait(&sh->pv_done, (j - 1) & 1);   // P buffer free, O holds blocks < j
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // O correction (rows whose running max moved)
+      bool prev_done = (j == 0);            // has pv_done of block j-1 been observed?
+      if (NPB == 2 && j >= 2) mbar_wait(&sh->pv_done[pb], ((j >> 1) - 1) & 1);  // P buffer pb is free again
+      uint32_t hi[NPB == 1 ? TS / 2 : 1], lo[NPB == 1 ? TS / 2 : 1];
+      float lsum, bmax;
+      while (true) {
+        const float m_sub = (m == -INFINITY) ? 0.f : m * c_log2;
+        lsum = 0.f; bmax = -INFINITY;
+        uint32_t v[TS];
+#pragma unroll
+        for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c0 = 0; c0 < TS; c0 += 16) {
+          const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
+          uint32_t h8[8], l8[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float s0 = __uint_as_float(v[c0 + e]), s1 = __uint_as_float(v[c0 + e + 1]);
+            const bool on0 = (w >> e) & 1u, on1 = (w >> (e + 1)) & 1u;
+            bmax = fmaxf(bmax, on0 ? s0 : -INFINITY);
+            bmax = fmaxf(bmax, on1 ? s1 : -INFINITY);
+            float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
+            float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
+            p0 = on0 ? p0 : 0.f;
+            p1 = on1 ? p1 : 0.f;
+            lsum += p0 + p1;
+            const uint32_t h2 = pack_bf16x2(p0, p1);
+            h8[e >> 1] = h2;
+            l8[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
+          }
+          if (NPB == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { hi[(c0 >> 1) + e] = h8[e]; lo[(c0 >> 1) + e] = l8[e]; }
+          } else {
+            // source chunks (c0 / 8) and (c0 / 8) + 1: 16 bytes each at [chunk][r][8]
+            const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
+            *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+            *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+            *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+          }
+        }
+        const bool exceeded = bmax > m + tau_raw;   // also true when m == -inf and the block has an edge
+        if (!__any_sync(0xffffffffu, exceeded)) break;
+        // rare: raise the reference point, rescale the history (l and O in TMEM), redo this block
+        const float m_new = exceeded ? bmax : m;
+        const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
+        if (!prev_done) {
+          mbar_wait(&sh->pv_done[(j - 1) % NPB], ((j - 1) / NPB) & 1);   // O holds every block < j
+          tc_fence_after();
+          prev_done = true;
+        }
+        if (j > 0) {
           for (int c0 = 0; c0 < Cpad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_o + lane_off + c0, v);
+            uint32_t o[16];
+            tmem_ld16(tmem_o + lane_off + c0, o);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            tmem_st16(tmem_o + lane_off + c0, v);
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st16(tmem_o + lane_off + c0, o);
           }
           tmem_st_wait();
         }
+        l *= alpha;
+        m = m_new;
       }
-      // pass 2: P = exp2(s*c - m*c) on the bitmap, split to bf16 hi/lo, store in the A-operand layout
-      float lsum = 0.f;
+      l += lsum;
+      if (NPB == 1) {
+        if (!prev_done) mbar_wait(&sh->pv_done[0], (j - 1) & 1);   // single P buffer: PV_{j-1} must have read it
 #pragma unroll
-      for (int c0 = 0; c0 < TS; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(s_addr + c0, v);
-        tmem_ld_wait();
-        const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[e]), c_log2, -m_sub));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[e + 1]), c_log2, -m_sub));
-          p0 = ((w >> e) & 1u) ? p0 : 0.f;
-          p1 = ((w >> (e + 1)) & 1u) ? p1 : 0.f;
-          lsum += p0 + p1;
-          const uint32_t h2 = pack_bf16x2(p0, p1);
-          hi[e >> 1] = h2;
-          lo[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
+        for (int c0 = 0; c0 < TS; c0 += 16) {
+          const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
+          const int i0 = c0 >> 1;
+          *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(hi[i0], hi[i0 + 1], hi[i0 + 2], hi[i0 + 3]);
+          *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(hi[i0 + 4], hi[i0 + 5], hi[i0 + 6], hi[i0 + 7]);
+          *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(lo[i0], lo[i0 + 1], lo[i0 + 2], lo[i0 + 3]);
+          *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(lo[i0 + 4], lo[i0 + 5], lo[i0 + 6], lo[i0 + 7]);
         }
-        // source chunk sc = (c0 / 8) and sc + 1: 16 bytes each at [sc][r][8]
-        const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
-        *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
-      l = l * alpha + lsum;
-      m = m_new;
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy P stores -> async proxy (MMA)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&sh->p_full); mbar_arrive(&sh->s_empty[b]); }
+      if (lane == 0) { mbar_arrive(&sh->p_full[pb]); mbar_arrive(&sh->s_empty[b]); }
     }
     // epilogue: un-normalised O and (m, l) to global
-    mbar_wait(&sh->pv_done, (nblk - 1) & 1);
+    mbar_wait(&sh->pv_done[(nblk - 1) % NPB], ((nblk - 1) / NPB) & 1);
     tc_fence_after();
     const int node = ti.node0 + r;
     const int HC = a.H * a.C;
@@ -424,22 +472,37 @@ cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+namespace {
+size_t dense_smem_bytes(int Cpad, int npb, int vst) {
+  return (size_t)2 * TM * Cpad * 2 + (size_t)(KST + vst) * 2 * TS * Cpad * 2 + (size_t)npb * 2 * TM * TS * 2 + sizeof(DenseSmem) + 128;
+}
+template <int NPB, int VST>
+cudaError_t launch_dense_variant(const AttnDenseArgs& a, int cols, cudaStream_t s) {
+  const size_t smem = dense_smem_bytes(a.Cpad, NPB, VST);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel<NPB, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  attn_dense_kernel<NPB, VST><<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   if (a.n_tiles <= 0) return cudaSuccess;
   const int Cpad = a.Cpad;
   if (Cpad % 16 || Cpad > 256 || Cpad < 16) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)2 * TM * Cpad * 2 + (size_t)(KST + 1) * 2 * TS * Cpad * 2 + (size_t)2 * TM * TS * 2 + sizeof(DenseSmem) + 128;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   int need = 2 * TS + Cpad, cols = 32;
   while (cols < need) cols <<= 1;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    smem_set = smem;
-  }
-  attn_dense_kernel<<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
-  return cudaGetLastError();
+  if (cols > 512) return cudaErrorInvalidValue;
+  // double-buffer P and V^T when two CTAs still fit per SM (small head dims); otherwise single buffers
+  const size_t limit = 227 * 1024;
+  if (dense_smem_bytes(Cpad, 2, 2) * 2 <= limit + 1024 && cols <= 256) return launch_dense_variant<2, 2>(a, cols, s);
+  if (dense_smem_bytes(Cpad, 2, 2) <= limit) return launch_dense_variant<2, 2>(a, cols, s);
+  if (dense_smem_bytes(Cpad, 1, 1) <= limit) return launch_dense_variant<1, 1>(a, cols, s);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace da
