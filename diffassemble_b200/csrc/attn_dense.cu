@@ -355,14 +355,12 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
           uint32_t h8[8], l8[8];
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
-            const float s0 = __uint_as_float(v[c0 + e]), s1 = __uint_as_float(v[c0 + e + 1]);
-            const bool on0 = (w >> e) & 1u, on1 = (w >> (e + 1)) & 1u;
-            bmax = fmaxf(bmax, on0 ? s0 : -INFINITY);
-            bmax = fmaxf(bmax, on1 ? s1 : -INFINITY);
-            float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
-            float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
-            p0 = on0 ? p0 : 0.f;
-            p1 = on1 ? p1 : 0.f;
+            // masked scores become -inf once: max ignores them and ex2(-inf) = +0 exactly
+            const float s0 = ((w >> e) & 1u) ? __uint_as_float(v[c0 + e]) : -INFINITY;
+            const float s1 = ((w >> (e + 1)) & 1u) ? __uint_as_float(v[c0 + e + 1]) : -INFINITY;
+            bmax = fmaxf(bmax, fmaxf(s0, s1));
+            const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
+            const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
             lsum += p0 + p1;
             const uint32_t h2 = pack_bf16x2(p0, p1);
             h8[e >> 1] = h2;

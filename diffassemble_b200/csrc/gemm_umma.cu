@@ -28,8 +28,9 @@ namespace {
 constexpr int BM = 128;       // rows per tile = UMMA M
 constexpr int BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_PITCH = 36;   // floats per staged row (32 + 4 pad: float4-aligned, conflict-free enough)
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_PITCH = 32;   // floats per staged row; 16-byte chunks are XOR-swizzled by (row & 7) instead of padded
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,7 +109,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * BM * BK * 2 + 2 * BN * BK * 2;   // a_hi, a_lo, w_hi, w_lo
   static constexpr int STAGES = (BN >= 256) ? 2 : ((BN >= 128) ? 3 : 4);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;            // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * EPI_PITCH * 4 /*epilogue staging*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 32 * EPI_PITCH * 4 /*epilogue staging*/;
 };
 
 struct EpiParams {
@@ -143,7 +144,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_ahi); tma_prefetch_desc(&map_alo); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // whole warp: allocate TMEM columns, publish the base address through smem
@@ -204,7 +205,8 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     }
   } else {  // ===== epilogue warps: TMEM -> registers -> smem (transpose) -> coalesced global stores =====
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    float* stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + q * (32 * EPI_PITCH);
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns this warp drains
+    float* stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * EPI_PITCH);
     const int sub_row = lane >> 3;             // read-back mapping: 4 rows x 8 float4 per instruction
     const int sub_col = (lane & 7) * 4;
     int acc = 0; uint32_t acc_phase = 0;
@@ -215,7 +217,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = (BN >= 64 ? half * (BN / 2) : 0); c0 < (BN >= 64 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0)); c0 += 32) {
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
@@ -223,7 +225,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         float4* srow = reinterpret_cast<float4*>(stage + lane * EPI_PITCH);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+          srow[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                 __uint_as_float(r[4 * j + 3]));
         __syncwarp();
         const int col = n0 + c0 + sub_col;
@@ -233,7 +235,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub_row;
           const int row = row_base + rr;
-          float4 v = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + sub_col);
+          float4 v = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((lane & 7) ^ (rr & 7)) << 2));
           v.x = apply_act_rt(v.x + b4.x, p.act); v.y = apply_act_rt(v.y + b4.y, p.act);
           v.z = apply_act_rt(v.z + b4.z, p.act); v.w = apply_act_rt(v.w + b4.w, p.act);
           if (row < p.M) {

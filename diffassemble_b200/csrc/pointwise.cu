@@ -13,19 +13,23 @@ namespace {
 //   here: h = act(P + W1[:, Dv:Dv+64] @ [pos(32), temb(32)]) with P = feats @ W1[:, :Dv]^T + b1
 //   hoisted out of the step loop by da_set_features (it does not depend on x or t).
 // ---------------------------------------------------------------------------------------------
-constexpr int PRO_NB = 8;      // nodes per CTA
+constexpr int PRO_NB = 32;     // nodes per CTA
 constexpr int PRO_NT = 256;
 
 __global__ void __launch_bounds__(PRO_NT)
 prologue_kernel(PrologueArgs a) {
+  extern __shared__ __align__(16) float pro_sm[];   // w1pt_T [64][Hm] staged once per CTA
   __shared__ float xs[PRO_NB][8];
   __shared__ float hid[PRO_NB][16];
   __shared__ float f64[PRO_NB][64];
   __shared__ int ts[PRO_NB];
   const int tid = threadIdx.x;
   const int node0 = blockIdx.x * PRO_NB;
-  if (tid < PRO_NB * 8) {
-    int nb = tid / 8, c = tid % 8, node = node0 + nb;
+  const int Hm = a.Hm;
+  for (int i = tid * 4; i < 64 * Hm; i += PRO_NT * 4)
+    *reinterpret_cast<float4*>(pro_sm + i) = __ldg(reinterpret_cast<const float4*>(a.w1pt_T + i));
+  {
+    int nb = tid / 8, c = tid % 8, node = node0 + nb;   // PRO_NB * 8 == PRO_NT
     xs[nb][c] = (node < a.M && c < a.C_in) ? a.x[(size_t)node * a.C_in + c] : 0.f;
     if (c == 0) {
       int tt = a.t_uniform;
@@ -34,15 +38,15 @@ prologue_kernel(PrologueArgs a) {
     }
   }
   __syncthreads();
-  if (tid < PRO_NB * 16) {  // pos_mlp[0] + GELU
-    int nb = tid / 16, u = tid % 16;
+  for (int idx = tid; idx < PRO_NB * 16; idx += PRO_NT) {  // pos_mlp[0] + GELU
+    int nb = idx / 16, u = idx % 16;
     float s = a.pos_b0[u];
     for (int c = 0; c < a.C_in; ++c) s = fmaf(a.pos_w0[u * a.C_in + c], xs[nb][c], s);
     hid[nb][u] = gelu_erf(s);
   }
   __syncthreads();
-  {  // pos_mlp[2] and the embedding row: PRO_NB * 32 == PRO_NT threads
-    int nb = tid / 32, v = tid % 32;
+  for (int idx = tid; idx < PRO_NB * 32; idx += PRO_NT) {  // pos_mlp[2] and the embedding row
+    int nb = idx / 32, v = idx % 32;
     float s = a.pos_b2[v];
 #pragma unroll
     for (int u = 0; u < 16; ++u) s = fmaf(a.pos_w2[v * 16 + u], hid[nb][u], s);
@@ -50,19 +54,32 @@ prologue_kernel(PrologueArgs a) {
     f64[nb][32 + v] = a.time_emb[(size_t)ts[nb] * 32 + v];
   }
   __syncthreads();
-  const int Hm = a.Hm;
-  for (int idx = tid; idx < PRO_NB * Hm; idx += PRO_NT) {
-    int nb = idx / Hm, n = idx % Hm, node = node0 + nb;
-    if (node >= a.M) continue;
-    float s = a.P ? a.P[(size_t)node * Hm + n] : a.b1[n];
+  // each thread: one output column n for 4 nodes at a time (weights from smem, node features broadcast)
+  for (int idx = tid; idx < (PRO_NB / 4) * Hm; idx += PRO_NT) {
+    const int n = idx % Hm, nb0 = (idx / Hm) * 4;
+    float s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int node = node0 + nb0 + q;
+      s[q] = (a.P && node < a.M) ? a.P[(size_t)node * Hm + n] : a.b1[n];
+    }
 #pragma unroll 8
-    for (int k = 0; k < 64; ++k) s = fmaf(a.w1pt_T[k * Hm + n], f64[nb][k], s);
-    s = apply_act_rt(s, a.act);
-    if (a.out.f32) a.out.f32[(size_t)node * a.out.ldc + n] = s;
-    if (a.out.hi) {
-      __nv_bfloat16 h = __float2bfloat16_rn(s);
-      a.out.hi[(size_t)node * a.out.ld_split + n] = h;
-      a.out.lo[(size_t)node * a.out.ld_split + n] = __float2bfloat16_rn(s - __bfloat162float(h));
+    for (int k = 0; k < 64; ++k) {
+      const float w = pro_sm[k * Hm + n];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] = fmaf(w, f64[nb0 + q][k], s[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int node = node0 + nb0 + q;
+      if (node >= a.M) continue;
+      const float v = apply_act_rt(s[q], a.act);
+      if (a.out.f32) a.out.f32[(size_t)node * a.out.ldc + n] = v;
+      if (a.out.hi) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        a.out.hi[(size_t)node * a.out.ld_split + n] = h;
+        a.out.lo[(size_t)node * a.out.ld_split + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
     }
   }
 }
@@ -192,7 +209,14 @@ __global__ void fill_rows_kernel(float* __restrict__ dst, int ld, const float* _
 cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
   if (a.M <= 0) return cudaSuccess;
   if (a.C_in > 8) return cudaErrorInvalidValue;
-  prologue_kernel<<<(a.M + PRO_NB - 1) / PRO_NB, PRO_NT, 0, s>>>(a);
+  const size_t smem = (size_t)64 * a.Hm * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 - 12 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  prologue_kernel<<<(a.M + PRO_NB - 1) / PRO_NB, PRO_NT, smem, s>>>(a);
   return cudaGetLastError();
 }
 
