@@ -63,7 +63,7 @@ struct da_handle {
   DensePlan plan;      // bitmap tiles + residual CSR (attn_mode = AUTO)
   bool use_plan = false;
   int num_real = 0, num_total = 0;
-  DevBuf qimg, kimg, vimg, dacc, dstats;
+  DevBuf qimg, kimg, vimg, qimg_l, kimg_l, vimg_l, dacc, dstats;   // operand images: hidden layers / last layer
   // activations / workspace
   DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
   // split-bf16 operand planes for the tensor-core path
@@ -81,7 +81,7 @@ struct da_handle {
   }
   size_t workspace_bytes() const {
     const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats, &qimg, &kimg, &vimg,
-                           &dacc, &dstats,
+                           &qimg_l, &kimg_l, &vimg_l, &dacc, &dstats,
                            &feats_sp_hi, &feats_sp_lo, &h_hi, &h_lo, &comb_hi, &comb_lo, &xa_hi, &xa_lo,
                            &xb_hi, &xb_lo, &r_hi, &r_lo};
     size_t s = 0;
@@ -187,20 +187,27 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
   for (int l = 0; l < L; ++l) {
     const int HC = layer_hc(h, l), C = HC / c.heads;
     const bool last = (l == L - 1);
+    const bool dense = h->use_plan && h->plan.n_tiles > 0;
+    const int Cpad = (C + 15) / 16 * 16;
+    __nv_bfloat16* qimg = (last ? h->qimg_l : h->qimg).as<__nv_bfloat16>();
+    __nv_bfloat16* kimg = (last ? h->kimg_l : h->kimg).as<__nv_bfloat16>();
+    __nv_bfloat16* vimg = (last ? h->vimg_l : h->vimg).as<__nv_bfloat16>();
     {
       LinearOut o; o.f32 = h->qkvs.as<float>(); o.ldc = 4 * HC;
+      if (dense && umma) {  // Q / K / V operand images straight from the GEMM epilogue
+        o.img_node_slot = h->plan.node_slot; o.qimg = qimg; o.kimg = kimg; o.vimg = vimg;
+        o.img_H = c.heads; o.img_C = C; o.img_Cpad = Cpad; o.img_rows = Mr;
+      }
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
       DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
-    const bool dense = h->use_plan && h->plan.n_tiles > 0;
     const CsrGraph& csr = h->use_plan ? h->plan.residual : h->csr;
     if (dense) {  // bitmap edges on the tensor cores; the CSR kernel below continues with the residual edges
-      const int Cpad = (C + 15) / 16 * 16;
       PackArgs pa{};
       pa.qkvs = h->qkvs.as<float>(); pa.ld = 4 * HC; pa.node_slot = h->plan.node_slot; pa.n = Mr;
       pa.H = c.heads; pa.C = C; pa.Cpad = Cpad;
-      pa.qimg = h->qimg.as<__nv_bfloat16>(); pa.kimg = h->kimg.as<__nv_bfloat16>(); pa.vimg = h->vimg.as<__nv_bfloat16>();
-      {
+      pa.qimg = qimg; pa.kimg = kimg; pa.vimg = vimg;
+      if (!umma) {  // exact-fp32 GEMM mode: separate repack pass
         Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
         DA_CK(launch_pack_images(pa, s), "pack images");
       }
@@ -354,7 +361,7 @@ void da_destroy(da_handle* h) {
                    &h->headb_b, &h->headr_w, &h->headr_b, &h->virt_emb, &h->P, &h->hbuf, &h->combined, &h->qkvs,
                    &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
                    &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
-                   &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->dacc, &h->dstats};
+                   &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l, &h->dacc, &h->dstats};
   for (auto* b : all) b->release();
   free_csr(&h->csr);
   free_plan(&h->plan);
@@ -539,13 +546,14 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
     DA_CK(h->r.ensure(Mt * D * sizeof(float)));
   }
   if (h->use_plan && h->plan.n_tiles > 0) {
-    const size_t img = dense_image_elems(h->plan.n_tiles, c.heads, cpad_max) * sizeof(__nv_bfloat16);
-    const bool fresh = img > h->vimg.bytes;
-    DA_CK(h->qimg.ensure(img)); DA_CK(h->kimg.ensure(img)); DA_CK(h->vimg.ensure(img));
-    if (fresh || true) {  // padded rows / channels must read as finite zeros
-      DA_CK(cudaMemsetAsync(h->qimg.p, 0, h->qimg.bytes, s));
-      DA_CK(cudaMemsetAsync(h->kimg.p, 0, h->kimg.bytes, s));
-      DA_CK(cudaMemsetAsync(h->vimg.p, 0, h->vimg.bytes, s));
+    // padded rows / channels of the operand images must read as zeros: clear once per graph; the
+    // epilogues only ever write real rows and real channels (hidden and last layers own separate images)
+    const size_t img_h = dense_image_elems(h->plan.n_tiles, c.heads, (c_hid + 15) / 16 * 16) * sizeof(__nv_bfloat16);
+    const size_t img_l = dense_image_elems(h->plan.n_tiles, c.heads, (c_last + 15) / 16 * 16) * sizeof(__nv_bfloat16);
+    DevBuf* imgs[6] = {&h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l};
+    for (int i = 0; i < 6; ++i) {
+      DA_CK(imgs[i]->ensure(i < 3 ? img_h : img_l));
+      DA_CK(cudaMemsetAsync(imgs[i]->p, 0, imgs[i]->bytes, s));
     }
     DA_CK(h->dacc.ensure(Mr * (size_t)(D > hid ? D : hid) * sizeof(float)));
     DA_CK(h->dstats.ensure(Mr * (size_t)c.heads * 2 * sizeof(float)));

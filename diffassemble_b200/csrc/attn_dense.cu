@@ -114,7 +114,8 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
 // ---- image layout ---------------------------------------------------------------------------------
 // Q image of (tile t, head h):   [plane 2][k-chunk Cpad/8][row 128][8]            bf16
 // K image of (block b, head h):  [plane 2][k-chunk Cpad/8][row 64][8]
-// V^T image of (block b, head h):[plane 2][src-chunk 8][channel Cpad][8 sources]
+// V image of (block b, head h):  same layout as K; tcgen05.mma reads it as an MN-major B operand
+//                                (N = channels contiguous in 16-byte units, K = sources 16 bytes apart)
 __host__ __device__ inline size_t q_block_elems(int Cpad) { return (size_t)2 * TM * Cpad; }
 __host__ __device__ inline size_t kv_block_elems(int Cpad) { return (size_t)2 * TS * Cpad; }
 
@@ -155,20 +156,11 @@ __global__ void pack_images_kernel(PackArgs a) {
       const size_t off = (size_t)ch * (TM * 8) + (size_t)r * 8;
       *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(base + (size_t)TM * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
-    } else if (part == 1) {
-      __nv_bfloat16* base = a.kimg + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
+    } else {  // K and V share one layout; V is consumed as an MN-major B operand
+      __nv_bfloat16* base = (part == 1 ? a.kimg : a.vimg) + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
       const size_t off = (size_t)ch * (TS * 8) + (size_t)rb * 8;
       *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
       *reinterpret_cast<uint4*>(base + (size_t)TS * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
-    } else {
-      __nv_bfloat16* base = a.vimg + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
-      const size_t off0 = (size_t)(rb >> 3) * (a.Cpad * 8) + (rb & 7);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const size_t off = off0 + (size_t)(c + e) * 8;
-        base[off] = hi[e];
-        base[(size_t)TS * a.Cpad + off] = lo[e];
-      }
     }
   }
 }
@@ -257,7 +249,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad);
+      const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad) | (1u << 16);  // bit 16: B is MN-major
       const uint32_t q_hi = smem_u32(q_sm), q_lo = q_hi + q_plane;
       const int ksteps = Cpad / 16;
       auto issue_s = [&](int j) {
@@ -297,8 +289,10 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         for (int kk = 0; kk < TS / 16; ++kk) {
           const uint64_t ap_hi = make_desc_nosw(p_hi + kk * 2 * (TM * 16), TM * 16, 128);
           const uint64_t ap_lo = make_desc_nosw(p_lo + kk * 2 * (TM * 16), TM * 16, 128);
-          const uint64_t bv_hi = make_desc_nosw(v_hi + kk * 2 * (Cpad * 16), Cpad * 16, 128);
-          const uint64_t bv_lo = make_desc_nosw(v_lo + kk * 2 * (Cpad * 16), Cpad * 16, 128);
+          // MN-major B: 8 sources x 8 channels per core matrix (sources 16 B apart); LBO = next 8 sources
+          // (128 B), SBO = next 8 channels (TS * 16 B); one k-step = 16 sources = 256 B
+          const uint64_t bv_hi = make_desc_nosw(v_hi + kk * 256, 128, TS * 16);
+          const uint64_t bv_lo = make_desc_nosw(v_lo + kk * 256, 128, TS * 16);
           tc_mma_bf16(tmem_o, ap_hi, bv_hi, idesc_o, (j | kk) ? 1u : 0u);
           tc_mma_bf16(tmem_o, ap_hi, bv_lo, idesc_o, 1u);
           tc_mma_bf16(tmem_o, ap_lo, bv_hi, idesc_o, 1u);

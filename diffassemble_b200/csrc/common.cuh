@@ -51,6 +51,14 @@ struct LinearOut {
   __nv_bfloat16* hi = nullptr;   // split-bf16 planes [M, ld_split] (operand of the next tensor-core GEMM)
   __nv_bfloat16* lo = nullptr;
   int ld_split = 0;
+  // optional: the output columns are [Q | K | V | skip] (each H*C wide) and Q / K / V are ALSO written as
+  // the split-bf16 operand images of the dense-tile attention (attn_dense.cu), fusing pack_images_kernel
+  // into the GEMM epilogue.  node_slot[row] >= 0 selects rows that belong to a dense tile.
+  const int32_t* img_node_slot = nullptr;
+  __nv_bfloat16* qimg = nullptr;
+  __nv_bfloat16* kimg = nullptr;
+  __nv_bfloat16* vimg = nullptr;
+  int img_H = 0, img_C = 0, img_Cpad = 0, img_rows = 0;   // img_rows: rows [0, img_rows) have a node_slot entry
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).

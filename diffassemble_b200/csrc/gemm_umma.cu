@@ -117,6 +117,9 @@ struct EpiParams {
   float* cf; int ldc;
   __nv_bfloat16* chi; __nv_bfloat16* clo; int ldsp;
   int M, N, K, act;
+  // fused operand-image output (see LinearOut)
+  const int32_t* node_slot; __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
+  int iH, iC, iCpad, irows;
 };
 
 template <int BN>
@@ -253,6 +256,49 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             }
           }
         }
+        if (p.node_slot != nullptr) {
+          // operand images: 8 consecutive channels (16 bytes of bf16) per lane, 8 rows per instruction
+          const int HC = p.iH * p.iC;
+          const int g_col = n0 + c0 + (lane & 3) * 8;
+          const int part = g_col / HC;
+          if (part < 3) {
+            const int within = g_col - part * HC;
+            const int h = within / p.iC, c = within - h * p.iC;
+            float4 bb0 = make_float4(0.f, 0.f, 0.f, 0.f), bb1 = bb0;
+            if (p.bias) { bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col)); bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col + 4)); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + (lane >> 2);
+              const int row = row_base + rr;
+              const int slot = (row < p.irows) ? __ldg(p.node_slot + row) : -1;
+              const int ch0 = (lane & 3) * 2;
+              const float4 v0 = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((ch0) ^ (rr & 7)) << 2));
+              const float4 v1 = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((ch0 + 1) ^ (rr & 7)) << 2));
+              if (slot < 0) continue;
+              const float vv[8] = {v0.x + bb0.x, v0.y + bb0.y, v0.z + bb0.z, v0.w + bb0.w,
+                                   v1.x + bb1.x, v1.y + bb1.y, v1.z + bb1.z, v1.w + bb1.w};
+              __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                hi[e] = __float2bfloat16_rn(vv[e]);
+                lo[e] = __float2bfloat16_rn(vv[e] - __bfloat162float(hi[e]));
+              }
+              if (part == 0) {
+                const int tile_i = slot >> 7, r_ = slot & 127;
+                __nv_bfloat16* base = p.qimg + ((size_t)tile_i * p.iH + h) * ((size_t)2 * 128 * p.iCpad);
+                const size_t off = (size_t)(c >> 3) * (128 * 8) + (size_t)r_ * 8;
+                *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+                *reinterpret_cast<uint4*>(base + (size_t)128 * p.iCpad + off) = *reinterpret_cast<uint4*>(lo);
+              } else {
+                const int blk = slot >> 6, rb = slot & 63;
+                __nv_bfloat16* base = (part == 1 ? p.kimg : p.vimg) + ((size_t)blk * p.iH + h) * ((size_t)2 * 64 * p.iCpad);
+                const size_t off = (size_t)(c >> 3) * (64 * 8) + (size_t)rb * 8;   // K and V share one layout
+                *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+                *reinterpret_cast<uint4*>(base + (size_t)64 * p.iCpad + off) = *reinterpret_cast<uint4*>(lo);
+              }
+            }
+          }
+        }
         __syncwarp();
       }
       tc_fence_before();
@@ -359,7 +405,9 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K % BK || N % 32 || (lda % 8) || (ldw % 8)) return cudaErrorInvalidValue;
   if ((out.f32 && out.ldc % 4) || (out.hi && out.ld_split % 8)) return cudaErrorInvalidValue;
-  EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act};
+  EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act,
+              out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows};
+  if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
   if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   return launch_bn<32>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
