@@ -216,11 +216,22 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int row_base = m0 + q * 32;
+      int slots[4] = {-1, -1, -1, -1};
+      if (p.node_slot != nullptr) {   // issued before the accumulator wait so the latency is hidden
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row_base + i * 8 + (lane >> 2);
+          if (row < p.irows) slots[i] = __ldg(p.node_slot + row);
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c0 = (BN >= 64 ? half * (BN / 2) : 0); c0 < (BN >= 64 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0)); c0 += 32) {
+        const int col = n0 + c0 + sub_col;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
@@ -231,9 +242,6 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           srow[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                 __uint_as_float(r[4 * j + 3]));
         __syncwarp();
-        const int col = n0 + c0 + sub_col;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub_row;
@@ -270,7 +278,8 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             for (int i = 0; i < 4; ++i) {
               const int rr = i * 8 + (lane >> 2);
               const int row = row_base + rr;
-              const int slot = (row < p.irows) ? __ldg(p.node_slot + row) : -1;
+              const int slot = slots[i];
+              (void)row;
               const int ch0 = (lane & 3) * 2;
               const float4 v0 = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((ch0) ^ (rr & 7)) << 2));
               const float4 v1 = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((ch0 + 1) ^ (rr & 7)) << 2));
