@@ -28,6 +28,7 @@ constexpr int TM = 128;   // targets per tile (UMMA M)
 constexpr int TS = 64;    // sources per block (UMMA N of S, K of PV)
 constexpr int NT = 192;
 constexpr int KST = 2;    // K ring depth
+constexpr int VST = 2;    // V ring depth
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -168,9 +169,10 @@ __global__ void pack_images_kernel(PackArgs a) {
 struct DenseSmem {
   uint64_t q_full;
   uint64_t k_full[KST], k_empty[KST];
-  uint64_t v_full[2], v_empty[2];
-  uint64_t s_full[2], s_empty[2];
-  uint64_t p_full[2], pv_done[2];
+  uint64_t v_full[VST], v_empty[VST];
+  uint64_t s_full[2];    // MMA -> softmax: S_j is in TMEM buffer j & 1
+  uint64_t p_full[2];    // softmax -> MMA: P_j (bf16 hi/lo) has replaced S_j in the same TMEM columns
+  uint64_t pv_done[2];   // MMA -> both:   P_j V_j retired (buffer free again, O holds blocks <= j)
   uint32_t tmem_base;
 };
 
@@ -179,18 +181,26 @@ struct DenseSmem {
 // rare, and the result is mathematically identical (any reference point cancels in acc / l).
 constexpr float LAZY_LOG2 = 8.0f;
 
-// NPB = number of P buffers in shared memory, VST = number of V^T stages (both 2 when they fit).
-template <int NPB, int VST>
+// A-operand-from-TMEM form of tcgen05.mma (P never touches shared memory)
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __global__ void __launch_bounds__(NT)
 attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int Cpad = a.Cpad;
-  const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2, p_plane = TM * TS * 2;  // bytes
+  const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2;  // bytes
   uint8_t* q_sm = smem;                                   // 2 planes
   uint8_t* k_sm = q_sm + 2 * q_plane;                     // KST stages x 2 planes
   uint8_t* v_sm = k_sm + KST * 2 * kv_plane;              // VST stages x 2 planes
-  uint8_t* p_sm = v_sm + VST * 2 * kv_plane;              // NPB buffers x 2 planes
-  DenseSmem* sh = reinterpret_cast<DenseSmem*>(p_sm + NPB * 2 * p_plane);
+  DenseSmem* sh = reinterpret_cast<DenseSmem*>(v_sm + VST * 2 * kv_plane);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / a.H, head = blockIdx.x % a.H;
@@ -200,11 +210,8 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   if (threadIdx.x == 0) {
     mbar_init(&sh->q_full, 1);
     for (int i = 0; i < KST; ++i) { mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
-      mbar_init(&sh->s_full[i], 1); mbar_init(&sh->s_empty[i], 4);
-      mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1);
-    }
+    for (int i = 0; i < VST; ++i) { mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -215,11 +222,11 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-  const uint32_t tmem_s = tmem_base;             // 2 x TS columns
+  const uint32_t tmem_s = tmem_base;             // 2 x TS columns: S_j (fp32), later P_j (bf16 hi | lo)
   const uint32_t tmem_o = tmem_base + 2 * TS;    // Cpad columns
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== bulk-copy producer: K runs two blocks ahead, V^T VST blocks ahead =====
+    if (lane == 0) {  // ===== bulk-copy producer: K and V blocks run two ahead =====
       const __nv_bfloat16* qsrc = a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cpad);
       mbar_expect_tx(&sh->q_full, 2 * q_plane);
       bulk_load(q_sm, qsrc, 2 * q_plane, &sh->q_full);
@@ -276,28 +283,26 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         if (j + 1 < nblk) {
           const int jn = j + 1;
           mbar_wait(&sh->k_full[jn % KST], (jn / KST) & 1);
-          if (jn >= 2) mbar_wait(&sh->s_empty[jn & 1], ((jn >> 1) - 1) & 1);  // softmax released this S buffer
+          if (jn >= 2) mbar_wait(&sh->pv_done[jn & 1], ((jn >> 1) - 1) & 1);  // P_{jn-2} consumed: buffer free
           tc_fence_after();
           issue_s(jn);
         }
-        const int pb = j % NPB, vs = j % VST;
-        mbar_wait(&sh->p_full[pb], (j / NPB) & 1);   // P_j in smem (and O corrected if needed)
+        const int b = j & 1, vs = j % VST;
+        mbar_wait(&sh->p_full[b], (j >> 1) & 1);   // P_j in TMEM (and O corrected if needed)
         mbar_wait(&sh->v_full[vs], (j / VST) & 1);
         tc_fence_after();
-        const uint32_t p_hi = smem_u32(p_sm + pb * 2 * p_plane), p_lo = p_hi + p_plane;
+        const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;   // packed bf16: 2 sources per column
         const uint32_t v_hi = smem_u32(v_sm + vs * 2 * kv_plane), v_lo = v_hi + kv_plane;
         for (int kk = 0; kk < TS / 16; ++kk) {
-          const uint64_t ap_hi = make_desc_nosw(p_hi + kk * 2 * (TM * 16), TM * 16, 128);
-          const uint64_t ap_lo = make_desc_nosw(p_lo + kk * 2 * (TM * 16), TM * 16, 128);
           // MN-major B: 8 sources x 8 channels per core matrix (sources 16 B apart); LBO = next 8 sources
-          // (128 B), SBO = next 8 channels (TS * 16 B); one k-step = 16 sources = 256 B
+          // (128 B), SBO = next 8 channels (TS * 16 B); one k-step = 16 sources = 256 B = 8 TMEM columns of P
           const uint64_t bv_hi = make_desc_nosw(v_hi + kk * 256, 128, TS * 16);
           const uint64_t bv_lo = make_desc_nosw(v_lo + kk * 256, 128, TS * 16);
-          tc_mma_bf16(tmem_o, ap_hi, bv_hi, idesc_o, (j | kk) ? 1u : 0u);
-          tc_mma_bf16(tmem_o, ap_hi, bv_lo, idesc_o, 1u);
-          tc_mma_bf16(tmem_o, ap_lo, bv_hi, idesc_o, 1u);
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, bv_hi, idesc_o, (j | kk) ? 1u : 0u);
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, bv_lo, idesc_o, 1u);
+          tc_mma_bf16_ts(tmem_o, p_lo + kk * 8, bv_hi, idesc_o, 1u);
         }
-        tc_commit(&sh->pv_done[pb]);
+        tc_commit(&sh->pv_done[b]);
         tc_commit(&sh->v_empty[vs]);
       }
     }
@@ -315,9 +320,6 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       const int b = j & 1;
       const uint2 bits = bits_next;
       if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (j + 1) * 2);
-      const int pb = j % NPB;
-      uint8_t* p_hi = p_sm + pb * 2 * p_plane;
-      uint8_t* p_lo = p_hi + p_plane;
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
@@ -333,8 +335,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         }
       }
       bool prev_done = (j == 0);            // has pv_done of block j-1 been observed?
-      if (NPB == 2 && j >= 2) mbar_wait(&sh->pv_done[pb], ((j >> 1) - 1) & 1);  // P buffer pb is free again
-      uint32_t hi[NPB == 1 ? TS / 2 : 1], lo[NPB == 1 ? TS / 2 : 1];
+      uint32_t ph[TS / 2], pl[TS / 2];      // P_j as packed bf16 pairs (hi and lo planes)
       float lsum, bmax;
       while (true) {
         const float m_sub = (m == -INFINITY) ? 0.f : m * c_log2;
@@ -344,33 +345,18 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
         tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < TS; c0 += 16) {
-          const uint32_t w = (c0 < 32) ? (bits.x >> c0) : (bits.y >> (c0 - 32));
-          uint32_t h8[8], l8[8];
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            // masked scores become -inf once: max ignores them and ex2(-inf) = +0 exactly
-            const float s0 = ((w >> e) & 1u) ? __uint_as_float(v[c0 + e]) : -INFINITY;
-            const float s1 = ((w >> (e + 1)) & 1u) ? __uint_as_float(v[c0 + e + 1]) : -INFINITY;
-            bmax = fmaxf(bmax, fmaxf(s0, s1));
-            const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
-            const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
-            lsum += p0 + p1;
-            const uint32_t h2 = pack_bf16x2(p0, p1);
-            h8[e >> 1] = h2;
-            l8[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
-          }
-          if (NPB == 1) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { hi[(c0 >> 1) + e] = h8[e]; lo[(c0 >> 1) + e] = l8[e]; }
-          } else {
-            // source chunks (c0 / 8) and (c0 / 8) + 1: 16 bytes each at [chunk][r][8]
-            const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
-            *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
-            *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(h8[4], h8[5], h8[6], h8[7]);
-            *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
-            *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(l8[4], l8[5], l8[6], l8[7]);
-          }
+        for (int e = 0; e < TS; e += 2) {
+          const uint32_t w = (e < 32) ? bits.x : bits.y;
+          // masked scores become -inf once: max ignores them and ex2(-inf) = +0 exactly
+          const float s0 = ((w >> (e & 31)) & 1u) ? __uint_as_float(v[e]) : -INFINITY;
+          const float s1 = ((w >> ((e + 1) & 31)) & 1u) ? __uint_as_float(v[e + 1]) : -INFINITY;
+          bmax = fmaxf(bmax, fmaxf(s0, s1));
+          const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
+          const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
+          lsum += p0 + p1;
+          const uint32_t h2 = pack_bf16x2(p0, p1);
+          ph[e >> 1] = h2;
+          pl[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
         }
         const bool exceeded = bmax > m + tau_raw;   // also true when m == -inf and the block has an edge
         if (!__any_sync(0xffffffffu, exceeded)) break;
@@ -378,7 +364,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         const float m_new = exceeded ? bmax : m;
         const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
         if (!prev_done) {
-          mbar_wait(&sh->pv_done[(j - 1) % NPB], ((j - 1) / NPB) & 1);   // O holds every block < j
+          mbar_wait(&sh->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // O holds every block < j
           tc_fence_after();
           prev_done = true;
         }
@@ -397,25 +383,18 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         m = m_new;
       }
       l += lsum;
-      if (NPB == 1) {
-        if (!prev_done) mbar_wait(&sh->pv_done[0], (j - 1) & 1);   // single P buffer: PV_{j-1} must have read it
-#pragma unroll
-        for (int c0 = 0; c0 < TS; c0 += 16) {
-          const uint32_t o0 = (uint32_t)(c0 >> 3) * (TM * 16) + (uint32_t)r * 16;
-          const int i0 = c0 >> 1;
-          *reinterpret_cast<uint4*>(p_hi + o0) = make_uint4(hi[i0], hi[i0 + 1], hi[i0 + 2], hi[i0 + 3]);
-          *reinterpret_cast<uint4*>(p_hi + o0 + TM * 16) = make_uint4(hi[i0 + 4], hi[i0 + 5], hi[i0 + 6], hi[i0 + 7]);
-          *reinterpret_cast<uint4*>(p_lo + o0) = make_uint4(lo[i0], lo[i0 + 1], lo[i0 + 2], lo[i0 + 3]);
-          *reinterpret_cast<uint4*>(p_lo + o0 + TM * 16) = make_uint4(lo[i0 + 4], lo[i0 + 5], lo[i0 + 6], lo[i0 + 7]);
-        }
-      }
+      // P_j replaces S_j in place (every S value of this row is already in registers): hi | lo planes
+      tmem_st16(s_addr, ph);
+      tmem_st16(s_addr + 16, ph + 16);
+      tmem_st16(s_addr + 32, pl);
+      tmem_st16(s_addr + 48, pl + 16);
+      tmem_st_wait();
       tc_fence_before();
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy P stores -> async proxy (MMA)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&sh->p_full[pb]); mbar_arrive(&sh->s_empty[b]); }
+      if (lane == 0) mbar_arrive(&sh->p_full[b]);
     }
     // epilogue: un-normalised O and (m, l) to global
-    mbar_wait(&sh->pv_done[(nblk - 1) % NPB], ((nblk - 1) / NPB) & 1);
+    mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
     const int node = ti.node0 + r;
     const int HC = a.H * a.C;
@@ -464,24 +443,6 @@ cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-namespace {
-size_t dense_smem_bytes(int Cpad, int npb, int vst) {
-  return (size_t)2 * TM * Cpad * 2 + (size_t)(KST + vst) * 2 * TS * Cpad * 2 + (size_t)npb * 2 * TM * TS * 2 + sizeof(DenseSmem) + 128;
-}
-template <int NPB, int VST>
-cudaError_t launch_dense_variant(const AttnDenseArgs& a, int cols, cudaStream_t s) {
-  const size_t smem = dense_smem_bytes(a.Cpad, NPB, VST);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel<NPB, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    smem_set = smem;
-  }
-  attn_dense_kernel<NPB, VST><<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
-  return cudaGetLastError();
-}
-}  // namespace
-
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   if (a.n_tiles <= 0) return cudaSuccess;
   const int Cpad = a.Cpad;
@@ -489,12 +450,16 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   int need = 2 * TS + Cpad, cols = 32;
   while (cols < need) cols <<= 1;
   if (cols > 512) return cudaErrorInvalidValue;
-  // double-buffer P and V^T when two CTAs still fit per SM (small head dims); otherwise single buffers
-  const size_t limit = 227 * 1024;
-  if (dense_smem_bytes(Cpad, 2, 2) * 2 <= limit + 1024 && cols <= 256) return launch_dense_variant<2, 2>(a, cols, s);
-  if (dense_smem_bytes(Cpad, 2, 2) <= limit) return launch_dense_variant<2, 2>(a, cols, s);
-  if (dense_smem_bytes(Cpad, 1, 1) <= limit) return launch_dense_variant<1, 1>(a, cols, s);
-  return cudaErrorInvalidValue;
+  const size_t smem = (size_t)2 * TM * Cpad * 2 + (size_t)(KST + VST) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  attn_dense_kernel<<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
+  return cudaGetLastError();
 }
 
 }  // namespace da
