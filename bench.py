@@ -82,7 +82,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -221,17 +221,27 @@ def run_b200(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(loops):
+        loop_s = []
+
+        def one_loop():
             ei_d = ei_h.to(device, non_blocking=True)
             batch_d = batch_h.to(device, non_blocking=True)
             feats_d = feats_h.to(device, non_blocking=True)
             imgs, _ = mod.p_sample_loop((M, 4), feats_d, ei_d, batch_d)
-            for s, img in enumerate(imgs):
-                host_out[s].copy_(img, non_blocking=True)
+            for s_, img in enumerate(imgs):
+                host_out[s_].copy_(img, non_blocking=True)
             if world > 1:
                 sharding.gather_poses(imgs[-1], [M] * world)
             torch.cuda.synchronize()
+
+        one_loop()  # untimed warm-up loop (first-use allocations, like the W warm-up steps of the device arm)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(loops):
+            tl = time.perf_counter()
+            one_loop()
+            loop_s.append(time.perf_counter() - tl)
         dt = time.perf_counter() - t0
         if world > 1:
             tdt = torch.tensor([dt], device=device)
@@ -240,8 +250,9 @@ def run_b200(args):
         nsteps = loops * len(sched)
         h2d = (ei_h.numel() * 8 + batch_h.numel() * 8 + feats_h.numel() * 4) / len(sched)
         e2e = {"value": w["B"] * world * nsteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(M * 4 * 4), "api": "GNN_Diffusion.p_sample_loop (DDIM, 30 steps/loop), pinned host inputs",
-               "loops": loops}
+               "d2h_bytes_per_step": int(M * 4 * 4), "api": "GNN_Diffusion.p_sample_loop (DDIM, 30 steps/loop): pinned host topology + features uploaded and the "
+                      "graph re-planned every loop, every step's x_t read back to pinned host memory",
+               "loops": loops, "loop_seconds": [round(x, 4) for x in loop_s]}
 
     if rank != 0:
         if world > 1:
@@ -404,13 +415,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3_exphander60_v8", choices=sorted(WORKLOADS))
     ap.add_argument("--gemm", default="bf16x3", choices=["fp32", "bf16x3"])
     ap.add_argument("--attn", default="auto", choices=["csr", "auto"])
-    ap.add_argument("--e2e-loops", type=int, default=2)
+    ap.add_argument("--e2e-loops", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

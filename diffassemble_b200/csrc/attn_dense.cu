@@ -27,8 +27,7 @@ namespace {
 constexpr int TM = 128;   // targets per tile (UMMA M)
 constexpr int TS = 64;    // sources per block (UMMA N of S, K of PV)
 constexpr int NT = 192;
-constexpr int KST = 2;    // K ring depth
-constexpr int VST = 2;    // V ring depth
+constexpr int MAXST = 4;  // maximum K / V ring depth (2 when the head dim is too large for more)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -168,8 +167,8 @@ __global__ void pack_images_kernel(PackArgs a) {
 
 struct DenseSmem {
   uint64_t q_full;
-  uint64_t k_full[KST], k_empty[KST];
-  uint64_t v_full[VST], v_empty[VST];
+  uint64_t k_full[MAXST], k_empty[MAXST];
+  uint64_t v_full[MAXST], v_empty[MAXST];
   uint64_t s_full[2];    // MMA -> softmax: S_j is in TMEM buffer j & 1
   uint64_t p_full[2];    // softmax -> MMA: P_j (bf16 hi/lo) has replaced S_j in the same TMEM columns
   uint64_t pv_done[2];   // MMA -> both:   P_j V_j retired (buffer free again, O holds blocks <= j)
@@ -192,10 +191,15 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 
+// CPAD_T: padded head dim as a compile-time constant (0 = take it from the arguments); ST: K / V ring
+// depth (power of two).  The single MMA-issuing thread is on the critical path of every block, so its
+// loops are fully unrolled and every operand descriptor is "base + immediate".
+template <int CPAD_T, int ST>
 __global__ void __launch_bounds__(NT)
 attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int Cpad = a.Cpad;
+  constexpr int KST = ST, VST = ST;
+  const int Cpad = CPAD_T ? CPAD_T : a.Cpad;
   const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2;  // bytes
   uint8_t* q_sm = smem;                                   // 2 planes
   uint8_t* k_sm = q_sm + 2 * q_plane;                     // KST stages x 2 planes
@@ -209,8 +213,10 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
 
   if (threadIdx.x == 0) {
     mbar_init(&sh->q_full, 1);
-    for (int i = 0; i < KST; ++i) { mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1); }
-    for (int i = 0; i < VST; ++i) { mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1); }
+    for (int i = 0; i < MAXST; ++i) {
+      mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1);
+      mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -232,12 +238,12 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       bulk_load(q_sm, qsrc, 2 * q_plane, &sh->q_full);
       auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad); };
       auto load_k = [&](int j) {
-        const int st = j % KST;
+        const int st = j & (KST - 1);
         mbar_expect_tx(&sh->k_full[st], 2 * kv_plane);
         bulk_load(k_sm + st * 2 * kv_plane, a.kimg + blk_off(j), 2 * kv_plane, &sh->k_full[st]);
       };
       auto load_v = [&](int j) {
-        const int st = j % VST;
+        const int st = j & (VST - 1);
         mbar_expect_tx(&sh->v_full[st], 2 * kv_plane);
         bulk_load(v_sm + st * 2 * kv_plane, a.vimg + blk_off(j), 2 * kv_plane, &sh->v_full[st]);
       };
@@ -245,11 +251,11 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       for (int j = 0; j < VST && j < nblk; ++j) load_v(j);
       for (int j = 0; j < nblk; ++j) {
         if (j + KST < nblk) {  // slot j % KST is free once S_j (its (j / KST)-th user) has retired
-          mbar_wait(&sh->k_empty[j % KST], (j / KST) & 1);
+          mbar_wait(&sh->k_empty[j & (KST - 1)], (j / KST) & 1);
           load_k(j + KST);
         }
         if (j + VST < nblk) {
-          mbar_wait(&sh->v_empty[j % VST], (j / VST) & 1);
+          mbar_wait(&sh->v_empty[j & (VST - 1)], (j / VST) & 1);
           load_v(j + VST);
         }
       }
@@ -257,23 +263,26 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad) | (1u << 16);  // bit 16: B is MN-major
-      const uint32_t q_hi = smem_u32(q_sm), q_lo = q_hi + q_plane;
       const int ksteps = Cpad / 16;
+      // descriptor bases; per-MMA descriptors are base + (byte offset >> 4) in the 14-bit address field
+      const uint64_t dq_hi = make_desc_nosw(smem_u32(q_sm), TM * 16, 128), dq_lo = dq_hi + (q_plane >> 4);
+      const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
+      const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);   // MN-major B: LBO = next 8 sources, SBO = next 8 channels
+      const uint32_t stage_u = (2 * kv_plane) >> 4, plane_u = kv_plane >> 4;
       auto issue_s = [&](int j) {
-        const uint32_t k_hi = smem_u32(k_sm + (j % KST) * 2 * kv_plane), k_lo = k_hi + kv_plane;
+        const uint64_t dk_hi = dk0 + (uint32_t)(j & (KST - 1)) * stage_u, dk_lo = dk_hi + plane_u;
         const uint32_t d = tmem_s + (uint32_t)((j & 1) * TS);
-        for (int kk = 0; kk < ksteps; ++kk) {
+#pragma unroll
+        for (int kk = 0; kk < (CPAD_T ? CPAD_T / 16 : 16); ++kk) {
+          if (!CPAD_T && kk >= ksteps) break;
           // one k-step = 16 channels = 2 chunks; Q chunk stride TM*16 B, K chunk stride TS*16 B
-          const uint64_t aq_hi = make_desc_nosw(q_hi + kk * 2 * (TM * 16), TM * 16, 128);
-          const uint64_t aq_lo = make_desc_nosw(q_lo + kk * 2 * (TM * 16), TM * 16, 128);
-          const uint64_t bk_hi = make_desc_nosw(k_hi + kk * 2 * (TS * 16), TS * 16, 128);
-          const uint64_t bk_lo = make_desc_nosw(k_lo + kk * 2 * (TS * 16), TS * 16, 128);
-          tc_mma_bf16(d, aq_hi, bk_hi, idesc_s, kk ? 1u : 0u);
-          tc_mma_bf16(d, aq_hi, bk_lo, idesc_s, 1u);
-          tc_mma_bf16(d, aq_lo, bk_hi, idesc_s, 1u);
+          const uint32_t qo = (uint32_t)kk * ((2 * TM * 16) >> 4), ko = (uint32_t)kk * ((2 * TS * 16) >> 4);
+          tc_mma_bf16(d, dq_hi + qo, dk_hi + ko, idesc_s, kk ? 1u : 0u);
+          tc_mma_bf16(d, dq_hi + qo, dk_lo + ko, idesc_s, 1u);
+          tc_mma_bf16(d, dq_lo + qo, dk_hi + ko, idesc_s, 1u);
         }
         tc_commit(&sh->s_full[j & 1]);
-        tc_commit(&sh->k_empty[j % KST]);
+        tc_commit(&sh->k_empty[j & (KST - 1)]);
       };
       mbar_wait(&sh->q_full, 0);
       mbar_wait(&sh->k_full[0], 0);
@@ -282,25 +291,23 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) {
           const int jn = j + 1;
-          mbar_wait(&sh->k_full[jn % KST], (jn / KST) & 1);
+          mbar_wait(&sh->k_full[jn & (KST - 1)], (jn / KST) & 1);
           if (jn >= 2) mbar_wait(&sh->pv_done[jn & 1], ((jn >> 1) - 1) & 1);  // P_{jn-2} consumed: buffer free
           tc_fence_after();
           issue_s(jn);
         }
-        const int b = j & 1, vs = j % VST;
+        const int b = j & 1, vs = j & (VST - 1);
         mbar_wait(&sh->p_full[b], (j >> 1) & 1);   // P_j in TMEM (and O corrected if needed)
         mbar_wait(&sh->v_full[vs], (j / VST) & 1);
         tc_fence_after();
         const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;   // packed bf16: 2 sources per column
-        const uint32_t v_hi = smem_u32(v_sm + vs * 2 * kv_plane), v_lo = v_hi + kv_plane;
+        const uint64_t dv_hi = dv0 + (uint32_t)vs * stage_u, dv_lo = dv_hi + plane_u;
+#pragma unroll
         for (int kk = 0; kk < TS / 16; ++kk) {
-          // MN-major B: 8 sources x 8 channels per core matrix (sources 16 B apart); LBO = next 8 sources
-          // (128 B), SBO = next 8 channels (TS * 16 B); one k-step = 16 sources = 256 B = 8 TMEM columns of P
-          const uint64_t bv_hi = make_desc_nosw(v_hi + kk * 256, 128, TS * 16);
-          const uint64_t bv_lo = make_desc_nosw(v_lo + kk * 256, 128, TS * 16);
-          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, bv_hi, idesc_o, (j | kk) ? 1u : 0u);
-          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, bv_lo, idesc_o, 1u);
-          tc_mma_bf16_ts(tmem_o, p_lo + kk * 8, bv_hi, idesc_o, 1u);
+          // one k-step = 16 sources = 256 B of the V block = 8 TMEM columns of P
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, dv_hi + kk * 16, idesc_o, (j | kk) ? 1u : 0u);
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, dv_lo + kk * 16, idesc_o, 1u);
+          tc_mma_bf16_ts(tmem_o, p_lo + kk * 8, dv_hi + kk * 16, idesc_o, 1u);
         }
         tc_commit(&sh->pv_done[b]);
         tc_commit(&sh->v_empty[vs]);
@@ -450,15 +457,28 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   int need = 2 * TS + Cpad, cols = 32;
   while (cols < need) cols <<= 1;
   if (cols > 512) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)2 * TM * Cpad * 2 + (size_t)(KST + VST) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    smem_set = smem;
-  }
-  attn_dense_kernel<<<a.n_tiles * a.H, NT, smem, s>>>(a, cols);
+  auto smem_for = [&](int st) { return (size_t)2 * TM * Cpad * 2 + (size_t)(2 * st) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128; };
+  const size_t limit = 227 * 1024;
+  // ring depth 4 when two CTAs still fit per SM (small head dims), otherwise 2
+  const bool deep = (cols <= 256) ? (2 * smem_for(4) + 2048 <= limit) : (smem_for(4) <= limit);
+  const size_t smem = smem_for(deep ? 4 : 2);
+  if (smem > limit) return cudaErrorInvalidValue;
+  const unsigned grid = a.n_tiles * a.H;
+#define DA_LAUNCH(CP, ST_)                                                                                          \
+  do {                                                                                                              \
+    static size_t smem_set = 0;                                                                                     \
+    if (smem > smem_set) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(attn_dense_kernel<CP, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                               \
+      smem_set = smem;                                                                                              \
+    }                                                                                                               \
+    attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols);                                                     \
+  } while (0)
+  if (Cpad == 32 && deep) DA_LAUNCH(32, 4);
+  else if (Cpad == 144 && !deep) DA_LAUNCH(144, 2);
+  else if (deep) DA_LAUNCH(0, 4);
+  else DA_LAUNCH(0, 2);
+#undef DA_LAUNCH
   return cudaGetLastError();
 }
 
