@@ -234,7 +234,8 @@ def run_b200(args):
                 sharding.gather_poses(imgs[-1], [M] * world)
             torch.cuda.synchronize()
 
-        one_loop()  # untimed warm-up loop (first-use allocations, like the W warm-up steps of the device arm)
+        for _ in range(2):  # untimed warm-up loops (first-use allocations / allocator cache, like the W warm-up steps)
+            one_loop()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()

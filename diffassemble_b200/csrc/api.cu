@@ -63,6 +63,7 @@ struct da_handle {
   DensePlan plan;      // bitmap tiles + residual CSR (attn_mode = AUTO)
   bool use_plan = false;
   int num_real = 0, num_total = 0;
+  void* dbg_trace = nullptr;   // development aid: clock64 trace buffer for the dense attention kernel
   DevBuf qimg, kimg, vimg, qimg_l, kimg_l, vimg_l, dacc, dstats;   // operand images: hidden layers / last layer
   // activations / workspace
   DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
@@ -216,6 +217,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
       da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
       da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
+      da_.dbg = (long long*)h->dbg_trace;
       {
         Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
         DA_CK(launch_attn_dense(da_, s), "dense attention");
@@ -651,6 +653,12 @@ int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_ed
   return DA_OK;
 }
 
+int da_debug_trace(da_handle* h, long long* device_buf) {
+  if (!h) return DA_ERR_INVALID;
+  h->dbg_trace = device_buf;
+  return DA_OK;
+}
+
 int da_set_profiling(da_handle* h, int32_t enable) {
   if (!h) return DA_ERR_INVALID;
   cudaSetDevice(h->cfg.device);
@@ -758,7 +766,7 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
       PackArgs pa{qkvs, 4 * H * C, plan.node_slot, n, H, C, Cpad, qi, ki, vi};
       ce = launch_pack_images(pa, s);
       if (ce == cudaSuccess) {
-        AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st};
+        AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st, nullptr};
         ce = launch_attn_dense(da_, s);
       }
     }

@@ -51,6 +51,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW instead of spinning
       : "memory");
 }
+// one hardware-elected lane of a converged warp (see gemm_umma.cu: keeps tcgen05 / bulk-copy issue free of
+// the per-instruction "waterfall" loop the compiler emits inside a divergent `if (lane == 0)` region)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
@@ -200,9 +212,8 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int KST = ST, VST = ST;
   const int Cpad = CPAD_T ? CPAD_T : a.Cpad;
-  const uint32_t q_plane = TM * Cpad * 2, kv_plane = TS * Cpad * 2;  // bytes
-  uint8_t* q_sm = smem;                                   // 2 planes
-  uint8_t* k_sm = q_sm + 2 * q_plane;                     // KST stages x 2 planes
+  const uint32_t kv_plane = TS * Cpad * 2;                 // bytes
+  uint8_t* k_sm = smem;                                    // KST stages x 2 planes
   uint8_t* v_sm = k_sm + KST * 2 * kv_plane;              // VST stages x 2 planes
   DenseSmem* sh = reinterpret_cast<DenseSmem*>(v_sm + VST * 2 * kv_plane);
 
@@ -212,7 +223,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   const int nblk = (ti.gn + TS - 1) / TS;
 
   if (threadIdx.x == 0) {
-    mbar_init(&sh->q_full, 1);
+    mbar_init(&sh->q_full, 4);   // the four softmax warps have parked Q in TMEM
     for (int i = 0; i < MAXST; ++i) {
       mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1);
       mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
@@ -230,76 +241,84 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
   const uint32_t tmem_base = sh->tmem_base;
   const uint32_t tmem_s = tmem_base;             // 2 x TS columns: S_j (fp32), later P_j (bf16 hi | lo)
   const uint32_t tmem_o = tmem_base + 2 * TS;    // Cpad columns
+  const uint32_t tmem_q = tmem_o + Cpad;         // Cpad columns: Q as packed bf16 pairs, hi plane then lo plane
 
-  if (warp == 0) {
-    if (lane == 0) {  // ===== bulk-copy producer: K and V blocks run two ahead =====
-      const __nv_bfloat16* qsrc = a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cpad);
-      mbar_expect_tx(&sh->q_full, 2 * q_plane);
-      bulk_load(q_sm, qsrc, 2 * q_plane, &sh->q_full);
-      auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad); };
-      auto load_k = [&](int j) {
-        const int st = j & (KST - 1);
+  if (warp == 0) {  // ===== bulk-copy producer (warp-uniform): K and V blocks run ST ahead =====
+    auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad); };
+    auto load_k = [&](int j) {
+      if (elect_one()) {
+        const int st = j % KST;
         mbar_expect_tx(&sh->k_full[st], 2 * kv_plane);
         bulk_load(k_sm + st * 2 * kv_plane, a.kimg + blk_off(j), 2 * kv_plane, &sh->k_full[st]);
-      };
-      auto load_v = [&](int j) {
-        const int st = j & (VST - 1);
+      }
+      __syncwarp();
+    };
+    auto load_v = [&](int j) {
+      if (elect_one()) {
+        const int st = j % VST;
         mbar_expect_tx(&sh->v_full[st], 2 * kv_plane);
         bulk_load(v_sm + st * 2 * kv_plane, a.vimg + blk_off(j), 2 * kv_plane, &sh->v_full[st]);
-      };
-      for (int j = 0; j < KST && j < nblk; ++j) load_k(j);
-      for (int j = 0; j < VST && j < nblk; ++j) load_v(j);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + KST < nblk) {  // slot j % KST is free once S_j (its (j / KST)-th user) has retired
-          mbar_wait(&sh->k_empty[j & (KST - 1)], (j / KST) & 1);
-          load_k(j + KST);
-        }
-        if (j + VST < nblk) {
-          mbar_wait(&sh->v_empty[j & (VST - 1)], (j / VST) & 1);
-          load_v(j + VST);
-        }
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < KST && j < nblk; ++j) load_k(j);
+    for (int j = 0; j < VST && j < nblk; ++j) load_v(j);
+    for (int j = 0; j < nblk; ++j) {
+      if (j + KST < nblk) {  // slot j % KST is free once S_j (its (j / KST)-th user) has retired
+        mbar_wait(&sh->k_empty[j % KST], (j / KST) & 1);
+        load_k(j + KST);
+      }
+      if (j + VST < nblk) {
+        mbar_wait(&sh->v_empty[j % VST], (j / VST) & 1);
+        load_v(j + VST);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad) | (1u << 16);  // bit 16: B is MN-major
-      const int ksteps = Cpad / 16;
-      // descriptor bases; per-MMA descriptors are base + (byte offset >> 4) in the 14-bit address field
-      const uint64_t dq_hi = make_desc_nosw(smem_u32(q_sm), TM * 16, 128), dq_lo = dq_hi + (q_plane >> 4);
-      const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
-      const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);   // MN-major B: LBO = next 8 sources, SBO = next 8 channels
-      const uint32_t stage_u = (2 * kv_plane) >> 4, plane_u = kv_plane >> 4;
-      auto issue_s = [&](int j) {
-        const uint64_t dk_hi = dk0 + (uint32_t)(j & (KST - 1)) * stage_u, dk_lo = dk_hi + plane_u;
+  } else if (warp == 1) {  // ===== MMA issuer (warp-uniform; one elected lane issues) =====
+    const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, Cpad) | (1u << 16);  // bit 16: B is MN-major
+    const int ksteps = Cpad / 16;
+    const uint32_t tq_hi = tmem_q, tq_lo = tmem_q + Cpad / 2;   // A operand from TMEM: 8 columns per k-step
+    // descriptor bases; per-MMA descriptors are base + (byte offset >> 4) in the 14-bit address field
+    const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
+    const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);   // MN-major B: LBO = next 8 sources, SBO = next 8 channels
+    const uint32_t stage_u = (2 * kv_plane) >> 4, plane_u = kv_plane >> 4;
+    auto issue_s = [&](int j) {
+      if (elect_one()) {
+        const uint64_t dk_hi = dk0 + (uint32_t)(j % KST) * stage_u, dk_lo = dk_hi + plane_u;
         const uint32_t d = tmem_s + (uint32_t)((j & 1) * TS);
 #pragma unroll
         for (int kk = 0; kk < (CPAD_T ? CPAD_T / 16 : 16); ++kk) {
           if (!CPAD_T && kk >= ksteps) break;
-          // one k-step = 16 channels = 2 chunks; Q chunk stride TM*16 B, K chunk stride TS*16 B
-          const uint32_t qo = (uint32_t)kk * ((2 * TM * 16) >> 4), ko = (uint32_t)kk * ((2 * TS * 16) >> 4);
-          tc_mma_bf16(d, dq_hi + qo, dk_hi + ko, idesc_s, kk ? 1u : 0u);
-          tc_mma_bf16(d, dq_hi + qo, dk_lo + ko, idesc_s, 1u);
-          tc_mma_bf16(d, dq_lo + qo, dk_hi + ko, idesc_s, 1u);
+          // one k-step = 16 channels = 2 K chunks (stride TS*16 B) = 8 TMEM columns of Q
+          const uint32_t ko = (uint32_t)kk * ((2 * TS * 16) >> 4);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_hi + ko, idesc_s, kk ? 1u : 0u);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_lo + ko, idesc_s, 1u);
+          tc_mma_bf16_ts(d, tq_lo + kk * 8, dk_hi + ko, idesc_s, 1u);
         }
         tc_commit(&sh->s_full[j & 1]);
-        tc_commit(&sh->k_empty[j & (KST - 1)]);
-      };
-      mbar_wait(&sh->q_full, 0);
-      mbar_wait(&sh->k_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          const int jn = j + 1;
-          mbar_wait(&sh->k_full[jn & (KST - 1)], (jn / KST) & 1);
-          if (jn >= 2) mbar_wait(&sh->pv_done[jn & 1], ((jn >> 1) - 1) & 1);  // P_{jn-2} consumed: buffer free
-          tc_fence_after();
-          issue_s(jn);
-        }
-        const int b = j & 1, vs = j & (VST - 1);
-        mbar_wait(&sh->p_full[b], (j >> 1) & 1);   // P_j in TMEM (and O corrected if needed)
-        mbar_wait(&sh->v_full[vs], (j / VST) & 1);
+        tc_commit(&sh->k_empty[j % KST]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sh->q_full, 0);   // Q is in TMEM
+    mbar_wait(&sh->k_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nblk; ++j) {
+      if (j + 1 < nblk) {
+        const int jn = j + 1;
+        mbar_wait(&sh->k_full[jn % KST], (jn / KST) & 1);
+        if (jn >= 2) mbar_wait(&sh->pv_done[jn & 1], ((jn >> 1) - 1) & 1);  // P_{jn-2} consumed: buffer free
         tc_fence_after();
+        if (a.dbg && blockIdx.x == 0 && lane == 0 && j < 15) a.dbg[0 * 64 + j * 4 + 0] = clock64();   // S_{j+1} issue
+        issue_s(jn);
+      }
+      const int b = j & 1, vs = j % VST;
+      mbar_wait(&sh->p_full[b], (j >> 1) & 1);   // P_j in TMEM (and O corrected if needed)
+      if (a.dbg && blockIdx.x == 0 && lane == 0 && j < 15) a.dbg[0 * 64 + j * 4 + 1] = clock64();     // p_full observed
+      mbar_wait(&sh->v_full[vs], (j / VST) & 1);
+      if (a.dbg && blockIdx.x == 0 && lane == 0 && j < 15) a.dbg[0 * 64 + j * 4 + 2] = clock64();     // v_full observed
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;   // packed bf16: 2 sources per column
         const uint64_t dv_hi = dv0 + (uint32_t)vs * stage_u, dv_lo = dv_hi + plane_u;
 #pragma unroll
@@ -312,6 +331,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         tc_commit(&sh->pv_done[b]);
         tc_commit(&sh->v_empty[vs]);
       }
+      __syncwarp();
     }
   } else {  // ===== softmax warps =====
     const int q = warp & 3;
@@ -321,13 +341,39 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
     const float c_log2 = 1.4426950408889634f / sqrtf((float)a.C);  // scale * log2(e)
     const float tau_raw = LAZY_LOG2 / c_log2;
     const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
+    {  // park this row's Q (split-bf16 image, [plane][chunk][row][8]) in TMEM: A operand of every S = Q K^T
+      const uint4* qsrc = reinterpret_cast<const uint4*>(a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cpad));
+      for (int pl_ = 0; pl_ < 2; ++pl_) {
+        for (int ch0 = 0; ch0 < Cpad / 8; ch0 += 4) {   // 4 chunks = 32 channels = 16 TMEM columns per store
+          uint32_t qv[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (ch0 + u < Cpad / 8) t = __ldg(qsrc + (size_t)pl_ * (TM * Cpad / 8) + (size_t)(ch0 + u) * TM + r);
+            qv[4 * u] = t.x; qv[4 * u + 1] = t.y; qv[4 * u + 2] = t.z; qv[4 * u + 3] = t.w;
+          }
+          const uint32_t dst = tmem_q + lane_off + (uint32_t)(pl_ * (Cpad / 2) + ch0 * 4);
+          if (ch0 + 4 <= Cpad / 8) tmem_st16(dst, qv);
+          else {  // tail of 8 columns (Cpad = 16 mod 32)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(dst), "r"(qv[0]),
+                         "r"(qv[1]), "r"(qv[2]), "r"(qv[3]), "r"(qv[4]), "r"(qv[5]), "r"(qv[6]), "r"(qv[7]) : "memory");
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->q_full);
+    }
     float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
     uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
       const int b = j & 1;
       const uint2 bits = bits_next;
       if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (j + 1) * 2);
+      if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 0] = clock64();   // start waiting for S_j
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
+      if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 1] = clock64();   // S_j ready
       tc_fence_after();
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
       if (j == 0) {  // first block: take its masked max as the reference point
@@ -399,6 +445,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->p_full[b]);
+      if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 2] = clock64();   // P_j published
     }
     // epilogue: un-normalised O and (m, l) to global
     mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
@@ -454,14 +501,15 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   if (a.n_tiles <= 0) return cudaSuccess;
   const int Cpad = a.Cpad;
   if (Cpad % 16 || Cpad > 256 || Cpad < 16) return cudaErrorInvalidValue;
-  int need = 2 * TS + Cpad, cols = 32;
+  int need = 2 * TS + 2 * Cpad, cols = 32;   // S/P double buffer + O + Q
   while (cols < need) cols <<= 1;
   if (cols > 512) return cudaErrorInvalidValue;
-  auto smem_for = [&](int st) { return (size_t)2 * TM * Cpad * 2 + (size_t)(2 * st) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128; };
+  auto smem_for = [&](int st) { return (size_t)(2 * st) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128; };
   const size_t limit = 227 * 1024;
-  // ring depth 4 when two CTAs still fit per SM (small head dims), otherwise 2
-  const bool deep = (cols <= 256) ? (2 * smem_for(4) + 2048 <= limit) : (smem_for(4) <= limit);
-  const size_t smem = smem_for(deep ? 4 : 2);
+  // K / V ring depth: 4 when two CTAs still fit per SM (small head dims), else 3, else 2
+  int st = 4;
+  if (cols <= 256 ? (2 * smem_for(4) + 2048 > limit) : (smem_for(4) > limit)) st = (smem_for(3) <= limit) ? 3 : 2;
+  const size_t smem = smem_for(st);
   if (smem > limit) return cudaErrorInvalidValue;
   const unsigned grid = a.n_tiles * a.H;
 #define DA_LAUNCH(CP, ST_)                                                                                          \
@@ -474,9 +522,10 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
     }                                                                                                               \
     attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols);                                                     \
   } while (0)
-  if (Cpad == 32 && deep) DA_LAUNCH(32, 4);
-  else if (Cpad == 144 && !deep) DA_LAUNCH(144, 2);
-  else if (deep) DA_LAUNCH(0, 4);
+  if (Cpad == 32 && st == 4) DA_LAUNCH(32, 4);
+  else if (Cpad == 144 && st == 3) DA_LAUNCH(144, 3);
+  else if (st == 4) DA_LAUNCH(0, 4);
+  else if (st == 3) DA_LAUNCH(0, 3);
   else DA_LAUNCH(0, 2);
 #undef DA_LAUNCH
   return cudaGetLastError();

@@ -219,6 +219,7 @@ struct AttnDenseArgs {
   int H, C, Cpad;
   float* acc;    // [n, H*C] un-normalised sum_e exp(a_e - m) v_e of the bitmap edges
   float* stats;  // [n, H, 2] (m, l) of the bitmap edges, natural-log units
+  long long* dbg;  // optional timing trace of CTA 0 (clock64 stamps); null in production
 };
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s);
 size_t dense_image_elems(int n_tiles, int H, int Cpad);  // elements of ONE of the q / k / v image buffers

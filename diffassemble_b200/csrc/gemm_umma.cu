@@ -56,6 +56,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in HW instead of spinning
       : "memory");
 }
+// One lane of a converged warp, chosen by the hardware.  Role warps keep warp-uniform control flow and
+// only predicate the uniform-datapath instructions (TMA, tcgen05.mma / commit) with this: inside a plain
+// `if (lane == 0)` region the compiler wraps EVERY such instruction in an elect/branch "waterfall" loop
+// (~50 cycles per MMA issue), which starves the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -159,52 +173,53 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+  if (warp == 0) {  // ===== TMA producer (warp-uniform; one elected lane issues) =====
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_2d(&map_ahi, &full_bar[stage], st, kb * BK, m0);
           tma_load_2d(&map_alo, &full_bar[stage], st + BM * BK * 2, kb * BK, m0);
           tma_load_2d(&map_whi, &full_bar[stage], st + 2 * BM * BK * 2, kb * BK, n0);
           tma_load_2d(&map_wlo, &full_bar[stage], st + 2 * BM * BK * 2 + BN * BK * 2, kb * BK, n0);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer (one thread) =====
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+  } else if (warp == 1) {  // ===== MMA issuer (warp-uniform; one elected lane issues) =====
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);          // TMA bytes have landed
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + BM * BK * 2, w_hi = st + 2 * BM * BK * 2, w_lo = w_hi + BN * BK * 2;
+          const uint64_t da_hi = make_desc_sw128(st), da_lo = make_desc_sw128(st + BM * BK * 2);
+          const uint64_t db_hi = make_desc_sw128(st + 2 * BM * BK * 2), db_lo = make_desc_sw128(st + 2 * BM * BK * 2 + BN * BK * 2);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 2;  // bytes along K inside the 128-byte swizzle row
-            const uint64_t da_hi = make_desc_sw128(a_hi + koff), da_lo = make_desc_sw128(a_lo + koff);
-            const uint64_t db_hi = make_desc_sw128(w_hi + koff), db_lo = make_desc_sw128(w_lo + koff);
-            tc_mma_bf16(d_tmem, da_hi, db_hi, idesc, (kb | k) ? 1u : 0u);
-            tc_mma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
-            tc_mma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+            const uint32_t koff = (k * UMMA_K * 2) >> 4;  // 16-byte units along K inside the 128-byte swizzle row
+            tc_mma_bf16(d_tmem, da_hi + koff, db_hi + koff, idesc, (kb | k) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, da_hi + koff, db_lo + koff, idesc, 1u);
+            tc_mma_bf16(d_tmem, da_lo + koff, db_hi + koff, idesc, 1u);
           }
           tc_commit(&empty_bar[stage]);                // frees the smem slot when these MMAs retire
           if (kb == num_kb - 1) tc_commit(&tmem_full[acc]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {  // ===== epilogue warps: TMEM -> registers -> smem (transpose) -> coalesced global stores =====
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
