@@ -63,6 +63,7 @@ struct da_handle {
   DensePlan plan;      // bitmap tiles + residual CSR (attn_mode = AUTO)
   bool use_plan = false;
   int num_real = 0, num_total = 0;
+  int dbg_layer = -1;
   void* dbg_trace = nullptr;   // development aid: clock64 trace buffer for the dense attention kernel
   DevBuf qimg, kimg, vimg, qimg_l, kimg_l, vimg_l, dacc, dstats;   // operand images: hidden layers / last layer
   // activations / workspace
@@ -217,7 +218,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
       da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
       da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
-      da_.dbg = (long long*)h->dbg_trace;
+      da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
       {
         Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
         DA_CK(launch_attn_dense(da_, s), "dense attention");
@@ -653,9 +654,9 @@ int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_ed
   return DA_OK;
 }
 
-int da_debug_trace(da_handle* h, long long* device_buf) {
+int da_debug_trace(da_handle* h, long long* device_buf, int layer) {
   if (!h) return DA_ERR_INVALID;
-  h->dbg_trace = device_buf;
+  h->dbg_trace = device_buf; h->dbg_layer = layer;
   return DA_OK;
 }
 

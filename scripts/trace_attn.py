@@ -11,11 +11,12 @@ ei, batch = ei.to(dev), batch.to(dev)
 feats, x = torch.randn(M, 1088, device=dev), torch.randn(M, 4, device=dev)
 eng = mod.model.engine_for(ei, feats, batch)
 lib = eng._lib
-lib.da_debug_trace.argtypes = [C.c_void_p, C.c_void_p]
+lib.da_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+layer = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 buf = torch.zeros(128, dtype=torch.int64, device=dev)
 coef = mod._step_coef(290, mod._pred_code())
 for _ in range(3): eng.ddim_step(x, coef)
-lib.da_debug_trace(eng._h, C.c_void_p(buf.data_ptr()))
+lib.da_debug_trace(eng._h, C.c_void_p(buf.data_ptr()), layer)
 eng.ddim_step(x, coef); torch.cuda.synchronize()
 t = buf.cpu().tolist()   # trace of the LAST attention launch (last layer, C=144)
 base = min(v for v in t if v > 0)
