@@ -17,7 +17,8 @@ from .spatial_diffusion import (  # noqa: F401
     linear_beta_schedule,
 )
 from .spatial_diffusion_3d import GNN_Diffusion_3d  # noqa: F401
-from . import sharding, topology  # noqa: F401
+from . import metrics, sharding, topology  # noqa: F401
+from .metrics import greedy_cost_assignment, greedy_cost_assignment_batched  # noqa: F401
 
 __all__ = [
     "GNN_Diffusion", "GNN_Diffusion_3d", "Eff_GAT", "Eff_GAT_3d", "Transformer_GNN", "Exophormer_GNN",

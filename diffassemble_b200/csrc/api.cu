@@ -741,6 +741,14 @@ int da_op_graph_attention(const float* qkvs, const int64_t* edge_src, const int6
   return rc;
 }
 
+int da_greedy_cost_assignment(const float* pos1, int32_t ld1, const float* pos2, int32_t ld2, const int32_t* graph_ptr,
+                              int32_t n_graphs, int32_t max_nodes, int64_t* out, void* stream) {
+  if (!pos1 || !pos2 || !graph_ptr || !out || n_graphs < 0 || max_nodes <= 0 || ld1 < 2 || ld2 < 2) return DA_ERR_INVALID;
+  cudaError_t ce = launch_greedy_assign(pos1, ld1, pos2, ld2, graph_ptr, n_graphs, max_nodes, out, (cudaStream_t)stream);
+  if (ce == cudaErrorInvalidValue) return DA_ERR_UNSUPPORTED;
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

@@ -156,6 +156,10 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
                                  const char** err);
 void free_csr(CsrGraph* g);
 
+// greedy assignment metric (scope row N2): out [sum n, 3] int64 = (row, column, int64(distance)) in greedy order
+cudaError_t launch_greedy_assign(const float* pos1, int ld1, const float* pos2, int ld2, const int32_t* graph_ptr,
+                                 int n_graphs, int max_n, int64_t* out, cudaStream_t s);
+
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);
 

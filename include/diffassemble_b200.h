@@ -205,6 +205,16 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
                                 int64_t E, const int64_t* batch, int32_t n, int32_t H, int32_t C,
                                 float* y, int64_t* n_dense_edges, void* stream);
 
+/* Scope row N2 -- replaces greedy_cost_assignment (spatial_diffusion.py:179-216), the metric step right
+ * after the sampling loop: for each puzzle g (nodes graph_ptr[g] .. graph_ptr[g+1]) repeatedly assign the
+ * globally closest unassigned (piece, grid cell) pair.  pos1 / pos2: fp32 device rows of at least 2 columns
+ * (x, y) with row strides ld1 / ld2 (so `img[:, :2]` of an [N, 4] sample can be passed in place);
+ * graph_ptr: int32 device [n_graphs + 1]; out: int64 device [N, 3] = (piece, cell, int64(distance)) per
+ * puzzle in greedy order, indices local to the puzzle.  One CTA per puzzle, no host synchronisation. */
+int da_greedy_cost_assignment(const float* pos1, int32_t ld1, const float* pos2, int32_t ld2,
+                              const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t* out,
+                              void* stream);
+
 int da_abi_version(void);
 
 #ifdef __cplusplus

@@ -40,3 +40,4 @@ from .topology import (  # noqa: F401
     generate_random_expander,
     batch_graphs,
 )
+from .assignment import greedy_cost_assignment_ref  # noqa: F401,E402

@@ -282,3 +282,38 @@ def test_whole_loop_cuda_graph_matches_eager_loop(sampling, mean_type, ratio):
             nz = cache["noise"][k] if cache["noise"] is not None else None
             x, _ = mod.p_sample(x, t, i, cond=feats, edge_index=ei, patch_feats=feats, batch=batch, noise=nz)
             assert torch.equal(x, imgs_g[k]), (rep, k)
+
+
+@pytest.mark.parametrize("sizes", [[36], [144, 100, 7], [900], [1, 2, 3]])
+def test_greedy_cost_assignment_matches_reference_loop(sizes):
+    """Scope row N2: index output is bit-exact against the restated reference loop, including the
+    all-ties case (ground-truth positions exactly on the grid)."""
+    from diffassemble_b200 import greedy_cost_assignment, greedy_cost_assignment_batched
+
+    g = torch.Generator().manual_seed(sum(sizes))
+    grids, preds = [], []
+    for n in sizes:
+        side = int(round(n ** 0.5))
+        if side * side == n:
+            y = torch.linspace(-1, 1, side); x = torch.linspace(-1, 1, side)
+            grid = torch.stack(torch.meshgrid(x, y, indexing="xy"), -1).reshape(-1, 2)
+        else:
+            grid = torch.rand(n, 2, generator=g) * 2 - 1
+        grids.append(grid)
+        preds.append(grid[torch.randperm(n, generator=g)] + 0.02 * torch.randn(n, 2, generator=g))
+    ptr = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32)
+    # batched, reading (x, y) in place from a [N, 4] sample (row stride 4)
+    sample = torch.cat([torch.cat(preds), torch.zeros(sum(sizes), 2)], 1).to(DEV)
+    got = greedy_cost_assignment_batched(sample[:, :2], torch.cat(grids).to(DEV), ptr).cpu()
+    off = 0
+    for n, p1, p2 in zip(sizes, preds, grids):
+        want = oracle.greedy_cost_assignment_ref(p1, p2, separately_rounded=True)
+        assert torch.equal(got[off:off + n], want), n
+        assert torch.equal(got[off:off + n, :2], oracle.greedy_cost_assignment_ref(p1, p2)[:, :2]), n  # verbatim torch.norm
+        off += n
+    # exact ties: pieces exactly on grid cells (every matched distance is 0)
+    n = sizes[0]
+    perm = torch.randperm(n, generator=g)
+    want = oracle.greedy_cost_assignment_ref(grids[0][perm], grids[0], separately_rounded=True)
+    got1 = greedy_cost_assignment(grids[0][perm].to(DEV), grids[0].to(DEV)).cpu()
+    assert torch.equal(got1, want)

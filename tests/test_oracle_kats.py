@@ -180,3 +180,20 @@ def test_expander_is_regular_symmetric_and_seeded():
     assert torch.equal(e, e2)
     small = oracle.generate_random_expander(6, 4)
     assert small.shape == (30, 2)
+
+
+def test_greedy_assignment_kats():
+    # pieces exactly on the grid: the assignment is the inverse permutation, all distances 0
+    side = 5
+    y = torch.linspace(-1, 1, side); x = torch.linspace(-1, 1, side)
+    grid = torch.stack(torch.meshgrid(x, y, indexing="xy"), -1).reshape(-1, 2)
+    perm = torch.randperm(25, generator=torch.Generator().manual_seed(0))
+    for flag in (False, True):
+        a = oracle.greedy_cost_assignment_ref(grid[perm], grid, separately_rounded=flag)
+        assert a.shape == (25, 3) and (a[:, 2] == 0).all()
+        order = a[torch.sort(a[:, 0])[1]]
+        assert torch.equal(order[:, 1], perm)
+    # greedy, not optimal: the globally closest pair is taken first
+    p1 = torch.tensor([[0.0, 0.0], [1.0, 0.0]]); p2 = torch.tensor([[0.9, 0.0], [5.0, 0.0]])
+    a = oracle.greedy_cost_assignment_ref(p1, p2)
+    assert a[:, :2].tolist() == [[1, 0], [0, 1]]
