@@ -749,6 +749,14 @@ int da_greedy_cost_assignment(const float* pos1, int32_t ld1, const float* pos2,
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+int da_expander_edge_index(const int32_t* perm, int32_t n, int32_t degree, int32_t n_graphs, int64_t* edge_src,
+                           int64_t* edge_dst, void* stream) {
+  if (!perm || !edge_src || !edge_dst || n <= 0 || degree < 0 || degree >= n || n_graphs <= 0) return DA_ERR_INVALID;
+  if (((long long)n * degree) % 2) return DA_ERR_INVALID;   // "nodes * degree must be even" (puzzle_dataset.py:128)
+  cudaError_t ce = launch_expander_edges(perm, n, degree, n_graphs, edge_src, edge_dst, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

@@ -160,6 +160,10 @@ void free_csr(CsrGraph* g);
 cudaError_t launch_greedy_assign(const float* pos1, int ld1, const float* pos2, int ld2, const int32_t* graph_ptr,
                                  int n_graphs, int max_n, int64_t* out, cudaStream_t s);
 
+// Exphander edge list on the device from per-graph permutations (scope row N3)
+cudaError_t launch_expander_edges(const int32_t* perm, int n, int degree, int n_graphs, int64_t* src, int64_t* dst,
+                                  cudaStream_t s);
+
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);
 

@@ -178,3 +178,50 @@ fail:
 }
 
 }  // namespace da
+
+// ---------------------------------------------------------------------------------------------
+// Scope row N3: Exphander topology on the device.  Given the per-graph random permutations (drawn
+// by the caller with the reference's numpy Generator so seeds match, puzzle_dataset.py:133-152),
+// writes the batched, symmetrised edge list in exactly the reference's order:
+//   per graph: A = tile(perm, d/2) [+ perm[:n/2]],  Bv = [roll(perm, s) for s = 1..d/2] [+ perm[n/2:]]
+//              senders = [A, Bv], receivers = [Bv, A];  node ids offset by g * n (PyG collation).
+// The 250 MB int64 edge_index of a 32 x 900-node batch is then never built on, or copied from, the host.
+// ---------------------------------------------------------------------------------------------
+namespace da {
+namespace {
+__global__ void expander_edges_kernel(const int32_t* __restrict__ perm, int n, int degree, int n_graphs,
+                                      int64_t* __restrict__ src, int64_t* __restrict__ dst) {
+  const int half = degree / 2;
+  const long long e_half = (long long)n * half + ((degree & 1) ? n / 2 : 0);
+  const long long e_graph = 2 * e_half;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= e_half * n_graphs) return;
+  const int g = (int)(idx / e_half);
+  const long long k = idx % e_half;
+  const int32_t* p = perm + (size_t)g * n;
+  int a, b;
+  if (k < (long long)n * half) {
+    const int rep = (int)(k / n), pos = (int)(k % n);
+    int q = pos - (rep + 1);            // np.roll(perm, s)[pos] == perm[(pos - s) mod n]
+    q %= n; if (q < 0) q += n;
+    a = p[pos]; b = p[q];
+  } else {
+    const int t = (int)(k - (long long)n * half);   // perfect matching of the odd-degree case
+    a = p[t]; b = p[n / 2 + t];
+  }
+  const long long off = (long long)g * n;
+  const long long base = (long long)g * e_graph;
+  src[base + k] = a + off;           dst[base + k] = b + off;
+  src[base + e_half + k] = b + off;  dst[base + e_half + k] = a + off;
+}
+}  // namespace
+
+cudaError_t launch_expander_edges(const int32_t* perm, int n, int degree, int n_graphs, int64_t* src, int64_t* dst,
+                                  cudaStream_t s) {
+  const long long e_half = (long long)n * (degree / 2) + ((degree & 1) ? n / 2 : 0);
+  const long long total = e_half * n_graphs;
+  if (total <= 0) return cudaSuccess;
+  expander_edges_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(perm, n, degree, n_graphs, src, dst);
+  return cudaGetLastError();
+}
+}  // namespace da

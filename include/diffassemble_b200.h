@@ -215,6 +215,13 @@ int da_greedy_cost_assignment(const float* pos1, int32_t ld1, const float* pos2,
                               const int32_t* graph_ptr, int32_t n_graphs, int32_t max_nodes, int64_t* out,
                               void* stream);
 
+/* Scope row N3 -- replaces generate_random_regular_graph + PyG collation (puzzle_dataset.py:115-152) for a
+ * batch of equally sized graphs: perm is int32 device [n_graphs, n] (one random permutation per graph, drawn by
+ * the caller with the reference's numpy Generator); writes edge_src / edge_dst (int64 device,
+ * n_graphs * n * degree entries each) in the reference's edge order with node ids offset by g * n. */
+int da_expander_edge_index(const int32_t* perm, int32_t n, int32_t degree, int32_t n_graphs, int64_t* edge_src,
+                           int64_t* edge_dst, void* stream);
+
 int da_abi_version(void);
 
 #ifdef __cplusplus

@@ -317,3 +317,16 @@ def test_greedy_cost_assignment_matches_reference_loop(sizes):
     want = oracle.greedy_cost_assignment_ref(grids[0][perm], grids[0], separately_rounded=True)
     got1 = greedy_cost_assignment(grids[0][perm].to(DEV), grids[0].to(DEV)).cpu()
     assert torch.equal(got1, want)
+
+
+@pytest.mark.parametrize("n,degree,B", [(900, "60%", 3), (64, 7, 4), (144, "20%", 2), (30, 4, 1)])
+def test_expander_topology_on_device_is_bit_identical(n, degree, B):
+    """Scope row N3: the device-built batched Exphander edge list equals the reference construction."""
+    from diffassemble_b200 import topology
+
+    seeds = [11 + g for g in range(B)]
+    ei_d, batch_d = topology.expander_batch_on_device(n, degree, B, seeds, DEV)
+    eis = [oracle.generate_random_expander(n, degree, rng=np.random.default_rng(s), check_spectral_gap=False).t().contiguous()
+           for s in seeds]
+    ei_ref, batch_ref = oracle.batch_graphs(eis, [n] * B)
+    assert torch.equal(ei_d.cpu(), ei_ref) and torch.equal(batch_d.cpu(), batch_ref)
