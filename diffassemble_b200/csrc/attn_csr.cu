@@ -126,8 +126,10 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
 // Heavy rows (hundreds of in-edges: the virtual nodes of the Exphander wiring): one CTA owns one
 // (target node, head); its 8 warps take interleaved 32-edge chunks with the same online softmax as
 // attn_csr_kernel, then the 8 partial states (m, l, acc) are merged through shared memory.
+constexpr int HEAVY_WARPS = 32;   // one 32-edge chunk per warp for rows of ~1000 in-edges
+
 template <int R>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(HEAVY_WARPS * 32)
 attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
                       const int32_t* __restrict__ col, const float* __restrict__ weight,
                       const int32_t* __restrict__ node_list, int H, int C, float scale,
@@ -138,8 +140,8 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
   extern __shared__ __align__(16) float sm[];  // q[C] | acc[WARPS][C] | m[WARPS] | l[WARPS]
   float* q = sm;
   float* acc_s = sm + C;
-  float* m_s = acc_s + WARPS_PER_CTA * C;
-  float* l_s = m_s + WARPS_PER_CTA;
+  float* m_s = acc_s + HEAVY_WARPS * C;
+  float* l_s = m_s + HEAVY_WARPS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int node = node_list[blockIdx.x / H], head = blockIdx.x % H;
   const int HC = H * C;
@@ -162,7 +164,7 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
       if (c < C) acc[r] = init_acc[(size_t)node * HC + head * C + c];
     }
   }
-  for (int base = beg + warp * 32; base < end; base += 32 * WARPS_PER_CTA) {
+  for (int base = beg + warp * 32; base < end; base += 32 * HEAVY_WARPS) {
     const int e = base + lane;
     const bool valid = e < end;
     const int j = valid ? col[e] : 0;
@@ -218,25 +220,23 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
   }
   __syncthreads();
   if (warp != 0) return;
-  float M = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < WARPS_PER_CTA; ++w) M = fmaxf(M, m_s[w]);
-  float L = 0.f;
-  float f[WARPS_PER_CTA];
-#pragma unroll
-  for (int w = 0; w < WARPS_PER_CTA; ++w) {
-    f[w] = (m_s[w] == -INFINITY) ? 0.f : expf(m_s[w] - M);
-    L += l_s[w] * f[w];
-  }
+  // lane w holds partial w's (m, l); M = max over partials, factor f = exp(m_w - M)
+  const float mw = m_s[lane], lw = l_s[lane];
+  const float M = warp_max(mw);
+  const float fw = (mw == -INFINITY) ? 0.f : expf(mw - M);
+  const float L = warp_sum(lw * fw);
   const float inv = 1.f / (L + 1e-16f);
   const float* srow = qkvs + (size_t)node * ld + 3 * HC + head * C;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int c = lane + 32 * r;
+    float a = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < HEAVY_WARPS; ++w) {   // shuffles are executed by every lane (c may be out of range)
+      const float f = __shfl_sync(0xffffffffu, fw, w);
+      if (c < C) a = fmaf(acc_s[w * C + c], f, a);
+    }
     if (c < C) {
-      float a = 0.f;
-#pragma unroll
-      for (int w = 0; w < WARPS_PER_CTA; ++w) a = fmaf(acc_s[w * C + c], f[w], a);
       float v = a * inv + srow[c];
       if (resid) v += resid[(size_t)node * ld_resid + head * C + c];
       v = apply_act_rt(v, act);
@@ -392,12 +392,12 @@ cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s) {
 cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s) {
   if (a.n_targets <= 0) return cudaSuccess;
   if (!a.node_list || a.scores || a.stats) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)(a.C + WARPS_PER_CTA * a.C + 2 * WARPS_PER_CTA) * sizeof(float);
+  const size_t smem = (size_t)(a.C + HEAVY_WARPS * a.C + 2 * HEAVY_WARPS) * sizeof(float);
   const float scale = 1.0f / sqrtf((float)a.C);
   const int R = (a.C + 31) / 32;
   const unsigned grid = (unsigned)a.n_targets * a.H;
 #define DA_LAUNCH(RR)                                                                                          \
-  attn_csr_heavy_kernel<RR><<<grid, WARPS_PER_CTA * 32, smem, s>>>(                                            \
+  attn_csr_heavy_kernel<RR><<<grid, HEAVY_WARPS * 32, smem, s>>>(                                            \
       a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.H, a.C, scale, a.resid, a.ld_resid, a.act,       \
       a.out.f32, a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot)
   if (R <= 1) DA_LAUNCH(1);
