@@ -757,6 +757,57 @@ int da_expander_edge_index(const int32_t* perm, int32_t n, int32_t degree, int32
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+// ---- training-side graph object and operators (scope row N1) ------------------------------------------------
+struct da_graph {
+  CsrGraph by_target, by_source;
+  int n = 0;
+  int64_t E = 0;
+};
+
+int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n, void* stream) {
+  if (!out || n <= 0 || E < 0 || (E > 0 && (!edge_src || !edge_dst))) return DA_ERR_INVALID;
+  *out = nullptr;
+  da_graph* g = new da_graph();
+  const char* why = "";
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t ce = build_csr(edge_src, edge_dst, E, n, &g->by_target, s, &why);
+  if (ce == cudaSuccess) ce = build_csr(edge_dst, edge_src, E, n, &g->by_source, s, &why);   // CSC = CSR of the reversed edges
+  if (ce != cudaSuccess) { free_csr(&g->by_target); free_csr(&g->by_source); delete g; return ce == cudaErrorInvalidValue ? DA_ERR_INVALID : DA_ERR_CUDA; }
+  g->n = n; g->E = E;
+  *out = g;
+  return DA_OK;
+}
+
+void da_graph_destroy(da_graph* g) {
+  if (!g) return;
+  free_csr(&g->by_target); free_csr(&g->by_source);
+  delete g;
+}
+
+int da_op_graph_attention_fwd(const da_graph* g, const float* qkvs, int32_t H, int32_t C, float* y, float* stats, void* stream) {
+  if (!g || !qkvs || !y || !stats || H <= 0 || C <= 0) return DA_ERR_INVALID;
+  if ((C + 31) / 32 > 13) return DA_ERR_UNSUPPORTED;
+  AttnCsrArgs a{};
+  a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = g->by_target.rowptr; a.col = g->by_target.col; a.n_targets = g->n; a.H = H; a.C = C;
+  a.act = ACT_NONE; a.out.f32 = y; a.out.ldc = H * C; a.stats = stats;
+  cudaError_t ce = launch_attn_csr(a, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_graph_attention_bwd(const da_graph* g, const float* qkvs, const float* stats, const float* dy, int32_t H, int32_t C,
+                              float* dqkvs, float* delta_ws, void* stream) {
+  if (!g || !qkvs || !stats || !dy || !dqkvs || !delta_ws || H <= 0 || C <= 0) return DA_ERR_INVALID;
+  if ((C + 31) / 32 > 13) return DA_ERR_UNSUPPORTED;
+  cudaError_t ce = launch_attn_backward(qkvs, dy, g->by_target, g->by_source, stats, g->n, H, C, dqkvs, delta_ws, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (!dy || !x || !dw || M <= 0 || N <= 0 || K <= 0) return DA_ERR_INVALID;
+  cudaError_t ce = launch_linear_wgrad(dy, x, dw, db, M, N, K, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

@@ -1,0 +1,253 @@
+// Training-side kernels (scope row N1): backward of the TransformerConv attention stage over CSR / CSC, and
+// the weight-gradient ("TN") GEMM.  Forward kernels are shared with inference (attn_csr.cu, gemm_*.cu).
+//
+// Forward (per target i, head h, in-edges e = (j -> i)):  a_e = scale <q_i, k_j>,  alpha_e = exp(a_e - m_i) / (l_i + 1e-16),
+//                                                        o_i = sum_e alpha_e v_j          (+ skip, handled by the caller)
+// Backward given dO:   dp_e = <dO_i, v_j>,  delta_i = sum_e alpha_e dp_e,  ds_e = alpha_e (dp_e - delta_i)
+//                      dq_i = scale sum_e ds_e k_j          (by target: CSR)
+//                      dk_j = scale sum_e ds_e q_i,  dv_j = sum_e alpha_e dO_i      (by source: CSC, no atomics)
+// (PyG's softmax denominator l + 1e-16 is treated as l for the derivative, exactly as autograd does through
+//  out / (out_sum + 1e-16) when out_sum >> 1e-16.)
+#include "common.cuh"
+
+namespace da {
+namespace {
+
+constexpr int TW = 8;  // warps per CTA
+
+// ---- by target: delta_i and dq_i ------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(TW * 32)
+attn_bwd_target_kernel(const float* __restrict__ qkvs, int ld, const float* __restrict__ dO, int ldo,
+                       const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const float* __restrict__ stats, int n, int H, int C, float scale,
+                       float* __restrict__ dqkvs, int ldg, float* __restrict__ delta) {
+  extern __shared__ __align__(16) float sm[];   // per warp: q[C] | dO[C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * TW + warp;
+  if (gw >= (long long)n * H) return;
+  const int node = (int)(gw / H), head = (int)(gw % H);
+  const int HC = H * C;
+  float* q = sm + warp * 2 * C;
+  float* go = q + C;
+  for (int c = lane; c < C; c += 32) {
+    q[c] = qkvs[(size_t)node * ld + head * C + c] * scale;
+    go[c] = dO[(size_t)node * ldo + head * C + c];
+  }
+  __syncwarp();
+  const float m = stats[((size_t)node * H + head) * 2 + 0];
+  const float inv_l = 1.f / (stats[((size_t)node * H + head) * 2 + 1] + 1e-16f);
+  const float* Kb = qkvs + HC + head * C;
+  const float* Vb = qkvs + 2 * HC + head * C;
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  float a1[R], a2[R];   // sum alpha dp k , sum alpha k   (channel = lane + 32 r)
+#pragma unroll
+  for (int r = 0; r < R; ++r) { a1[r] = 0.f; a2[r] = 0.f; }
+  float dsum = 0.f;
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const int j = valid ? col[e] : 0;
+    float alpha = 0.f, dp = 0.f;
+    if (valid) {
+      const float* kr = Kb + (size_t)j * ld;
+      const float* vr = Vb + (size_t)j * ld;
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) { s = fmaf(__ldg(kr + c), q[c], s); dp = fmaf(__ldg(vr + c), go[c], dp); }
+      alpha = expf(s - m) * inv_l;
+    }
+    dsum += warp_sum(alpha * dp);
+    const int cnt = min(32, end - base);
+    for (int t = 0; t < cnt; ++t) {
+      const float at = __shfl_sync(0xffffffffu, alpha, t);
+      const float adp = at * __shfl_sync(0xffffffffu, dp, t);
+      const float* kr = Kb + (size_t)__shfl_sync(0xffffffffu, j, t) * ld;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int c = lane + 32 * r;
+        if (c < C) { const float kv = __ldg(kr + c); a1[r] = fmaf(adp, kv, a1[r]); a2[r] = fmaf(at, kv, a2[r]); }
+      }
+    }
+  }
+  if (lane == 0) delta[(size_t)node * H + head] = dsum;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) dqkvs[(size_t)node * ldg + head * C + c] = scale * (a1[r] - dsum * a2[r]);
+  }
+}
+
+// ---- by source: dk_j and dv_j ---------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(TW * 32)
+attn_bwd_source_kernel(const float* __restrict__ qkvs, int ld, const float* __restrict__ dO, int ldo,
+                       const int32_t* __restrict__ colptr, const int32_t* __restrict__ row,
+                       const float* __restrict__ stats, const float* __restrict__ delta, int n, int H, int C,
+                       float scale, float* __restrict__ dqkvs, int ldg) {
+  extern __shared__ __align__(16) float sm[];   // per warp: k[C] | v[C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * TW + warp;
+  if (gw >= (long long)n * H) return;
+  const int node = (int)(gw / H), head = (int)(gw % H);   // node = source j
+  const int HC = H * C;
+  float* k = sm + warp * 2 * C;
+  float* v = k + C;
+  for (int c = lane; c < C; c += 32) {
+    k[c] = qkvs[(size_t)node * ld + HC + head * C + c];
+    v[c] = qkvs[(size_t)node * ld + 2 * HC + head * C + c];
+  }
+  __syncwarp();
+  const int beg = colptr[node], end = colptr[node + 1];
+  float dk[R], dv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { dk[r] = 0.f; dv[r] = 0.f; }
+  for (int base = beg; base < end; base += 32) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const int i = valid ? row[e] : 0;   // target
+    float alpha = 0.f, ds = 0.f;
+    if (valid) {
+      const float* qr = qkvs + (size_t)i * ld + head * C;
+      const float* gr = dO + (size_t)i * ldo + head * C;
+      float s = 0.f, dp = 0.f;
+      for (int c = 0; c < C; ++c) { s = fmaf(__ldg(qr + c), k[c], s); dp = fmaf(__ldg(gr + c), v[c], dp); }
+      const float m = stats[((size_t)i * H + head) * 2 + 0];
+      const float inv_l = 1.f / (stats[((size_t)i * H + head) * 2 + 1] + 1e-16f);
+      alpha = expf(s * scale - m) * inv_l;
+      ds = alpha * (dp - delta[(size_t)i * H + head]);
+    }
+    const int cnt = min(32, end - base);
+    for (int t = 0; t < cnt; ++t) {
+      const float at = __shfl_sync(0xffffffffu, alpha, t);
+      const float dst = __shfl_sync(0xffffffffu, ds, t);
+      const int it = __shfl_sync(0xffffffffu, i, t);
+      const float* qr = qkvs + (size_t)it * ld + head * C;
+      const float* gr = dO + (size_t)it * ldo + head * C;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int c = lane + 32 * r;
+        if (c < C) { dk[r] = fmaf(dst, __ldg(qr + c), dk[r]); dv[r] = fmaf(at, __ldg(gr + c), dv[r]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = lane + 32 * r;
+    if (c < C) {
+      dqkvs[(size_t)node * ldg + HC + head * C + c] = scale * dk[r];
+      dqkvs[(size_t)node * ldg + 2 * HC + head * C + c] = dv[r];
+    }
+  }
+}
+
+__global__ void copy_skip_grad_kernel(const float* __restrict__ dO, int ldo, float* __restrict__ dqkvs, int ldg, int n, int HC) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * HC) return;
+  const int r = (int)(idx / HC), c = (int)(idx % HC);
+  dqkvs[(size_t)r * ldg + 3 * HC + c] = dO[(size_t)r * ldo + c];
+}
+
+// ---- weight gradient: dW[N, K] = sum_m dY[m, N] * X[m, K]   (split over m, fp32 atomics) ------------------
+constexpr int WG_BN = 64, WG_BK = 64, WG_BM = 32, WG_NT = 256;
+__global__ void __launch_bounds__(WG_NT)
+linear_wgrad_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx, float* __restrict__ dW,
+                    int ldw, int M, int N, int K, int m_chunk) {
+  __shared__ float ys[WG_BM][WG_BN + 4];
+  __shared__ float xs[WG_BM][WG_BK + 4];
+  const int n0 = blockIdx.x * WG_BN, k0 = blockIdx.y * WG_BK;
+  const int m_beg = blockIdx.z * m_chunk, m_end = min(M, m_beg + m_chunk);
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;   // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int m0 = m_beg; m0 < m_end; m0 += WG_BM) {
+    for (int idx = tid; idx < WG_BM * WG_BN; idx += WG_NT) {
+      const int mm = idx / WG_BN, nn = idx % WG_BN;
+      ys[mm][nn] = (m0 + mm < m_end && n0 + nn < N) ? dY[(size_t)(m0 + mm) * ldy + n0 + nn] : 0.f;
+    }
+    for (int idx = tid; idx < WG_BM * WG_BK; idx += WG_NT) {
+      const int mm = idx / WG_BK, kk = idx % WG_BK;
+      xs[mm][kk] = (m0 + mm < m_end && k0 + kk < K) ? X[(size_t)(m0 + mm) * ldx + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < WG_BM; ++mm) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = ys[mm][ty * 4 + i]; b[i] = xs[mm][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + ty * 4 + i, kk = k0 + tx * 4 + j;
+      if (nn < N && kk < K) atomicAdd(dW + (size_t)nn * ldw + kk, acc[i][j]);
+    }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ dY, int ldy, float* __restrict__ db, int M, int N, int m_chunk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m_beg = blockIdx.y * m_chunk, m_end = min(M, m_beg + m_chunk);
+  float s = 0.f;
+  for (int m = m_beg; m < m_end; ++m) s += dY[(size_t)m * ldy + n];
+  atomicAdd(db + n, s);
+}
+
+}  // namespace
+
+cudaError_t launch_attn_backward(const float* qkvs, const float* dO, const CsrGraph& by_target, const CsrGraph& by_source,
+                                 const float* stats, int n, int H, int C, float* dqkvs, float* delta, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  const int HC = H * C, ld = 4 * HC;
+  const long long warps = (long long)n * H;
+  const unsigned grid = (unsigned)((warps + TW - 1) / TW);
+  const size_t smem = (size_t)TW * 2 * C * sizeof(float);
+  const float scale = 1.0f / sqrtf((float)C);
+  const int R = (C + 31) / 32;
+#define DA_LAUNCH(RR)                                                                                                      \
+  do {                                                                                                                     \
+    attn_bwd_target_kernel<RR><<<grid, TW * 32, smem, s>>>(qkvs, ld, dO, HC, by_target.rowptr, by_target.col, stats, n, H, \
+                                                           C, scale, dqkvs, ld, delta);                                    \
+    attn_bwd_source_kernel<RR><<<grid, TW * 32, smem, s>>>(qkvs, ld, dO, HC, by_source.rowptr, by_source.col, stats,       \
+                                                           delta, n, H, C, scale, dqkvs, ld);                              \
+  } while (0)
+  if (R <= 1) DA_LAUNCH(1);
+  else if (R <= 2) DA_LAUNCH(2);
+  else if (R <= 5) DA_LAUNCH(5);
+  else if (R <= 13) DA_LAUNCH(13);
+  else return cudaErrorInvalidValue;
+#undef DA_LAUNCH
+  const size_t total = (size_t)n * HC;
+  copy_skip_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dO, HC, dqkvs, ld, n, HC);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, s);
+  if (e != cudaSuccess) return e;
+  int splits = (M + 2047) / 2048;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  int m_chunk = ((M + splits - 1) / splits + WG_BM - 1) / WG_BM * WG_BM;
+  dim3 grid((N + WG_BN - 1) / WG_BN, (K + WG_BK - 1) / WG_BK, (M + m_chunk - 1) / m_chunk);
+  linear_wgrad_kernel<<<grid, WG_NT, 0, s>>>(dY, N, X, K, dW, K, M, N, K, m_chunk);
+  if (db) {
+    e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, s);
+    if (e != cudaSuccess) return e;
+    dim3 g2((N + 255) / 256, (M + m_chunk - 1) / m_chunk);
+    colsum_kernel<<<g2, 256, 0, s>>>(dY, N, db, M, N, m_chunk);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace da

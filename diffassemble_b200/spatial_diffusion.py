@@ -277,16 +277,26 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             + extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
         )
 
-    @torch.no_grad()
     def p_losses(self, x_start, t, noise=None, loss_type="l1", cond=None, edge_index=None, batch=None):
-        """Loss VALUE of ``spatial_diffusion.py:432-483`` (no autograd: training is scope row N1)."""
+        """``spatial_diffusion.py:432-483``.  With autograd enabled the denoiser runs through the differentiable
+        CUDA operators of :mod:`diffassemble_b200.training` (scope row N1); under ``torch.no_grad()`` it uses the
+        fused inference engine."""
         if noise is None:
             noise = torch.randn_like(x_start)
         x_noisy = self.q_sample(x_start=x_start, t=t, noise=noise)
         if self.steps == 1:
             x_noisy = torch.zeros_like(x_noisy)
         patch_feats = self._features_from_cond(cond)
-        prediction = self.forward_with_feats(x_noisy, t, cond, edge_index, patch_feats=patch_feats, batch=batch)
+        if torch.is_grad_enabled():
+            from .training import denoiser_forward_train
+
+            key = (self.model._tensor_key(edge_index), self.model._tensor_key(batch))
+            cached = getattr(self, "_train_graph", None)
+            graph = cached[1] if cached is not None and cached[0] == key else None
+            prediction, graph = denoiser_forward_train(self.model, x_noisy, t, edge_index, patch_feats, batch, graph)
+            self._train_graph = (key, graph)
+        else:
+            prediction = self.forward_with_feats(x_noisy, t, cond, edge_index, patch_feats=patch_feats, batch=batch)
         target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
         if loss_type == "l1":
             return F.l1_loss(target, prediction)
@@ -451,4 +461,11 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
         return self.validation_step(batch, batch_idx)
 
     def training_step(self, batch, batch_idx):
-        raise NotImplementedError("training (backward + Adafactor) through the CUDA denoiser is scope row N1")
+        """``spatial_diffusion.py:707-722`` without the image dumps: per-graph t broadcast to nodes, Huber loss."""
+        batch_size = int(batch.batch.max()) + 1
+        t = torch.randint(0, self.steps, (batch_size,), device=batch.x.device).long()
+        new_t = torch.gather(t, 0, batch.batch)
+        loss = self.p_losses(batch.x, new_t, loss_type="huber", cond=batch.patches, edge_index=batch.edge_index,
+                             batch=batch.batch)
+        self.log("loss", loss)
+        return loss

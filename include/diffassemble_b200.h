@@ -222,6 +222,23 @@ int da_greedy_cost_assignment(const float* pos1, int32_t ld1, const float* pos2,
 int da_expander_edge_index(const int32_t* perm, int32_t n, int32_t degree, int32_t n_graphs, int64_t* edge_src,
                            int64_t* edge_dst, void* stream);
 
+/* ---- Scope row N1 (training step, spatial_diffusion.py:432-483,707-722): operator-level entry points the
+ * host-side autograd functions call.  A da_graph holds the CSR-by-target and CSR-by-source forms of one batch's
+ * edge multiset (built once per batch). */
+typedef struct da_graph da_graph;
+int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n, void* stream);
+void da_graph_destroy(da_graph* g);
+/* forward of the TransformerConv attention stage, also returning the per-(node, head) softmax statistics
+ * stats[n, H, 2] = (max, sum) that the backward needs;  y[n, H*C] = aggregate + skip */
+int da_op_graph_attention_fwd(const da_graph* g, const float* qkvs, int32_t H, int32_t C, float* y, float* stats,
+                              void* stream);
+/* backward: dy[n, H*C] -> dqkvs[n, 4*H*C] = [dQ | dK | dV | dskip];  delta_ws: fp32 workspace [n, H] */
+int da_op_graph_attention_bwd(const da_graph* g, const float* qkvs, const float* stats, const float* dy, int32_t H,
+                              int32_t C, float* dqkvs, float* delta_ws, void* stream);
+/* weight / bias gradient of y = x @ w^T + b:  dw[N, K] = dy^T @ x,  db[N] = column sums of dy (db may be NULL) */
+int da_op_linear_wgrad(const float* dy, const float* x, float* dw, float* db, int32_t M, int32_t N, int32_t K,
+                       void* stream);
+
 int da_abi_version(void);
 
 #ifdef __cplusplus

@@ -330,3 +330,70 @@ def test_expander_topology_on_device_is_bit_identical(n, degree, B):
            for s in seeds]
     ei_ref, batch_ref = oracle.batch_graphs(eis, [n] * B)
     assert torch.equal(ei_d.cpu(), ei_ref) and torch.equal(batch_d.cpu(), batch_ref)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-3), ("bf16x3", 1e-3)])
+@pytest.mark.parametrize("arch,V", [("transformer", 0), ("exophormer", 4)])
+def test_training_step_gradients_match_oracle_autograd(arch, V, mode, tol):
+    """Scope row N1: loss and every parameter gradient of one p_losses step against torch autograd
+    through the CPU oracle (identical weights, inputs, t and noise).  Tolerance 1e-3 relative per tensor
+    (max|g - g_ref| / max|g_ref|): several gradients (query/key biases of the last layer) are ~1e-10 sums of
+    cancelling terms, where the fp32 oracle itself carries ~3e-4 of rounding noise."""
+    ref, mod = make_pair_2d(seed=6, steps=50, sampling="DDIM", architecture=arch, virt_nodes=V, model_mean_type="EPSILON",
+                            gemm_mode=mode, attn_mode="csr")
+    mod = mod.to(DEV)
+    ref.train(); mod.train()
+    ei, batch = synth_graph_batch([36, 25, 16])
+    M = len(batch)
+    g = torch.Generator().manual_seed(0)
+    feats = torch.randn(M, 1088, generator=g)
+    x0 = torch.rand(M, 4, generator=g) * 2 - 1
+    noise = torch.randn(M, 4, generator=g)
+    t = torch.randint(0, 50, (3,), generator=g)[batch]
+    loss_ref = ref.p_losses(x0, t, noise=noise, loss_type="huber", edge_index=ei, patch_feats=feats, batch=batch)
+    loss_ref.backward()
+    loss = mod.p_losses(x0.to(DEV), t.to(DEV), noise=noise.to(DEV), loss_type="huber", cond=feats.to(DEV),
+                        edge_index=ei.to(DEV), batch=batch.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    ref_grads = dict(ref.named_parameters())
+    checked = 0
+    for name, p in mod.named_parameters():
+        gr = ref_grads[name].grad
+        if gr is None:
+            assert p.grad is None or p.grad.abs().max() == 0, name
+            continue
+        assert p.grad is not None, name
+        if gr.abs().max() < 1e-9:   # e.g. lin_key.bias: softmax is shift-invariant, the true gradient is exactly 0
+            assert p.grad.abs().max() < 1e-9, name
+            continue
+        assert rel_err(p.grad, gr) < tol, (name, rel_err(p.grad, gr))
+        checked += 1
+    assert checked >= 30
+
+
+def test_training_reduces_loss_with_adafactor():
+    """A few Adafactor steps (the reference's optimizer, default arguments) on a fixed batch reduce the loss,
+    and the inference engine picks up the updated weights."""
+    import diffassemble_b200 as dab
+
+    torch.manual_seed(0)
+    mod = dab.GNN_Diffusion(steps=50, sampling="DDIM", rotation=True, inference_ratio=10, gemm_mode="bf16x3", attn_mode="auto").to(DEV)
+    ei, batch = synth_graph_batch([64, 64])
+    ei, batch = ei.to(DEV), batch.to(DEV)
+    M = 128
+    feats, x0 = torch.randn(M, 1088, device=DEV), torch.rand(M, 4, device=DEV) * 2 - 1
+    noise = torch.randn(M, 4, device=DEV)
+    t = torch.randint(0, 50, (2,), device=DEV)[batch]
+    opt = mod.configure_optimizers()
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        loss = mod.p_losses(x0, t, noise=noise, loss_type="huber", cond=feats, edge_index=ei, batch=batch)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    with torch.no_grad():
+        after = mod.p_losses(x0, t, noise=noise, loss_type="huber", cond=feats, edge_index=ei, batch=batch).item()
+    assert abs(after - mod.p_losses(x0, t, noise=noise, loss_type="huber", cond=feats, edge_index=ei, batch=batch).item()) < 1e-3
