@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "da_set_features", "da_forward", "da_ddpm_step", "da_ddim_step", "da_ddim_update", "da_workspace_bytes",
     "da_launch_count", "da_graph_stats", "da_set_profiling", "da_get_profile", "da_profile_tag_name",
     "da_op_linear", "da_op_graph_attention", "da_op_graph_attention_dense", "da_greedy_cost_assignment", "da_expander_edge_index", "da_graph_create", "da_graph_destroy",
-    "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad",
+    "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws",
+    "da_op_linear_workspace_bytes",
 ]
 
 
@@ -104,6 +105,9 @@ def load_library():
     lib.da_op_graph_attention_fwd.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.da_op_graph_attention_bwd.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     lib.da_op_linear_wgrad.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.da_op_linear_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.da_op_linear_workspace_bytes.restype = C.c_size_t
+    lib.da_op_linear_ws.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, vp, C.c_size_t, vp]
     lib.da_expander_edge_index.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     lib.da_greedy_cost_assignment.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp]
     for name in EXPORTED_SYMBOLS:

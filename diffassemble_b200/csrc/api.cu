@@ -683,8 +683,17 @@ int da_get_profile(da_handle* h, double* ms_out, int64_t* launches_out, int32_t 
 const char* da_profile_tag_name(int32_t i) { return (i >= 0 && i < TAG_COUNT) ? kTagNames[i] : ""; }
 
 // ---- stand-alone operators ------------------------------------------------------------------
-int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
-                 int32_t K, int32_t act, void* stream) {
+size_t da_op_linear_workspace_bytes(int32_t mode, int32_t M, int32_t N, int32_t K) {
+  if (mode != DA_GEMM_BF16X3_UMMA) return 0;
+  const size_t align = 256;
+  auto up = [&](size_t b) { return (b + align - 1) / align * align; };
+  return 2 * up((size_t)M * K * sizeof(__nv_bfloat16)) + 2 * up((size_t)N * K * sizeof(__nv_bfloat16));
+}
+
+// y = act(a @ w^T + bias) with caller-provided workspace (no allocation, no synchronisation): the form the
+// training-side autograd functions call.  workspace must hold da_op_linear_workspace_bytes(...) bytes.
+int da_op_linear_ws(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
+                    int32_t K, int32_t act, void* workspace, size_t workspace_bytes, void* stream) {
   if (!a || !w || !y || M <= 0 || N <= 0 || K <= 0) return DA_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   LinearOut o; o.f32 = y; o.ldc = N;
@@ -694,21 +703,32 @@ int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias
     return ce == cudaSuccess ? DA_OK : (ce == cudaErrorInvalidValue ? DA_ERR_UNSUPPORTED : DA_ERR_CUDA);
   }
   if (mode != DA_GEMM_BF16X3_UMMA) return DA_ERR_INVALID;
-  if (K % 64 || N % 16) return DA_ERR_UNSUPPORTED;
-  __nv_bfloat16 *ahi = nullptr, *alo = nullptr, *whi = nullptr, *wlo = nullptr;
-  const size_t b2 = sizeof(__nv_bfloat16);
-  int rc = DA_OK;
-  if (cudaMalloc(&ahi, (size_t)M * K * b2) != cudaSuccess || cudaMalloc(&alo, (size_t)M * K * b2) != cudaSuccess ||
-      cudaMalloc(&whi, (size_t)N * K * b2) != cudaSuccess || cudaMalloc(&wlo, (size_t)N * K * b2) != cudaSuccess) {
-    rc = DA_ERR_CUDA;
-  } else {
-    ce = launch_split_bf16(a, K, ahi, alo, K, M, K, s);
-    if (ce == cudaSuccess) ce = launch_split_bf16(w, K, whi, wlo, K, N, K, s);
-    if (ce == cudaSuccess) ce = launch_linear_umma(ahi, alo, K, whi, wlo, K, bias, o, M, N, K, act, s);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    if (ce != cudaSuccess) rc = (ce == cudaErrorInvalidValue) ? DA_ERR_UNSUPPORTED : DA_ERR_CUDA;
+  if (K % 64 || N % 32) return DA_ERR_UNSUPPORTED;
+  if (!workspace || workspace_bytes < da_op_linear_workspace_bytes(mode, M, N, K)) return DA_ERR_INVALID;
+  const size_t align = 256;
+  auto up = [&](size_t b) { return (b + align - 1) / align * align; };
+  uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* ahi = reinterpret_cast<__nv_bfloat16*>(p); p += up((size_t)M * K * 2);
+  __nv_bfloat16* alo = reinterpret_cast<__nv_bfloat16*>(p); p += up((size_t)M * K * 2);
+  __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(p); p += up((size_t)N * K * 2);
+  __nv_bfloat16* wlo = reinterpret_cast<__nv_bfloat16*>(p);
+  ce = launch_split_bf16(a, K, ahi, alo, K, M, K, s);
+  if (ce == cudaSuccess) ce = launch_split_bf16(w, K, whi, wlo, K, N, K, s);
+  if (ce == cudaSuccess) ce = launch_linear_umma(ahi, alo, K, whi, wlo, K, bias, o, M, N, K, act, s);
+  if (ce != cudaSuccess) return (ce == cudaErrorInvalidValue) ? DA_ERR_UNSUPPORTED : DA_ERR_CUDA;
+  return DA_OK;
+}
+
+int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
+                 int32_t K, int32_t act, void* stream) {
+  const size_t bytes = da_op_linear_workspace_bytes(mode, M, N, K);
+  void* ws = nullptr;
+  if (bytes && cudaMalloc(&ws, bytes) != cudaSuccess) return DA_ERR_CUDA;
+  int rc = da_op_linear_ws(mode, a, w, bias, y, M, N, K, act, ws, bytes, stream);
+  if (bytes) {
+    if (rc == DA_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = DA_ERR_CUDA;
+    cudaFree(ws);
   }
-  cudaFree(ahi); cudaFree(alo); cudaFree(whi); cudaFree(wlo);
   return rc;
 }
 

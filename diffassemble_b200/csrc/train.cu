@@ -53,7 +53,16 @@ attn_bwd_target_kernel(const float* __restrict__ qkvs, int ld, const float* __re
       const float* kr = Kb + (size_t)j * ld;
       const float* vr = Vb + (size_t)j * ld;
       float s = 0.f;
-      for (int c = 0; c < C; ++c) { s = fmaf(__ldg(kr + c), q[c], s); dp = fmaf(__ldg(vr + c), go[c], dp); }
+      if ((C & 3) == 0) {
+        for (int c = 0; c < C; c += 4) {
+          const float4 kk = __ldg(reinterpret_cast<const float4*>(kr + c)), vv = __ldg(reinterpret_cast<const float4*>(vr + c));
+          const float4 qq = *reinterpret_cast<const float4*>(q + c), gg = *reinterpret_cast<const float4*>(go + c);
+          s = fmaf(kk.x, qq.x, s); s = fmaf(kk.y, qq.y, s); s = fmaf(kk.z, qq.z, s); s = fmaf(kk.w, qq.w, s);
+          dp = fmaf(vv.x, gg.x, dp); dp = fmaf(vv.y, gg.y, dp); dp = fmaf(vv.z, gg.z, dp); dp = fmaf(vv.w, gg.w, dp);
+        }
+      } else {
+        for (int c = 0; c < C; ++c) { s = fmaf(__ldg(kr + c), q[c], s); dp = fmaf(__ldg(vr + c), go[c], dp); }
+      }
       alpha = expf(s - m) * inv_l;
     }
     dsum += warp_sum(alpha * dp);
@@ -110,7 +119,16 @@ attn_bwd_source_kernel(const float* __restrict__ qkvs, int ld, const float* __re
       const float* qr = qkvs + (size_t)i * ld + head * C;
       const float* gr = dO + (size_t)i * ldo + head * C;
       float s = 0.f, dp = 0.f;
-      for (int c = 0; c < C; ++c) { s = fmaf(__ldg(qr + c), k[c], s); dp = fmaf(__ldg(gr + c), v[c], dp); }
+      if ((C & 3) == 0) {
+        for (int c = 0; c < C; c += 4) {
+          const float4 qq = __ldg(reinterpret_cast<const float4*>(qr + c)), gg = __ldg(reinterpret_cast<const float4*>(gr + c));
+          const float4 kk = *reinterpret_cast<const float4*>(k + c), vv = *reinterpret_cast<const float4*>(v + c);
+          s = fmaf(qq.x, kk.x, s); s = fmaf(qq.y, kk.y, s); s = fmaf(qq.z, kk.z, s); s = fmaf(qq.w, kk.w, s);
+          dp = fmaf(gg.x, vv.x, dp); dp = fmaf(gg.y, vv.y, dp); dp = fmaf(gg.z, vv.z, dp); dp = fmaf(gg.w, vv.w, dp);
+        }
+      } else {
+        for (int c = 0; c < C; ++c) { s = fmaf(__ldg(qr + c), k[c], s); dp = fmaf(__ldg(gr + c), v[c], dp); }
+      }
       const float m = stats[((size_t)i * H + head) * 2 + 0];
       const float inv_l = 1.f / (stats[((size_t)i * H + head) * 2 + 1] + 1e-16f);
       alpha = expf(s * scale - m) * inv_l;

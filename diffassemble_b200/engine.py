@@ -181,6 +181,8 @@ class DenoiserEngine:
 
 # -- stand-alone operators (unit-level parity tests) ----------------------------------------------
 def op_linear(a, w, bias=None, act=0, mode="fp32"):
+    """y = act(a @ w^T + bias) on the device; scratch for the split-bf16 planes comes from torch's caching
+    allocator (stream-ordered), so the call neither allocates with cudaMalloc nor synchronises."""
     lib = _cabi.load_library()
     _require_cuda(a, "a")
     a = a.float().contiguous()
@@ -189,10 +191,13 @@ def op_linear(a, w, bias=None, act=0, mode="fp32"):
     M, K = a.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    m = _cabi.GEMM_MODES[mode]
+    nbytes = int(lib.da_op_linear_workspace_bytes(m, M, N, K))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device) if nbytes else None
     with torch.cuda.device(a.device):
-        st = lib.da_op_linear(_cabi.GEMM_MODES[mode], _ptr(a), _ptr(w), _ptr(b), _ptr(y), M, N, K, act, _stream(a.device))
+        st = lib.da_op_linear_ws(m, _ptr(a), _ptr(w), _ptr(b), _ptr(y), M, N, K, act, _ptr(ws), nbytes, _stream(a.device))
     if st != _cabi.DA_OK:
-        raise DiffAssembleError(st, "da_op_linear failed")
+        raise DiffAssembleError(st, "da_op_linear_ws failed")
     return y
 
 

@@ -190,6 +190,10 @@ const char* da_profile_tag_name(int32_t i);
  * mode = DA_GEMM_*; all pointers device fp32. */
 int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y,
                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* Same operator with caller-provided scratch (split-bf16 operand planes): no allocation, no synchronisation. */
+size_t da_op_linear_workspace_bytes(int32_t mode, int32_t M, int32_t N, int32_t K);
+int da_op_linear_ws(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
+                    int32_t K, int32_t act, void* workspace, size_t workspace_bytes, void* stream);
 /* TransformerConv attention stage on precomputed projections (section 2.3c of SURVEY.md):
  * qkvs fp32 [n, 4*H*C] laid out [Q | K | V | skip]; edges as in da_set_graph;
  * y[n, H*C] = softmax-aggregate + skip. */

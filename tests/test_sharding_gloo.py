@@ -40,3 +40,36 @@ def test_shard_then_single_gather_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from diffassemble_b200.training import allreduce_gradients
+
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    unused = torch.nn.Parameter(torch.zeros(2))  # no grad: must be skipped
+    x = torch.full((2, 4), float(rank + 1))
+    lin(x).sum().backward()
+    allreduce_gradients(list(lin.parameters()) + [unused], world)
+    want_w = torch.full((3, 4), 2.0 * (1 + 2) / 2)   # mean over ranks of (2 rows * (rank + 1))
+    q.put((rank, torch.allclose(lin.weight.grad, want_w) and torch.allclose(lin.bias.grad, torch.full((3,), 2.0))
+           and unused.grad is None))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    """N1 multi-GPU leg: DDP-style gradient averaging (one flat all-reduce), checked with gloo on CPU."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
