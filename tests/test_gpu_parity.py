@@ -455,3 +455,28 @@ def test_random_multigraph_attention_both_paths(seed):
     assert rel_err(y_csr, ref) < 1e-5
     y_dense, _ = op_graph_attention_dense(qkvs.to(DEV), ei.to(DEV), batch.to(DEV), H)
     assert rel_err(y_dense, ref) < 2e-5
+
+
+@pytest.mark.parametrize("kw", [dict(n_layers=3), dict(rotation=False), dict(classifier_free_prob=0.1, classifier_free_w=0.5),
+                                dict(n_layers=2, architecture="exophormer", virt_nodes=2)])
+def test_constructor_variants(kw):
+    """Less common constructor settings of the reference module: other layer counts, no rotation channels
+    (C_in = C_out = 2), classifier-free guidance (two forwards, spatial_diffusion.py:568-589)."""
+    kw = dict(kw)
+    rotation = kw.pop("rotation", True)
+    arch = kw.pop("architecture", "transformer")
+    V = kw.pop("virt_nodes", 0)
+    ref, mod = make_pair_2d(seed=8, steps=100, sampling="DDIM", architecture=arch, virt_nodes=V, rotation=rotation,
+                            model_mean_type="START_X", inference_ratio=10, gemm_mode="bf16x3", attn_mode="auto", **kw)
+    mod = mod.to(DEV)
+    ei, batch = synth_graph_batch([80, 50])
+    M, Cc = 130, (4 if rotation else 2)
+    g = torch.Generator().manual_seed(1)
+    feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, Cc, generator=g)
+    for i in (90, 0):
+        t = torch.full((M,), i, dtype=torch.long)
+        with torch.no_grad():
+            want, _ = ref.p_sample(x, t, i, edge_index=ei, patch_feats=feats, batch=batch)
+        got, _ = mod.p_sample(x.to(DEV), t.to(DEV), i, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV),
+                              batch=batch.to(DEV))
+        assert rel_err(got, want) < TOL, (kw, i)
