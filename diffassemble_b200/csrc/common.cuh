@@ -140,6 +140,27 @@ cudaError_t launch_sampler_update(const float* x_in, const float* model_out, flo
                                   int head_kind, int step_mode, const da_step_coef& coef,
                                   const float* noise, cudaStream_t s);
 
+// Stream-ordered scratch allocations for the once-per-batch graph preparation: served from the device's default
+// memory pool with an unlimited release threshold, so after the first batch no cudaMalloc / cudaFree (both
+// device-synchronising and ~1 ms for 100 MB blocks) happens on the da_set_graph path.
+inline cudaError_t tmp_alloc(void** p, size_t bytes, cudaStream_t s) {
+  static bool pool_ready = false;
+  if (!pool_ready) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_ready = true;
+  }
+  return cudaMallocAsync(p, bytes ? bytes : 16, s);
+}
+template <typename T>
+inline cudaError_t tmp_alloc(T** p, size_t bytes, cudaStream_t s) { return tmp_alloc(reinterpret_cast<void**>(p), bytes, s); }
+inline void tmp_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+
 // graph structure
 struct CsrGraph {
   int32_t* rowptr = nullptr;  // [n + 1]

@@ -92,13 +92,13 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
     DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
     return cudaSuccess;
   }
-  DA_TRY(cudaMalloc(&key, sizeof(unsigned long long) * (size_t)E));
-  DA_TRY(cudaMalloc(&key_sorted, sizeof(unsigned long long) * (size_t)E));
-  DA_TRY(cudaMalloc(&ukey, sizeof(unsigned long long) * (size_t)E));
-  DA_TRY(cudaMalloc(&cnt, sizeof(int32_t) * (size_t)E));
-  DA_TRY(cudaMalloc(&udst, sizeof(int32_t) * (size_t)E));
-  DA_TRY(cudaMalloc(&nruns, sizeof(int32_t)));
-  DA_TRY(cudaMalloc(&bad, sizeof(int32_t)));
+  DA_TRY(tmp_alloc(&key, sizeof(unsigned long long) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&key_sorted, sizeof(unsigned long long) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&ukey, sizeof(unsigned long long) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&cnt, sizeof(int32_t) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&udst, sizeof(int32_t) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&nruns, sizeof(int32_t), s));
+  DA_TRY(tmp_alloc(&bad, sizeof(int32_t), s));
   DA_TRY(cudaMemsetAsync(bad, 0, sizeof(int32_t), s));
   pack_keys_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, n, key, bad);
   DA_TRY(cudaGetLastError());
@@ -106,7 +106,7 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
   DA_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tb1, key, key_sorted, (int)E, 0, 32 + bits, s));
   DA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tb2, key_sorted, ukey, cnt, nruns, (int)E, s));
   if (tb2 > tb1) tb1 = tb2;
-  DA_TRY(cudaMalloc(&tmp, tb1));
+  DA_TRY(tmp_alloc(&tmp, tb1, s));
   DA_TRY(cub::DeviceRadixSort::SortKeys(tmp, tb1, key, key_sorted, (int)E, 0, 32 + bits, s));
   DA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tb1, key_sorted, ukey, cnt, nruns, (int)E, s));
   DA_TRY(cudaMemcpyAsync(&nruns_h, nruns, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -121,10 +121,10 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
   rowptr_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(udst, nruns_h, n, g->rowptr);
   DA_TRY(cudaGetLastError());
   DA_TRY(cudaStreamSynchronize(s));
-  cudaFree(key); cudaFree(key_sorted); cudaFree(ukey); cudaFree(cnt); cudaFree(udst); cudaFree(nruns); cudaFree(bad); cudaFree(tmp);
+  tmp_free(key, s); tmp_free(key_sorted, s); tmp_free(ukey, s); tmp_free(cnt, s); tmp_free(udst, s); tmp_free(nruns, s); tmp_free(bad, s); tmp_free(tmp, s);
   return cudaSuccess;
 fail:
-  cudaFree(key); cudaFree(key_sorted); cudaFree(ukey); cudaFree(cnt); cudaFree(udst); cudaFree(nruns); cudaFree(bad); cudaFree(tmp);
+  tmp_free(key, s); tmp_free(key_sorted, s); tmp_free(ukey, s); tmp_free(cnt, s); tmp_free(udst, s); tmp_free(nruns, s); tmp_free(bad, s); tmp_free(tmp, s);
   free_csr(g);
   return ce;
 #undef DA_TRY
@@ -150,16 +150,16 @@ cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, 
     DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
     return cudaSuccess;
   }
-  DA_TRY(cudaMalloc(&key, sizeof(int32_t) * (size_t)E));
-  DA_TRY(cudaMalloc(&val, sizeof(int32_t) * (size_t)E));
-  DA_TRY(cudaMalloc(&key_sorted, sizeof(int32_t) * (size_t)E));
-  DA_TRY(cudaMalloc(&bad, sizeof(int32_t)));
+  DA_TRY(tmp_alloc(&key, sizeof(int32_t) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&val, sizeof(int32_t) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&key_sorted, sizeof(int32_t) * (size_t)E, s));
+  DA_TRY(tmp_alloc(&bad, sizeof(int32_t), s));
   DA_TRY(cudaMemsetAsync(bad, 0, sizeof(int32_t), s));
   narrow_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, n, key, val, bad);
   DA_TRY(cudaGetLastError());
   while ((1ll << bits) < (long long)n + 1 && bits < 31) ++bits;
   DA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key_sorted, val, g->eid, (int)E, 0, bits, s));
-  DA_TRY(cudaMalloc(&tmp, tmp_bytes));
+  DA_TRY(tmp_alloc(&tmp, tmp_bytes, s));
   DA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_sorted, val, g->eid, (int)E, 0, bits, s));
   gather_cols_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, g->eid, E, n, g->col);
   DA_TRY(cudaGetLastError());
@@ -167,11 +167,11 @@ cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, 
   DA_TRY(cudaGetLastError());
   DA_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   DA_TRY(cudaStreamSynchronize(s));
-  cudaFree(key); cudaFree(val); cudaFree(key_sorted); cudaFree(bad); cudaFree(tmp);
+  tmp_free(key, s); tmp_free(val, s); tmp_free(key_sorted, s); tmp_free(bad, s); tmp_free(tmp, s);
   if (bad_h) { *err = "edge_index entry outside [0, num_total)"; free_csr(g); return cudaErrorInvalidValue; }
   return cudaSuccess;
 fail:
-  cudaFree(key); cudaFree(val); cudaFree(key_sorted); cudaFree(bad); cudaFree(tmp);
+  tmp_free(key, s); tmp_free(val, s); tmp_free(key_sorted, s); tmp_free(bad, s); tmp_free(tmp, s);
   free_csr(g);
   return ce;
 #undef DA_TRY

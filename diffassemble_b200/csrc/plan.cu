@@ -92,7 +92,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   size_t words = 0;
   int block64 = 0;
 
-  DA_TRY(cudaMalloc(&d_bad, sizeof(int32_t)));
+  DA_TRY(tmp_alloc(&d_bad, sizeof(int32_t), s));
   DA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), s));
   check_sorted_kernel<<<(num_real + 255) / 256, 256, 0, s>>>(batch, num_real, d_bad);
   DA_TRY(cudaGetLastError());
@@ -108,7 +108,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   for (int i = 0; i < num_real && B > 0; ++i) g_n[hbatch[i]]++;
   for (int g = 1; g < B; ++g) g_node0[g] = g_node0[g - 1] + g_n[g - 1];
   if (B > 0 && E > 0) {
-    DA_TRY(cudaMalloc(&dcnt, sizeof(unsigned long long) * B));
+    DA_TRY(tmp_alloc(&dcnt, sizeof(unsigned long long) * B, s));
     DA_TRY(cudaMemsetAsync(dcnt, 0, sizeof(unsigned long long) * B, s));
     count_ingraph_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, dcnt);
     DA_TRY(cudaGetLastError());
@@ -153,25 +153,25 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     DA_TRY(cudaMemcpyAsync(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, s));
     DA_TRY(cudaMalloc(&plan->bitmap, sizeof(uint32_t) * words));
     DA_TRY(cudaMemsetAsync(plan->bitmap, 0, sizeof(uint32_t) * words, s));
-    DA_TRY(cudaMalloc(&d_g_node0, sizeof(int32_t) * B));
-    DA_TRY(cudaMalloc(&d_g_bm_words, sizeof(int32_t) * B));
-    DA_TRY(cudaMalloc(&d_g_bm_off, sizeof(int64_t) * B));
+    DA_TRY(tmp_alloc(&d_g_node0, sizeof(int32_t) * B, s));
+    DA_TRY(tmp_alloc(&d_g_bm_words, sizeof(int32_t) * B, s));
+    DA_TRY(tmp_alloc(&d_g_bm_off, sizeof(int64_t) * B, s));
     DA_TRY(cudaMemcpyAsync(d_g_node0, g_node0.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
     DA_TRY(cudaMemcpyAsync(d_g_bm_words, g_bm_words.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
     DA_TRY(cudaMemcpyAsync(d_g_bm_off, g_bm_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
   }
   if (plan->n_tiles > 0 && E > 0) {
-    DA_TRY(cudaMalloc(&flag, (size_t)E));
+    DA_TRY(tmp_alloc(&flag, (size_t)E, s));
     classify_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, d_g_node0, d_g_bm_off,
                                                                      d_g_bm_words, plan->bitmap, flag);
     DA_TRY(cudaGetLastError());
-    DA_TRY(cudaMalloc(&res_src, sizeof(int64_t) * (size_t)E));
-    DA_TRY(cudaMalloc(&res_dst, sizeof(int64_t) * (size_t)E));
-    DA_TRY(cudaMalloc(&d_nsel, sizeof(int64_t)));
+    DA_TRY(tmp_alloc(&res_src, sizeof(int64_t) * (size_t)E, s));
+    DA_TRY(tmp_alloc(&res_dst, sizeof(int64_t) * (size_t)E, s));
+    DA_TRY(tmp_alloc(&d_nsel, sizeof(int64_t), s));
     DA_TRY(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, src, flag, res_src, d_nsel, (int)E, s));
     DA_TRY(cub::DeviceSelect::Flagged(nullptr, tb2, dst, flag, res_dst, d_nsel, (int)E, s));
     if (tb2 > tmp_bytes) tmp_bytes = tb2;
-    DA_TRY(cudaMalloc(&tmp, tmp_bytes));
+    DA_TRY(tmp_alloc(&tmp, tmp_bytes, s));
     DA_TRY(cub::DeviceSelect::Flagged(tmp, tmp_bytes, src, flag, res_src, d_nsel, (int)E, s));
     DA_TRY(cub::DeviceSelect::Flagged(tmp, tmp_bytes, dst, flag, res_dst, d_nsel, (int)E, s));
     DA_TRY(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
@@ -200,12 +200,12 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     DA_TRY(cudaMemcpy(plan->light, light.data(), sizeof(int32_t) * light.size(), cudaMemcpyHostToDevice));
     DA_TRY(cudaMemcpy(plan->heavy, heavy.data(), sizeof(int32_t) * heavy.size(), cudaMemcpyHostToDevice));
   }
-  cudaFree(dcnt); cudaFree(d_g_node0); cudaFree(d_g_bm_words); cudaFree(d_bad); cudaFree(d_g_bm_off);
-  cudaFree(res_src); cudaFree(res_dst); cudaFree(d_nsel); cudaFree(flag); cudaFree(tmp);
+  tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
+  tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
   return cudaSuccess;
 fail:
-  cudaFree(dcnt); cudaFree(d_g_node0); cudaFree(d_g_bm_words); cudaFree(d_bad); cudaFree(d_g_bm_off);
-  cudaFree(res_src); cudaFree(res_dst); cudaFree(d_nsel); cudaFree(flag); cudaFree(tmp);
+  tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
+  tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
   free_plan(plan);
   return ce;
 #undef DA_TRY
