@@ -199,6 +199,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       if (dense && umma) {  // Q / K / V operand images straight from the GEMM epilogue
         o.img_node_slot = h->plan.node_slot; o.qimg = qimg; o.kimg = kimg; o.vimg = vimg;
         o.img_H = c.heads; o.img_C = C; o.img_Cpad = Cpad; o.img_rows = Mr;
+        if (attn_csr_rows_supported(c.heads, C) && !alpha_last) o.f32_tile_flags = h->plan.f32_tile_flags[last ? 1 : 0];
       }
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
       DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");

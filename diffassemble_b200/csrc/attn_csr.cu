@@ -282,9 +282,12 @@ attn_csr_rows_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __re
     }
   };
   float q[VPL], acc[VPL];
-  load_row(qkvs + (size_t)node * ld + c0, q);
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  if (end > beg) {   // rows without residual edges never read their fp32 Q (the GEMM may not even have stored it)
+    load_row(qkvs + (size_t)node * ld + c0, q);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) q[i] *= scale;
+    for (int i = 0; i < VPL; ++i) q[i] *= scale;
+  }
   float m = -INFINITY, l = 0.f;
   if (init_slot != nullptr && init_slot[node] >= 0) {
     m = init_stats[((size_t)node * H + head) * 2 + 0];
@@ -294,7 +297,6 @@ attn_csr_rows_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __re
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
   }
-  const int beg = rowptr[node], end = rowptr[node + 1];
   for (int e = beg; e < end; ++e) {
     const int j = col[e];
     const float w = weight ? weight[e] : 1.f;

@@ -59,6 +59,9 @@ struct LinearOut {
   __nv_bfloat16* kimg = nullptr;
   __nv_bfloat16* vimg = nullptr;
   int img_H = 0, img_C = 0, img_Cpad = 0, img_rows = 0;   // img_rows: rows [0, img_rows) have a node_slot entry
+  // optional per-128-row-tile flags (bit 0: some row's fp32 Q is read later, bit 1: some row's fp32 K / V is):
+  // tiles whose Q / K / V only feed the tensor-core attention skip those fp32 stores (HBM-write-bound GEMMs).
+  const uint8_t* f32_tile_flags = nullptr;
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
@@ -231,6 +234,9 @@ struct DensePlan {
   // "heavy" rows (virtual nodes with hundreds of in-edges) the edge-parallel one.  Real nodes first.
   int32_t* light = nullptr; int n_light = 0, n_light_real = 0;
   int32_t* heavy = nullptr; int n_heavy = 0, n_heavy_real = 0;
+  // per 128-row tile of the node index space: bit 0 = a row has residual in-edges (its fp32 Q is read),
+  // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
+  uint8_t* f32_tile_flags[2] = {nullptr, nullptr};
 };
 void free_plan(DensePlan* p);
 // Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.

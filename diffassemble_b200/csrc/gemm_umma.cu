@@ -134,6 +134,7 @@ struct EpiParams {
   // fused operand-image output (see LinearOut)
   const int32_t* node_slot; __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
   int iH, iC, iCpad, irows;
+  const uint8_t* f32_tile_flags;
 };
 
 template <int BN>
@@ -239,6 +240,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           if (row < p.irows) slots[i] = __ldg(p.node_slot + row);
         }
       }
+      const uint32_t tflags = p.f32_tile_flags ? (uint32_t)__ldg(p.f32_tile_flags + (m0 >> 7)) : 3u;   // BM == 128
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -257,6 +259,13 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           srow[j ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                 __uint_as_float(r[4 * j + 3]));
         __syncwarp();
+        // [Q | K | V | skip] outputs: a 32-column chunk lies in one part; tiles nobody reads in fp32 skip the store
+        bool f32_on = p.cf != nullptr;
+        if (tflags != 3u) {
+          const int part = (n0 + c0) / (p.iH * p.iC);
+          f32_on = f32_on && (part == 3 || (part == 0 ? (tflags & 1u) : (tflags & 2u)) != 0u);
+        }
+        if (f32_on || p.chi)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = i * 4 + sub_row;
@@ -265,7 +274,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           v.x = apply_act_rt(v.x + b4.x, p.act); v.y = apply_act_rt(v.y + b4.y, p.act);
           v.z = apply_act_rt(v.z + b4.z, p.act); v.w = apply_act_rt(v.w + b4.w, p.act);
           if (row < p.M) {
-            if (p.cf) *reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + col) = v;
+            if (f32_on) *reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + col) = v;
             if (p.chi) {
               __nv_bfloat16 h[4], l[4];
               const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -430,7 +439,8 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
   if (K % BK || N % 32 || (lda % 8) || (ldw % 8)) return cudaErrorInvalidValue;
   if ((out.f32 && out.ldc % 4) || (out.hi && out.ld_split % 8)) return cudaErrorInvalidValue;
   EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act,
-              out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows};
+              out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows,
+              out.img_node_slot ? out.f32_tile_flags : nullptr};
   if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
   if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);

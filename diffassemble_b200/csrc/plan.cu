@@ -62,7 +62,7 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 
 void free_plan(DensePlan* p) {
   if (!p) return;
-  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy);
+  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy); cudaFree(p->f32_tile_flags[0]); cudaFree(p->f32_tile_flags[1]);
   free_csr(&p->residual);
   *p = DensePlan();
 }
@@ -195,6 +195,24 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     }
     if (num_total == num_real) { plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size(); }
     plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size();
+    {  // which 128-row tiles contain rows whose fp32 Q / K / V some CSR kernel reads?
+      std::vector<int32_t> colv((size_t)(plan->residual.E > 0 ? plan->residual.E : 1));
+      if (plan->residual.E > 0)
+        DA_TRY(cudaMemcpy(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)plan->residual.E, cudaMemcpyDeviceToHost));
+      const int n_mt = (num_total + 127) / 128;
+      for (int v = 0; v < 2; ++v) {
+        std::vector<uint8_t> fl((size_t)n_mt, 0);
+        const int n_targets = v == 0 ? num_total : num_real;
+        for (int i = 0; i < n_targets; ++i) {
+          if (rp[i + 1] > rp[i]) fl[i >> 7] |= 1;
+          for (int e = rp[i]; e < rp[i + 1]; ++e) fl[colv[e] >> 7] |= 2;
+        }
+        for (int i = 0; i < num_total; ++i)
+          if (node_slot[i] < 0) fl[i >> 7] = 3;   // rows outside the dense tiles are served by the CSR kernels only
+        DA_TRY(cudaMalloc(&plan->f32_tile_flags[v], (size_t)n_mt));
+        DA_TRY(cudaMemcpy(plan->f32_tile_flags[v], fl.data(), (size_t)n_mt, cudaMemcpyHostToDevice));
+      }
+    }
     DA_TRY(cudaMalloc(&plan->light, sizeof(int32_t) * (light.size() + 1)));
     DA_TRY(cudaMalloc(&plan->heavy, sizeof(int32_t) * (heavy.size() + 1)));
     DA_TRY(cudaMemcpy(plan->light, light.data(), sizeof(int32_t) * light.size(), cudaMemcpyHostToDevice));
