@@ -264,14 +264,16 @@ attn_csr_rows_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __re
                      const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                      __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
                      const float* __restrict__ init_acc, const float* __restrict__ init_stats,
-                     const int32_t* __restrict__ init_slot) {
+                     const int32_t* __restrict__ init_slot, int wpn) {
+  // wpn warps share one node: each owns 32 * VPL contiguous channels (a whole number of heads)
   constexpr int W = (VPL % 4 == 0) ? 4 : ((VPL % 2 == 0) ? 2 : 1);
   const int lane = threadIdx.x & 31;
   const int wg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (wg >= n_list) return;
-  const int node = node_list ? node_list[wg] : wg;
-  const int HC = H * C, lph = 32 / H, head = lane / lph;
-  const int c0 = lane * VPL;  // first channel (within the H*C row) owned by this lane
+  if (wg >= n_list * wpn) return;
+  const int node = node_list ? node_list[wg / wpn] : wg / wpn;
+  const int HC = H * C, lph = C / VPL;
+  const int c0 = (wg % wpn) * (32 * VPL) + lane * VPL;  // first channel (within the H*C row) owned by this lane
+  const int head = c0 / C;
 
   auto load_row = [&](const float* p, float* dst) {
 #pragma unroll
@@ -411,24 +413,37 @@ cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-bool attn_csr_rows_supported(int H, int C) {
-  if (H <= 0 || 32 % H) return false;
-  const int vpl = H * C / 32;
-  return (H * C) % 32 == 0 && (vpl == 8 || vpl == 36 || vpl == 6);
+namespace {
+// channels per lane of the row kernel: the whole H*C row over one warp when that is <= 8 values per lane,
+// otherwise half a row per warp (two warps per node) -- more warps in flight for the 1152-wide last layer
+int rows_vpl(int H, int C) {
+  const int HC = H * C;
+  if (HC % 32) return 0;
+  int vpl = HC / 32;
+  if (vpl > 8) { if (HC % 64) return 0; vpl = HC / 64; }
+  if (!(vpl == 8 || vpl == 18 || vpl == 6)) return 0;
+  if (C % vpl) return 0;
+  const int lph = C / vpl;
+  if (lph < 1 || lph > 32 || (lph & (lph - 1))) return 0;
+  return vpl;
 }
+}  // namespace
+
+bool attn_csr_rows_supported(int H, int C) { return rows_vpl(H, C) != 0; }
 
 cudaError_t launch_attn_csr_rows(const AttnCsrArgs& a, cudaStream_t s) {
   if (a.n_targets <= 0) return cudaSuccess;
-  if (!attn_csr_rows_supported(a.H, a.C) || a.scores || a.stats) return cudaErrorInvalidValue;
-  const int vpl = a.H * a.C / 32;
-  const unsigned grid = (unsigned)(((long long)a.n_targets * 32 + 255) / 256);
+  const int vpl = rows_vpl(a.H, a.C);
+  if (!vpl || a.scores || a.stats) return cudaErrorInvalidValue;
+  const int wpn = a.H * a.C / (32 * vpl);
+  const unsigned grid = (unsigned)(((long long)a.n_targets * wpn * 32 + 255) / 256);
   const float scale = 1.0f / sqrtf((float)a.C);
 #define DA_LAUNCH(V)                                                                                              \
   attn_csr_rows_kernel<V><<<grid, 256, 0, s>>>(a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, a.H, \
                                                a.C, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc, a.out.hi, \
-                                               a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot)
+                                               a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot, wpn)
   if (vpl == 8) DA_LAUNCH(8);
-  else if (vpl == 36) DA_LAUNCH(36);
+  else if (vpl == 18) DA_LAUNCH(18);
   else DA_LAUNCH(6);
 #undef DA_LAUNCH
   return cudaGetLastError();
