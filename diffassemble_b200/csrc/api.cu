@@ -255,6 +255,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       const DensePlan& pl = h->plan;
       AttnCsrArgs hv = a, lt = a;
       hv.node_list = pl.heavy; hv.n_targets = last ? pl.n_heavy_real : pl.n_heavy;
+      if (dense && umma) { hv.img_slot = pl.node_slot; hv.kimg = kimg; hv.vimg = vimg; hv.img_Cpad = Cpad; }
       lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light;
       if (hv.n_targets > 0) {
         Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);

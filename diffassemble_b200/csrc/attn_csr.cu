@@ -126,6 +126,9 @@ attn_csr_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restric
 // Heavy rows (hundreds of in-edges: the virtual nodes of the Exphander wiring): one CTA owns one
 // (target node, head); its 8 warps take interleaved 32-edge chunks with the same online softmax as
 // attn_csr_kernel, then the 8 partial states (m, l, acc) are merged through shared memory.
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 constexpr int HEAVY_WARPS = 32;   // one 32-edge chunk per warp for rows of ~1000 in-edges
 
 template <int R>
@@ -136,7 +139,8 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
                       const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                       __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
                       const float* __restrict__ init_acc, const float* __restrict__ init_stats,
-                      const int32_t* __restrict__ init_slot) {
+                      const int32_t* __restrict__ init_slot, const int32_t* __restrict__ img_slot,
+                      const __nv_bfloat16* __restrict__ kimg, const __nv_bfloat16* __restrict__ vimg, int Cpad) {
   extern __shared__ __align__(16) float sm[];  // q[C] | acc[WARPS][C] | m[WARPS] | l[WARPS]
   float* q = sm;
   float* acc_s = sm + C;
@@ -168,11 +172,23 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
     const int e = base + lane;
     const bool valid = e < end;
     const int j = valid ? col[e] : 0;
+    const int sj = (img_slot != nullptr && valid) ? __ldg(img_slot + j) : -1;
     float s = -INFINITY;
     if (valid) {
       const float* kr = Kbase + (size_t)j * ld;
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-      if ((C & 3) == 0) {
+      if (sj >= 0) {   // K row from the operand image: 8-channel chunks, hi plane then lo plane
+        const __nv_bfloat16* kb = kimg + ((size_t)(sj >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (sj & 63) * 8;
+        for (int c = 0; c < C; c += 8) {
+          const uint4 hi = __ldg(reinterpret_cast<const uint4*>(kb + (size_t)(c >> 3) * 512));
+          const uint4 lo = __ldg(reinterpret_cast<const uint4*>(kb + (size_t)64 * Cpad + (size_t)(c >> 3) * 512));
+          const float4 q0 = *reinterpret_cast<const float4*>(q + c), q1 = *reinterpret_cast<const float4*>(q + c + 4);
+          d0 = fmaf(bf_lo(hi.x) + bf_lo(lo.x), q0.x, d0); d1 = fmaf(bf_hi(hi.x) + bf_hi(lo.x), q0.y, d1);
+          d2 = fmaf(bf_lo(hi.y) + bf_lo(lo.y), q0.z, d2); d3 = fmaf(bf_hi(hi.y) + bf_hi(lo.y), q0.w, d3);
+          d0 = fmaf(bf_lo(hi.z) + bf_lo(lo.z), q1.x, d0); d1 = fmaf(bf_hi(hi.z) + bf_hi(lo.z), q1.y, d1);
+          d2 = fmaf(bf_lo(hi.w) + bf_lo(lo.w), q1.z, d2); d3 = fmaf(bf_hi(hi.w) + bf_hi(lo.w), q1.w, d3);
+        }
+      } else if ((C & 3) == 0) {
         for (int c = 0; c < C; c += 4) {
           float4 kk = __ldg(reinterpret_cast<const float4*>(kr + c));
           float4 qq = *reinterpret_cast<const float4*>(q + c);
@@ -195,19 +211,25 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
     // aggregate: 4 V rows in flight per step (invalid lanes carry p = 0 and row 0)
 #pragma unroll 1
     for (int t = 0; t < 32; t += 4) {
-      float pt[4]; const float* vr[4];
+      float pt[4]; const float* vr[4]; const __nv_bfloat16* vi[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         pt[u] = __shfl_sync(0xffffffffu, p, t + u);
         vr[u] = Vbase + (size_t)__shfl_sync(0xffffffffu, j, t + u) * ld;
+        const int su = __shfl_sync(0xffffffffu, sj, t + u);   // warp-uniform: image row or fp32 row
+        vi[u] = su >= 0 ? vimg + ((size_t)(su >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (su & 63) * 8 : nullptr;
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int c = lane + 32 * r;
         if (c < C) {
-          float v0 = __ldg(vr[0] + c), v1 = __ldg(vr[1] + c), v2 = __ldg(vr[2] + c), v3 = __ldg(vr[3] + c);
-          acc[r] = fmaf(pt[0], v0, acc[r]); acc[r] = fmaf(pt[1], v1, acc[r]);
-          acc[r] = fmaf(pt[2], v2, acc[r]); acc[r] = fmaf(pt[3], v3, acc[r]);
+          const size_t io = (size_t)(c >> 3) * 512 + (c & 7);
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = vi[u] ? __bfloat162float(vi[u][io]) + __bfloat162float(vi[u][(size_t)64 * Cpad + io]) : __ldg(vr[u] + c);
+          acc[r] = fmaf(pt[0], v[0], acc[r]); acc[r] = fmaf(pt[1], v[1], acc[r]);
+          acc[r] = fmaf(pt[2], v[2], acc[r]); acc[r] = fmaf(pt[3], v[3], acc[r]);
         }
       }
     }
@@ -403,7 +425,9 @@ cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s) {
 #define DA_LAUNCH(RR)                                                                                          \
   attn_csr_heavy_kernel<RR><<<grid, HEAVY_WARPS * 32, smem, s>>>(                                            \
       a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.H, a.C, scale, a.resid, a.ld_resid, a.act,       \
-      a.out.f32, a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot)
+      a.out.f32, a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.init_acc, a.init_stats, a.init_slot,        \
+      a.img_slot, a.kimg, a.vimg, a.img_Cpad)
+  if (a.img_slot != nullptr && (a.C % 8 != 0 || a.kimg == nullptr || a.vimg == nullptr)) return cudaErrorInvalidValue;
   if (R <= 1) DA_LAUNCH(1);
   else if (R <= 2) DA_LAUNCH(2);
   else if (R <= 5) DA_LAUNCH(5);

@@ -92,6 +92,12 @@ struct AttnCsrArgs {
   const float* init_stats;    // [n, H, 2] (m, l)
   const int32_t* init_slot;   // [n] >= 0 where the init state is valid
   const int32_t* node_list;   // optional: the n_targets target ids to process (null = 0 .. n_targets-1)
+  // heavy-row kernel only: sources with img_slot[j] >= 0 are read from the split-bf16 K / V operand images
+  // (hi + lo) instead of the fp32 row, so the GEMM can skip the fp32 K / V stores of dense-tile rows
+  const int32_t* img_slot = nullptr;
+  const __nv_bfloat16* kimg = nullptr;
+  const __nv_bfloat16* vimg = nullptr;
+  int img_Cpad = 0;
 };
 cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s);
 // warp-per-node variant for low-degree targets (all heads at once, fully coalesced rows)

@@ -205,7 +205,10 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
         const int n_targets = v == 0 ? num_total : num_real;
         for (int i = 0; i < n_targets; ++i) {
           if (rp[i + 1] > rp[i]) fl[i >> 7] |= 1;
-          for (int e = rp[i]; e < rp[i + 1]; ++e) fl[colv[e] >> 7] |= 2;
+          // heavy rows read dense-tile sources from the K / V operand images, light rows from the fp32 row
+          const bool heavy_row = rp[i + 1] - rp[i] > 16;
+          for (int e = rp[i]; e < rp[i + 1]; ++e)
+            if (!(heavy_row && node_slot[colv[e]] >= 0)) fl[colv[e] >> 7] |= 2;
         }
         for (int i = 0; i < num_total; ++i)
           if (node_slot[i] < 0) fl[i >> 7] = 3;   // rows outside the dense tiles are served by the CSR kernels only
