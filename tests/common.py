@@ -65,3 +65,34 @@ def synth_graph_batch(sizes, kind="dense", degree="60%", seed=0):
             rng = np.random.default_rng(seed + g)
             eis.append(oracle.generate_random_expander(n, degree, rng=rng, check_spectral_gap=False).t().contiguous())
     return oracle.batch_graphs(eis, sizes)
+
+
+def reseed_parameters(module, seed=0, gain=1.5, qk_gain=1.5):
+    """Overwrite every parameter with values derived from (seed, parameter NAME, shape) only.
+
+    The reference module and the oracle create their sub-modules in different orders, so
+    ``torch.manual_seed`` + default initialisers give them different weights.  This makes the
+    weights a function of the state_dict key alone: ``tests/golden/make_reference_golden.py``
+    applies it to the real reference module, the tests apply it to the oracle / CUDA mirror, and
+    both end up with identical tensors without 13 MB of weights per fixture in the repository.
+    Magnitudes follow torch's defaults (uniform +-1/sqrt(fan_in), N(0,1) embeddings) times a gain
+    (weights x1.5, query/key weights x1.5 again): with the plain defaults the attention of a
+    random network is uniform to 1e-5 and the outputs barely differ between nodes, which would
+    make the fixtures blind to attention errors; with the gain alpha spans 1e-4 .. 0.9.
+    """
+    import zlib
+
+    with torch.no_grad():
+        for name, p in sorted(module.named_parameters()):
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + 7919 * seed) % (2**31))
+            if "emb" in name:
+                v = torch.randn(p.shape, generator=g)
+            else:
+                fan_in = p.shape[-1] if p.dim() > 1 else max(p.numel(), 16)
+                v = (torch.rand(p.shape, generator=g) * 2 - 1) / fan_in ** 0.5
+                if p.dim() > 1:
+                    v = v * gain
+                if "lin_query" in name or "lin_key" in name:
+                    v = v * qk_gain
+            p.copy_(v.to(p.dtype))
+    return module

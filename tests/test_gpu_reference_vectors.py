@@ -1,0 +1,114 @@
+"""GPU parity against vectors produced by executing the reference's own Python.
+
+``tests/golden/ref_*.pt`` come from ``tests/golden/make_reference_golden.py`` (the real
+``GNN_Diffusion`` / ``Eff_GAT`` / ``Exophormer_GNN`` / 3-D sampler code of the reference, run in
+the build container; see that script for what is and is not pinned).  Here the CUDA path -- through
+the Python mirror and the C ABI -- is held to those vectors directly, in every GEMM / attention
+mode, at the 1e-4 relative bar of BASELINE.json's north_star.
+"""
+from pathlib import Path
+
+import pytest
+import torch
+
+import diffassemble_b200 as dab
+from common import TOL, quat_rel_err, rel_err, reseed_parameters
+from test_oracle_pinned import CASES_2D, check_grads
+
+pytestmark = pytest.mark.gpu
+G = Path(__file__).resolve().parent / "golden"
+DEV = "cuda:0"
+MODES = [("fp32", "csr"), ("bf16x3", "csr"), ("bf16x3", "auto"), ("fp32", "auto")]
+
+
+def product_2d(d, gemm, attn, steps=None):
+    mod = dab.GNN_Diffusion(
+        steps=steps or d["T"], sampling=d["sampling"], rotation=d["rotation"], architecture=d["architecture"],
+        virt_nodes=d["virt_nodes"], model_mean_type=dab.ModelMeanType[d["mean_type"]], inference_ratio=d["ratio"],
+        noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1], gemm_mode=gemm, attn_mode=attn)
+    reseed_parameters(mod, d["seed"])
+    return mod.to(DEV)
+
+
+@pytest.mark.parametrize("gemm,attn", MODES)
+@pytest.mark.parametrize("name", CASES_2D)
+def test_cuda_matches_reference_2d(name, gemm, attn):
+    d = torch.load(G / f"ref_{name}.pt")
+    mod = product_2d(d, gemm, attn)
+    x, t, ei, feats, batch = (d[k].to(DEV) for k in ("x", "t", "edge_index", "feats", "batch"))
+    out, atts = mod.forward_with_feats(x, t, None, ei, feats, batch, return_attentions=True)
+    assert rel_err(out, d["out"]) < TOL
+    # attention weights of the last layer, in the reference's edge order (virtual-node wiring included)
+    assert atts[-1][1].shape == d["alpha_last"].shape
+    assert torch.equal(atts[-1][0].cpu(), d["alpha_edge_index"])
+    assert rel_err(atts[-1][1], d["alpha_last"]) < TOL
+    for ti, noise, want in zip(d["step_ts"], d["step_noise"], d["step_out"]):
+        tt = torch.full_like(t, ti)
+        got, _ = mod.p_sample(x, tt, ti, cond=feats, edge_index=ei, patch_feats=feats, batch=batch, noise=noise.to(DEV))
+        assert rel_err(got, want) < TOL, ti
+
+
+@pytest.mark.parametrize("gemm,attn", [("fp32", "csr"), ("bf16x3", "auto")])
+@pytest.mark.parametrize("name", ["dense_ragged_ddim", "exph_2x64_v4_ddim"])
+def test_cuda_matches_reference_sampling_loop(name, gemm, attn):
+    """The reference's ``p_sample_loop`` trajectory (every step), replayed from its own x_T."""
+    d = torch.load(G / f"ref_{name}.pt")
+    mod = product_2d(d, gemm, attn, steps=d["loop_T"])
+    ei, feats, batch = (d[k].to(DEV) for k in ("edge_index", "feats", "batch"))
+    img = d["loop_xT"].to(DEV) * mod.noise_weight
+    M = img.shape[0]
+    for k, i in enumerate(reversed(range(0, d["loop_T"], d["ratio"]))):
+        t = torch.full((M,), i, device=DEV, dtype=torch.long)
+        img, _ = mod.p_sample(img, t, i, cond=feats, edge_index=ei, patch_feats=feats, batch=batch)
+        assert rel_err(img, d["loop_imgs"][k]) < TOL * (k + 1), k
+
+
+@pytest.mark.parametrize("gemm,attn", [("fp32", "csr"), ("bf16x3", "auto")])
+def test_cuda_matches_reference_3d(gemm, attn):
+    d = torch.load(G / "ref_se3_ragged.pt")
+    mod = dab.GNN_Diffusion_3d(steps=d["T"], sampling="DDIM", backbone="pointnet", inference_ratio=d["ratio"],
+                               model_mean_type=dab.ModelMeanType.START_X, noise_weight=1.0, gemm_mode=gemm, attn_mode=attn)
+    reseed_parameters(mod, d["seed"])
+    mod = mod.to(DEV)
+    x, ei, feats, batch = (d[k].to(DEV) for k in ("x", "edge_index", "feats", "batch"))
+    M = x.shape[0]
+    for ti, want_f, want_s in zip(d["step_ts"], d["fwd_out"], d["step_out"]):
+        t = torch.full((M,), ti, device=DEV, dtype=torch.long)
+        out, _ = mod.forward_with_feats(x, t, ei, feats, batch)
+        assert quat_rel_err(out, want_f) < TOL
+        got, _ = mod.p_sample(x, t, ti, edge_index=ei, pcd_feats=feats, batch=batch)
+        assert quat_rel_err(got, want_s) < TOL, ti
+    img = torch.cat([torch.tensor([[1.0, 0, 0, 0]]).repeat(M, 1), d["loop_xT"]], 1).to(DEV)
+    for k, i in enumerate(reversed(range(0, d["T"], d["ratio"]))):
+        t = torch.full((M,), i, device=DEV, dtype=torch.long)
+        img, _ = mod.p_sample(img, t, i, edge_index=ei, pcd_feats=feats, batch=batch)
+        if k == 0:
+            assert quat_rel_err(img, d["loop_imgs"][0]) < TOL
+    assert quat_rel_err(img, d["loop_imgs"][-1]) < TOL * 10  # 30 chained SO(3) log/exp steps
+
+
+def test_cuda_assignment_matches_reference():
+    from diffassemble_b200 import greedy_cost_assignment
+
+    d = torch.load(G / "ref_assignment.pt")
+    for key, c in d.items():
+        got = greedy_cost_assignment(c["pos1"].to(DEV), c["pos2"].to(DEV)).cpu()
+        assert torch.equal(got[:, :2], c["assignment"][:, :2]), key   # index output: bit-exact
+        assert torch.equal(got[:, 2], c["assignment"][:, 2]), key     # truncated distance column
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", ["dense", "exph_v4"])
+def test_cuda_training_loss_and_gradients_match_reference(name, gemm):
+    d = torch.load(G / f"ref_train_{name}.pt")
+    mod = dab.GNN_Diffusion(steps=d["T"], sampling="DDIM", rotation=True, architecture=d["architecture"],
+                            virt_nodes=d["virt_nodes"], model_mean_type=dab.ModelMeanType[d["mean_type"]],
+                            gemm_mode=gemm, attn_mode="csr")
+    reseed_parameters(mod, d["seed"])
+    mod = mod.to(DEV).train()
+    loss = mod.p_losses(d["x0"].to(DEV), d["t"].to(DEV), noise=d["noise"].to(DEV), loss_type="huber",
+                        cond=d["feats"].to(DEV), edge_index=d["edge_index"].to(DEV), batch=d["batch"].to(DEV))
+    assert abs(loss.item() - d["loss"].item()) < 1e-5 * abs(d["loss"].item())
+    loss.backward()
+    n = check_grads({k: p.grad for k, p in mod.named_parameters()}, d["grads"], 1e-3)
+    assert n >= 40
