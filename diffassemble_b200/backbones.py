@@ -165,6 +165,7 @@ class _EngineMixin:
         if gkey != self._graph_key:
             ext, num_total, virt_ids = self.gnn_backbone.extend_graph(edge_index, batch)
             eng.set_graph(ext, batch, num_real=len(batch), num_total=num_total, virt_ids=virt_ids)
+            self._ext_edge_index = ext  # what TransformerConv sees: the reference returns THIS with alpha
             self._graph_key = gkey
             self._feats_key = None
         fkey = self._tensor_key(feats) if feats is not None else "zero"
@@ -235,7 +236,7 @@ class Eff_GAT(nn.Module, _EngineMixin):
         eng = self.engine_for(edge_index, patch_feats, batch)
         if return_attention:
             out, alpha = eng.forward(xy_pos, time, return_alpha=True)
-            return out, [(edge_index, alpha)]
+            return out, [(self._ext_edge_index, alpha)]  # exophormer_gnn.py:203-208: edge list incl. virtual wiring
         return eng.forward(xy_pos, time), None
 
     def visual_features(self, patch_rgb):

@@ -1,4 +1,5 @@
-"""Known-answer tests that anchor the CPU oracle (the reference ships none: parity unpinned).
+"""Known-answer tests that anchor the CPU oracle -- in particular the two un-vendored third-party pieces
+(``TransformerConv``, pytorch3d's quaternion conversions) that ``test_oracle_pinned.py`` cannot pin.
 
 Each test states a property of the reference formulation that must
 hold independently of weights."""

@@ -131,18 +131,26 @@ def test_greedy_assignment_matches_reference():
 
 
 def check_grads(named_grads, want, tol):
-    """Compare gradients with the fixture's (full tensors when small, else sum / abs-sum / strided samples)."""
+    """Compare gradients with the fixture's (full tensors when small, else abs-sum + strided samples).
+
+    Gradients that are exactly zero in theory (``lin_key.bias``: the softmax is invariant to a shift of
+    the keys) are ~1e-10 cancellation noise in the reference itself; those only have to stay negligible."""
+    gmax = max(w["samples"].abs().max().item() for w in want.values())
     seen = 0
     for k, w in want.items():
         g = named_grads[k]
         assert g is not None, k
         gflat = g.detach().flatten().cpu()
-        scale = max(w["abssum"] / gflat.numel(), 1e-12)
-        if w["full"] is not None:
-            assert (g.detach().cpu() - w["full"]).abs().max().item() <= tol * max(w["full"].abs().max().item(), scale), k
         samples = gflat[:: max(1, gflat.numel() // 64)][:64]
-        assert (samples - w["samples"]).abs().max().item() <= tol * max(w["samples"].abs().max().item(), scale), k
-        assert abs(gflat.double().abs().sum().item() - w["abssum"]) <= tol * w["abssum"] + 1e-12, k
+        wmax = w["samples"].abs().max().item() if w["full"] is None else w["full"].abs().max().item()
+        if w["abssum"] < 1e-7 * gmax * gflat.numel():
+            assert gflat.abs().max().item() < 1e-6 * gmax, k
+            continue
+        wmax = max(wmax, w["abssum"] / gflat.numel())  # sparse gradients (time_emb): the samples may all be 0
+        if w["full"] is not None:
+            assert (g.detach().cpu() - w["full"]).abs().max().item() <= tol * wmax, k
+        assert (samples - w["samples"]).abs().max().item() <= tol * wmax, k
+        assert abs(gflat.double().abs().sum().item() - w["abssum"]) <= tol * w["abssum"], k
         seen += 1
     return seen
 
@@ -158,4 +166,4 @@ def test_oracle_training_loss_and_gradients_match_reference(name):
     assert abs(loss.item() - d["loss"].item()) < 1e-6 * abs(d["loss"].item())
     loss.backward()
     n = check_grads({k: p.grad for k, p in ref.named_parameters()}, d["grads"], 2e-5)
-    assert n >= 40
+    assert n >= 38
