@@ -5,6 +5,7 @@
 #include <cstring>
 #include <cstdio>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -64,6 +65,9 @@ struct da_handle {
   bool use_plan = false;
   int num_real = 0, num_total = 0;
   int dbg_layer = -1;
+  // development switches (environment, read once per handle): DA_NO_FUSE=1 keeps the un-fused
+  // dense -> (acc, stats) -> CSR-continuation pipeline for A/B measurements
+  bool no_fuse = getenv("DA_NO_FUSE") != nullptr && getenv("DA_NO_FUSE")[0] == '1';
   void* dbg_trace = nullptr;   // development aid: clock64 trace buffer for the dense attention kernel
   DevBuf qimg, kimg, vimg, qimg_l, kimg_l, vimg_l, dacc, dstats;   // operand images: hidden layers / last layer
   // activations / workspace
@@ -194,13 +198,20 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     __nv_bfloat16* qimg = (last ? h->qimg_l : h->qimg).as<__nv_bfloat16>();
     __nv_bfloat16* kimg = (last ? h->kimg_l : h->kimg).as<__nv_bfloat16>();
     __nv_bfloat16* vimg = (last ? h->vimg_l : h->vimg).as<__nv_bfloat16>();
+    // rows of dense tiles with at most DA_FUSE_MAX_RESIDUAL residual in-edges are finalised by the dense kernel itself
+    const bool fuse = dense && attn_csr_rows_supported(c.heads, C) && !alpha_last && h->plan.n_fused > 0 && !h->no_fuse &&
+                      attn_dense_can_fuse(C);
+    const bool fold_resid = fuse && last && umma;   // trunk residual folded into the skip columns by the GEMM epilogue
     {
       LinearOut o; o.f32 = h->qkvs.as<float>(); o.ldc = 4 * HC;
       if (dense && umma) {  // Q / K / V operand images straight from the GEMM epilogue
         o.img_node_slot = h->plan.node_slot; o.qimg = qimg; o.kimg = kimg; o.vimg = vimg;
         o.img_H = c.heads; o.img_C = C; o.img_Cpad = Cpad; o.img_rows = Mr;
-        if (attn_csr_rows_supported(c.heads, C) && !alpha_last) o.f32_tile_flags = h->plan.f32_tile_flags[last ? 1 : 0];
+        // the flags assume the fused rows take Q from TMEM (plan.cu)
+        if (attn_csr_rows_supported(c.heads, C) && !alpha_last && (fuse || h->plan.n_fused == 0))
+          o.f32_tile_flags = h->plan.f32_tile_flags[last ? 1 : 0];
       }
+      if (fold_resid) { o.addend = h->combined.as<float>(); o.ld_addend = D; o.addend_col0 = 3 * HC; o.addend_rows = Mr; }
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
       DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
@@ -214,15 +225,9 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
         Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
         DA_CK(launch_pack_images(pa, s), "pack images");
       }
-      AttnDenseArgs da_{};
-      da_.qimg = pa.qimg; da_.kimg = pa.kimg; da_.vimg = pa.vimg;
-      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
-      da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
-      da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
-      da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
-      {
-        Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
-        DA_CK(launch_attn_dense(da_, s), "dense attention");
+      if (h->plan.n_extra > 0) {  // copies of the promoted residual sources' K / V rows into the padding image rows
+        Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
+        DA_CK(launch_gather_extra(pa, h->plan.x_src, h->plan.x_slot, h->plan.n_extra, s), "gather extra sources");
       }
     }
     AttnCsrArgs a{};
@@ -250,13 +255,31 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
       xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
     }
+    if (fold_resid) a.resid = nullptr;   // already inside the skip columns
+    if (dense) {
+      AttnDenseArgs da_{};
+      da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;
+      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
+      da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
+      da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
+      da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
+      if (fuse) {
+        da_.row_fused = h->plan.row_fused;
+        da_.qkvs = a.qkvs; da_.ld = a.ld;
+        da_.rowptr = csr.rowptr; da_.col = csr.col; da_.weight = csr.weight;
+        da_.resid = a.resid; da_.ld_resid = a.ld_resid; da_.act = a.act; da_.out = a.out;
+      }
+      Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
+      DA_CK(launch_attn_dense(da_, s), "dense attention");
+    }
     if (h->use_plan && attn_csr_rows_supported(c.heads, C) && !a.scores) {
       // residual edges: low-degree rows on the warp-per-node kernel, heavy rows (virtual nodes) edge-parallel
       const DensePlan& pl = h->plan;
       AttnCsrArgs hv = a, lt = a;
       hv.node_list = pl.heavy; hv.n_targets = last ? pl.n_heavy_real : pl.n_heavy;
       if (dense && umma) { hv.img_slot = pl.node_slot; hv.kimg = kimg; hv.vimg = vimg; hv.img_Cpad = Cpad; }
-      lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light;
+      if (fuse) { lt.node_list = pl.light_nf; lt.n_targets = last ? pl.n_light_nf_real : pl.n_light_nf; }
+      else { lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light; }
       if (hv.n_targets > 0) {
         Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
         DA_CK(launch_attn_csr_heavy(hv, s), "graph attention (heavy rows)");
@@ -845,6 +868,8 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
   __nv_bfloat16 *qi = nullptr, *ki = nullptr, *vi = nullptr;
   float *acc = nullptr, *st = nullptr;
   int rc = DA_OK;
+  const bool fuse = plan.n_tiles > 0 && plan.n_fused > 0 && attn_csr_rows_supported(H, C) && attn_dense_can_fuse(C) &&
+                    !(getenv("DA_NO_FUSE") && getenv("DA_NO_FUSE")[0] == '1');
   const size_t img = dense_image_elems(plan.n_tiles > 0 ? plan.n_tiles : 1, H, Cpad) * sizeof(__nv_bfloat16);
   if (cudaMalloc(&qi, img) != cudaSuccess || cudaMalloc(&ki, img) != cudaSuccess || cudaMalloc(&vi, img) != cudaSuccess ||
       cudaMalloc(&acc, sizeof(float) * (size_t)n * H * C) != cudaSuccess || cudaMalloc(&st, sizeof(float) * (size_t)n * H * 2) != cudaSuccess) {
@@ -855,8 +880,14 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
     if (plan.n_tiles > 0) {
       PackArgs pa{qkvs, 4 * H * C, plan.node_slot, n, H, C, Cpad, qi, ki, vi};
       ce = launch_pack_images(pa, s);
+      if (ce == cudaSuccess) ce = launch_gather_extra(pa, plan.x_src, plan.x_slot, plan.n_extra, s);
       if (ce == cudaSuccess) {
         AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st, nullptr};
+        if (fuse) {
+          da_.row_fused = plan.row_fused; da_.qkvs = qkvs; da_.ld = 4 * H * C;
+          da_.rowptr = plan.residual.rowptr; da_.col = plan.residual.col; da_.weight = plan.residual.weight;
+          da_.act = ACT_NONE; da_.out.f32 = y; da_.out.ldc = H * C;
+        }
         ce = launch_attn_dense(da_, s);
       }
     }
@@ -868,7 +899,8 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
       if (attn_csr_rows_supported(H, C)) {
         AttnCsrArgs hv = a, lt = a;
         hv.node_list = plan.heavy; hv.n_targets = plan.n_heavy;
-        lt.node_list = plan.light; lt.n_targets = plan.n_light;
+        if (fuse) { lt.node_list = plan.light_nf; lt.n_targets = plan.n_light_nf; }
+        else { lt.node_list = plan.light; lt.n_targets = plan.n_light; }
         ce = launch_attn_csr_heavy(hv, s);
         if (ce == cudaSuccess) ce = launch_attn_csr_rows(lt, s);
       } else {

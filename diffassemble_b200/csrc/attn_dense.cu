@@ -90,6 +90,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -177,6 +182,40 @@ __global__ void pack_images_kernel(PackArgs a) {
   }
 }
 
+// K / V rows of the plan's extra sources -> their (padding) image rows.  One warp per (entry, part); lanes over
+// (head, 8-channel chunk) items.
+__global__ void gather_extra_kernel(PackArgs a, const int32_t* __restrict__ x_src, const int32_t* __restrict__ x_slot, int n_extra) {
+  const int lane = threadIdx.x & 31;
+  const int wg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (wg >= n_extra * 2) return;
+  const int ent = wg >> 1, part = 1 + (wg & 1);   // 1 = K, 2 = V
+  const int node = x_src[ent], slot = x_slot[ent];
+  const int HC = a.H * a.C, chunks = a.Cpad / 8;
+  const int blk = slot >> 6, rb = slot & 63;
+  const float* row = a.qkvs + (size_t)node * a.ld + part * HC;
+  for (int it = lane; it < a.H * chunks; it += 32) {
+    const int h = it / chunks, ch = it % chunks, c = ch * 8;
+    __nv_bfloat16 hi[8], lo[8];
+    if (c < a.C) {
+      const float4 v0 = *reinterpret_cast<const float4*>(row + h * a.C + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(row + h * a.C + c + 4);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hi[e] = __float2bfloat16_rn(v[e]);
+        lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { hi[e] = __float2bfloat16_rn(0.f); lo[e] = hi[e]; }
+    }
+    __nv_bfloat16* base = (part == 1 ? a.kimg : a.vimg) + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
+    const size_t off = (size_t)ch * (TS * 8) + (size_t)rb * 8;
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + (size_t)TS * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
 struct DenseSmem {
   uint64_t q_full;
   uint64_t k_full[MAXST], k_empty[MAXST];
@@ -184,6 +223,7 @@ struct DenseSmem {
   uint64_t s_full[2];    // MMA -> softmax: S_j is in TMEM buffer j & 1
   uint64_t p_full[2];    // softmax -> MMA: P_j (bf16 hi/lo) has replaced S_j in the same TMEM columns
   uint64_t pv_done[2];   // MMA -> both:   P_j V_j retired (buffer free again, O holds blocks <= j)
+  uint64_t epi_full;     // fused epilogue: every row's skip values have landed in the (by then idle) K ring
   uint32_t tmem_base;
 };
 
@@ -229,6 +269,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1); }
+    mbar_init(&sh->epi_full, 128);   // one arrive (+ expected bytes) per softmax thread
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -365,6 +406,13 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->q_full);
     }
+    const int node = ti.node0 + r;
+    const int HC = a.H * a.C;
+    // fused finalisation (see the epilogue): this row's skip values are staged in the K ring, one row per
+    // thread, padded by 16 bytes so that the per-row float4 reads are bank-conflict free
+    const bool fused = a.row_fused != nullptr && row_valid && a.row_fused[node] != 0;
+    const uint32_t epi_pitch = (uint32_t)a.C * 4u + 16u;
+    const float* epi_row = reinterpret_cast<const float*>(k_sm + (size_t)r * epi_pitch);
     float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
     uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
@@ -375,6 +423,13 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 1] = clock64();   // S_j ready
       tc_fence_after();
+      if (a.row_fused != nullptr && j == nblk - 1) {
+        // S of the LAST block has retired, so no MMA reads the K ring any more: start copying this row's skip
+        // values into it now; the copy runs under the last softmax + PV and is waited for in the epilogue
+        const uint32_t bytes = fused ? (uint32_t)a.C * 4u : 0u;
+        mbar_expect_tx(&sh->epi_full, bytes);
+        if (fused) bulk_load(const_cast<float*>(epi_row), a.qkvs + (size_t)node * a.ld + 3 * HC + head * a.C, bytes, &sh->epi_full);
+      }
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
       if (j == 0) {  // first block: take its masked max as the reference point
         uint32_t v[TS];
@@ -447,29 +502,188 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       if (lane == 0) mbar_arrive(&sh->p_full[b]);
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 2] = clock64();   // P_j published
     }
-    // epilogue: un-normalised O and (m, l) to global
+    // epilogue
     mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
-    const int node = ti.node0 + r;
-    const int HC = a.H * a.C;
-    for (int c0 = 0; c0 < Cpad; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_o + lane_off + c0, v);
-      tmem_ld_wait();
-      if (row_valid) {
-        float* dst = a.acc + (size_t)node * HC + head * a.C + c0;
-        if (c0 + 16 <= a.C && (a.C & 3) == 0) {
+    // ---- fused finalisation (rows flagged by the planner): continue the online softmax over this row's
+    // (<= DA_FUSE_MAX_RESIDUAL) residual in-edges, normalise, + skip (+ trunk residual), activation, store the
+    // layer output.  Same arithmetic as attn_csr_rows_kernel, minus the (acc, stats) round trip through HBM.
+    // tcgen05.ld / wait are warp-collective, so those are executed by every lane and only the per-row work
+    // is predicated.
+    constexpr int RM = DA_FUSE_MAX_RESIDUAL;
+    int n_e = 0;
+    int src[RM]; float pe[RM], wgt[RM], d[RM];
+    float o_scale = 0.f;
+    if (fused) {
+      const int beg = a.rowptr[node];
+      n_e = a.rowptr[node + 1] - beg;
 #pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                               __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        } else {
-          for (int e = 0; e < 16; ++e)
-            if (c0 + e < a.C) dst[e] = __uint_as_float(v[e]);
+      for (int e = 0; e < RM; ++e) {
+        src[e] = (e < n_e) ? a.col[beg + e] : node;
+        wgt[e] = (e < n_e) ? (a.weight ? a.weight[beg + e] : 1.f) : 0.f;
+        d[e] = 0.f;
+      }
+    }
+    if (__any_sync(0xffffffffu, n_e > 0)) {
+      // raw (unscaled) scores q . k_j in the units of m.  Q comes back from TMEM (this lane's row, split-bf16
+      // hi + lo planes: the same operand the tensor-core scores used), K_j from the source's fp32 row.
+      for (int c0 = 0; c0 < Cpad; c0 += 16) {   // 16 channels = 8 TMEM columns of packed pairs per plane
+        uint32_t qh[8], ql[8];
+        tmem_ld8(tmem_q + lane_off + (uint32_t)(c0 >> 1), qh);
+        tmem_ld8(tmem_q + lane_off + (uint32_t)((Cpad >> 1) + (c0 >> 1)), ql);
+        float4 kk[RM][4];
+#pragma unroll
+        for (int e = 0; e < RM; ++e) {
+          if (e < n_e) {
+            const float* krow = a.qkvs + (size_t)src[e] * a.ld + HC + head * a.C + c0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              kk[e][u] = (c0 + 4 * u < a.C) ? __ldg(reinterpret_cast<const float4*>(krow + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tmem_ld_wait();
+        float qf[16];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          qf[2 * w] = __uint_as_float(qh[w] << 16) + __uint_as_float(ql[w] << 16);
+          qf[2 * w + 1] = __uint_as_float(qh[w] & 0xffff0000u) + __uint_as_float(ql[w] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int e = 0; e < RM; ++e) {
+          if (e < n_e) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              d[e] = fmaf(qf[4 * u], kk[e][u].x, fmaf(qf[4 * u + 1], kk[e][u].y,
+                     fmaf(qf[4 * u + 2], kk[e][u].z, fmaf(qf[4 * u + 3], kk[e][u].w, d[e]))));
+          }
         }
       }
     }
-    if (row_valid) {
+    if (fused) {
+      float m_fin = m;
+#pragma unroll
+      for (int e = 0; e < RM; ++e) if (e < n_e) m_fin = fmaxf(m_fin, d[e]);
+      // m == -inf: no bitmap edge on this row (O and l are exactly 0); m_fin == -inf: no in-edge at all
+      const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_fin) * c_log2);
+      float l_fin = l * alpha;
+#pragma unroll
+      for (int e = 0; e < RM; ++e) {
+        pe[e] = (e < n_e) ? wgt[e] * ex2_approx((d[e] - m_fin) * c_log2) : 0.f;
+        l_fin += pe[e];
+      }
+      const float inv = 1.f / (l_fin + 1e-16f);
+      o_scale = alpha * inv;
+#pragma unroll
+      for (int e = 0; e < RM; ++e) pe[e] *= inv;
+    }
+    if (a.row_fused != nullptr) mbar_wait(&sh->epi_full, 0);   // skip rows are in shared memory
+    const float* rsd = a.resid ? a.resid + (size_t)node * a.ld_resid + head * a.C : nullptr;
+    const bool vec = (a.C & 3) == 0;
+    for (int c0 = 0; c0 < Cpad; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_o + lane_off + c0, v);
+      float4 vv[RM][4];   // V rows of the residual sources: issued before the TMEM wait
+#pragma unroll
+      for (int ee = 0; ee < RM; ++ee) {
+        if (ee < n_e) {
+          const float* vrow = a.qkvs + (size_t)src[ee] * a.ld + 2 * HC + head * a.C + c0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            vv[ee][u] = (c0 + 4 * u < a.C) ? __ldg(reinterpret_cast<const float4*>(vrow + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tmem_ld_wait();   // warp-collective as well: keep it outside the per-row branches
+      if (fused) {
+        float y[16];
+        if (vec && c0 + 16 <= a.C) {
+#pragma unroll
+          for (int e4 = 0; e4 < 16; e4 += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(epi_row + c0 + e4);
+            y[e4] = t.x; y[e4 + 1] = t.y; y[e4 + 2] = t.z; y[e4 + 3] = t.w;
+          }
+          if (rsd) {
+#pragma unroll
+            for (int e4 = 0; e4 < 16; e4 += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rsd + c0 + e4));
+              y[e4] += t.x; y[e4 + 1] += t.y; y[e4 + 2] += t.z; y[e4 + 3] += t.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            y[e] = (c0 + e < a.C) ? epi_row[c0 + e] : 0.f;
+            if (rsd && c0 + e < a.C) y[e] += __ldg(rsd + c0 + e);
+          }
+        }
+        // reference order: (attention + skip) + resid; the attention term is added to the pre-summed rest
+        float att[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) att[e] = __uint_as_float(v[e]) * o_scale;
+#pragma unroll
+        for (int ee = 0; ee < RM; ++ee) {
+          if (ee < n_e) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              att[4 * u] = fmaf(pe[ee], vv[ee][u].x, att[4 * u]); att[4 * u + 1] = fmaf(pe[ee], vv[ee][u].y, att[4 * u + 1]);
+              att[4 * u + 2] = fmaf(pe[ee], vv[ee][u].z, att[4 * u + 2]); att[4 * u + 3] = fmaf(pe[ee], vv[ee][u].w, att[4 * u + 3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) y[e] = apply_act_rt(att[e] + y[e], a.act);
+        const int nval = (a.C - c0) < 16 ? (a.C - c0) : 16;   // valid channels of this chunk (> 0: Cpad - C < 16)
+        if (a.out.f32) {
+          float* dst = a.out.f32 + (size_t)node * a.out.ldc + head * a.C + c0;
+          if (vec && nval == 16) {
+#pragma unroll
+            for (int e4 = 0; e4 < 16; e4 += 4)
+              *reinterpret_cast<float4*>(dst + e4) = make_float4(y[e4], y[e4 + 1], y[e4 + 2], y[e4 + 3]);
+          } else {
+            for (int e = 0; e < nval; ++e) dst[e] = y[e];
+          }
+        }
+        if (a.out.hi) {
+          uint32_t hh[8], ll[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const uint32_t h2 = pack_bf16x2(y[e], y[e + 1]);
+            hh[e >> 1] = h2;
+            ll[e >> 1] = pack_bf16x2(y[e] - __uint_as_float(h2 << 16), y[e + 1] - __uint_as_float(h2 & 0xffff0000u));
+          }
+          __nv_bfloat16* dh = a.out.hi + (size_t)node * a.out.ld_split + head * a.C + c0;
+          __nv_bfloat16* dl = a.out.lo + (size_t)node * a.out.ld_split + head * a.C + c0;
+          if (nval == 16 && (a.C & 7) == 0 && (a.out.ld_split & 7) == 0) {
+            *reinterpret_cast<uint4*>(dh) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(dh + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            *reinterpret_cast<uint4*>(dl) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4*>(dl + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+          } else {
+            for (int e = 0; e < nval; ++e) {
+              const uint32_t hw = hh[e >> 1], lw = ll[e >> 1];
+              const unsigned short hb = (e & 1) ? (unsigned short)(hw >> 16) : (unsigned short)(hw & 0xffffu);
+              const unsigned short lb = (e & 1) ? (unsigned short)(lw >> 16) : (unsigned short)(lw & 0xffffu);
+              reinterpret_cast<unsigned short*>(dh)[e] = hb;
+              reinterpret_cast<unsigned short*>(dl)[e] = lb;
+            }
+          }
+        }
+      } else {
+        // un-normalised O to global; attn_csr.cu continues over the residual edges
+        if (row_valid) {
+          float* dst = a.acc + (size_t)node * HC + head * a.C + c0;
+          if (c0 + 16 <= a.C && (a.C & 3) == 0) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                 __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          } else {
+            for (int e = 0; e < 16; ++e)
+              if (c0 + e < a.C) dst[e] = __uint_as_float(v[e]);
+          }
+        }
+      }
+    }
+    if (row_valid && !fused) {
       float* st = a.stats + ((size_t)node * a.H + head) * 2;
       st[0] = (m == -INFINITY) ? -INFINITY : m / sqrtf((float)a.C);  // natural-log units of the scaled score
       st[1] = l;
@@ -497,20 +711,46 @@ cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
-  if (a.n_tiles <= 0) return cudaSuccess;
-  const int Cpad = a.Cpad;
-  if (Cpad % 16 || Cpad > 256 || Cpad < 16) return cudaErrorInvalidValue;
+cudaError_t launch_gather_extra(const PackArgs& a, const int32_t* x_src, const int32_t* x_slot, int n_extra, cudaStream_t s) {
+  if (n_extra <= 0) return cudaSuccess;
+  if ((a.C % 8) || (a.ld % 4) || a.Cpad % 16 || a.Cpad < a.C) return cudaErrorInvalidValue;
+  const long long threads = (long long)n_extra * 2 * 32;
+  gather_extra_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, x_src, x_slot, n_extra);
+  return cudaGetLastError();
+}
+
+namespace {
+// TMEM columns, K / V ring depth and dynamic shared memory of the kernel for a padded head dim
+bool dense_config(int Cpad, int* cols_out, int* st_out, size_t* smem_out) {
+  if (Cpad % 16 || Cpad > 256 || Cpad < 16) return false;
   int need = 2 * TS + 2 * Cpad, cols = 32;   // S/P double buffer + O + Q
   while (cols < need) cols <<= 1;
-  if (cols > 512) return cudaErrorInvalidValue;
+  if (cols > 512) return false;
   auto smem_for = [&](int st) { return (size_t)(2 * st) * 2 * TS * Cpad * 2 + sizeof(DenseSmem) + 128; };
   const size_t limit = 227 * 1024;
   // K / V ring depth: 4 when two CTAs still fit per SM (small head dims), else 3, else 2
   int st = 4;
   if (cols <= 256 ? (2 * smem_for(4) + 2048 > limit) : (smem_for(4) > limit)) st = (smem_for(3) <= limit) ? 3 : 2;
-  const size_t smem = smem_for(st);
-  if (smem > limit) return cudaErrorInvalidValue;
+  if (smem_for(st) > limit) return false;
+  *cols_out = cols; *st_out = st; *smem_out = smem_for(st);
+  return true;
+}
+}  // namespace
+
+bool attn_dense_can_fuse(int C) {
+  const int Cpad = (C + 15) / 16 * 16;
+  int cols, st; size_t smem;
+  if ((C & 3) || !dense_config(Cpad, &cols, &st, &smem)) return false;
+  // 128 staged skip rows of (4 C + 16) bytes must fit the K ring (st stages of 2 planes of 64 x Cpad bf16)
+  return (size_t)TM * ((size_t)C * 4 + 16) <= (size_t)st * 2 * TS * Cpad * 2;
+}
+
+cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
+  if (a.n_tiles <= 0) return cudaSuccess;
+  const int Cpad = a.Cpad;
+  int cols, st; size_t smem;
+  if (!dense_config(Cpad, &cols, &st, &smem)) return cudaErrorInvalidValue;
+  if (a.row_fused != nullptr && !attn_dense_can_fuse(a.C)) return cudaErrorInvalidValue;
   const unsigned grid = a.n_tiles * a.H;
 #define DA_LAUNCH(CP, ST_)                                                                                          \
   do {                                                                                                              \

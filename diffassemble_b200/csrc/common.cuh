@@ -62,6 +62,11 @@ struct LinearOut {
   // optional per-128-row-tile flags (bit 0: some row's fp32 Q is read later, bit 1: some row's fp32 K / V is):
   // tiles whose Q / K / V only feed the tensor-core attention skip those fp32 stores (HBM-write-bound GEMMs).
   const uint8_t* f32_tile_flags = nullptr;
+  // optional: rows [0, addend_rows) of `addend` ([*, ld_addend] fp32) are added to the fp32 output columns
+  // [addend_col0, addend_col0 + ...) after bias / activation.  The last layer folds the trunk residual
+  // `combined` into the skip part this way, so the attention epilogue reads ONE row instead of two.
+  const float* addend = nullptr;
+  int ld_addend = 0, addend_col0 = 0, addend_rows = 0;
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
@@ -240,6 +245,20 @@ struct DensePlan {
   // "heavy" rows (virtual nodes with hundreds of in-edges) the edge-parallel one.  Real nodes first.
   int32_t* light = nullptr; int n_light = 0, n_light_real = 0;
   int32_t* heavy = nullptr; int n_heavy = 0, n_heavy_real = 0;
+  // rows finalised inside the dense kernel (in a dense tile, <= DA_FUSE_MAX_RESIDUAL residual in-edges), and the
+  // light rows that are NOT (outside every tile, or more residual edges): the CSR rows kernel only sees the latter
+  uint8_t* row_fused = nullptr;    // [n_total] device
+  int n_fused = 0;
+  // "promoted" residual edges: a multiplicity-one residual in-edge of a dense-tile row whose source is not a
+  // column of the row's graph (virtual-node wiring, cross-graph edges, the second copy of a duplicate) becomes a
+  // bitmap bit on an EXTRA column of that graph: a copy of the source's K / V rows is placed in one of the padding
+  // image rows behind the graph's own nodes (gather_extra kernel, once per layer).  The tensor-core kernel then
+  // covers those edges for free and the rows need no CSR continuation at all.
+  int n_extra = 0;                 // extra columns over all graphs
+  int32_t* x_src = nullptr;        // [n_extra] device: node whose K / V rows are copied
+  int32_t* x_slot = nullptr;       // [n_extra] device: destination image row (tile * 128 + r)
+  int64_t n_promoted_edges = 0;
+  int32_t* light_nf = nullptr; int n_light_nf = 0, n_light_nf_real = 0;
   // per 128-row tile of the node index space: bit 0 = a row has residual in-edges (its fp32 Q is read),
   // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
   uint8_t* f32_tile_flags[2] = {nullptr, nullptr};
@@ -257,6 +276,8 @@ struct PackArgs {
   __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
 };
 cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s);
+// copies the fp32 K / V rows of the plan's extra sources into their image rows (PackArgs: node_slot unused)
+cudaError_t launch_gather_extra(const PackArgs& a, const int32_t* x_src, const int32_t* x_slot, int n_extra, cudaStream_t s);
 
 struct AttnDenseArgs {
   const __nv_bfloat16* qimg; const __nv_bfloat16* kimg; const __nv_bfloat16* vimg;
@@ -266,7 +287,20 @@ struct AttnDenseArgs {
   float* acc;    // [n, H*C] un-normalised sum_e exp(a_e - m) v_e of the bitmap edges
   float* stats;  // [n, H, 2] (m, l) of the bitmap edges, natural-log units
   long long* dbg;  // optional timing trace of CTA 0 (clock64 stamps); null in production
+  // Fused finalisation (optional, row_fused != null): rows with row_fused[node] != 0 have at most
+  // DA_FUSE_MAX_RESIDUAL residual in-edges; the dense kernel's epilogue continues the online softmax over them
+  // (fp32 Q / K / V rows of `qkvs`), normalises, adds skip (+ resid), applies `act` and writes the layer
+  // output itself -- no (acc, stats) round trip through HBM and no CSR continuation launch for those rows.
+  const uint8_t* row_fused = nullptr;
+  const float* qkvs = nullptr; int ld = 0;      // [n, 4*H*C] rows [Q | K | V | skip]
+  const int32_t* rowptr = nullptr; const int32_t* col = nullptr; const float* weight = nullptr;   // residual CSR
+  const float* resid = nullptr; int ld_resid = 0;   // optional second addend read straight from global (slow path)
+  int act = 0;
+  LinearOut out;
 };
+constexpr int DA_FUSE_MAX_RESIDUAL = 2;
+// true when the fused epilogue's staging area (128 skip rows of C floats) fits the kernel's K ring
+bool attn_dense_can_fuse(int C);
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s);
 size_t dense_image_elems(int n_tiles, int H, int Cpad);  // elements of ONE of the q / k / v image buffers
 

@@ -8,6 +8,7 @@
 // softmax over all in-edges (exophormer_gnn.py:198-200 wiring included).
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -52,6 +53,12 @@ __global__ void classify_edges_kernel(const int64_t* __restrict__ src, const int
   flag[e] = residual;
 }
 
+__global__ void set_bits_kernel(const int64_t* __restrict__ word, const uint32_t* __restrict__ bit, int n,
+                                uint32_t* __restrict__ bitmap) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicOr(bitmap + word[i], bit[i]);
+}
+
 __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, int32_t* __restrict__ bad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i + 1 < n && batch[i + 1] < batch[i]) atomicExch(bad, 1);
@@ -62,7 +69,7 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 
 void free_plan(DensePlan* p) {
   if (!p) return;
-  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy); cudaFree(p->f32_tile_flags[0]); cudaFree(p->f32_tile_flags[1]);
+  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy); cudaFree(p->row_fused); cudaFree(p->light_nf); cudaFree(p->x_src); cudaFree(p->x_slot); cudaFree(p->f32_tile_flags[0]); cudaFree(p->f32_tile_flags[1]);
   free_csr(&p->residual);
   *p = DensePlan();
 }
@@ -77,9 +84,10 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
 #define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
   std::vector<int64_t> hbatch(num_real);
   std::vector<unsigned long long> hcnt;
-  std::vector<int32_t> g_node0, g_n, g_bm_words, node_slot(num_total, -1);
+  std::vector<int32_t> g_node0, g_n, g_bm_words, g_tile0, node_slot(num_total, -1);
   std::vector<int64_t> g_bm_off;
   std::vector<TileInfo> tiles;
+  std::vector<int32_t> extra_sources;
   unsigned long long* dcnt = nullptr;
   int32_t *d_g_node0 = nullptr, *d_g_bm_words = nullptr, *d_bad = nullptr;
   int64_t *d_g_bm_off = nullptr, *res_src = nullptr, *res_dst = nullptr, *d_nsel = nullptr;
@@ -104,7 +112,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   } else {
     B = (int)hbatch[num_real - 1] + 1;
   }
-  g_node0.assign(B, 0); g_n.assign(B, 0); g_bm_words.assign(B, 0); g_bm_off.assign(B, -1);
+  g_node0.assign(B, 0); g_n.assign(B, 0); g_bm_words.assign(B, 0); g_bm_off.assign(B, -1); g_tile0.assign(B, -1);
   for (int i = 0; i < num_real && B > 0; ++i) g_n[hbatch[i]]++;
   for (int g = 1; g < B; ++g) g_node0[g] = g_node0[g - 1] + g_n[g - 1];
   if (B > 0 && E > 0) {
@@ -123,9 +131,9 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     const long long n = g_n[g];
     if (n < MIN_DENSE_NODES || (long long)hcnt[g] * DENSITY_DIV < n * n) continue;
     const int ntile = (int)((n + 127) / 128);
-    const int nblk64 = (int)((n + 63) / 64);
-    g_bm_words[g] = nblk64 * 2;
+    g_bm_words[g] = ntile * 4;   // one bit per image row of the graph (its nodes + the padding rows extra sources may use)
     g_bm_off[g] = (int64_t)words;
+    g_tile0[g] = (int)tiles.size();
     words += (size_t)ntile * 128 * g_bm_words[g];
     for (int t = 0; t < ntile; ++t) {
       TileInfo ti;
@@ -149,8 +157,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   DA_TRY(cudaMalloc(&plan->node_slot, sizeof(int32_t) * (size_t)num_total));
   DA_TRY(cudaMemcpyAsync(plan->node_slot, node_slot.data(), sizeof(int32_t) * (size_t)num_total, cudaMemcpyHostToDevice, s));
   if (plan->n_tiles > 0) {
-    DA_TRY(cudaMalloc(&plan->tiles, sizeof(TileInfo) * tiles.size()));
-    DA_TRY(cudaMemcpyAsync(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, s));
+    DA_TRY(cudaMalloc(&plan->tiles, sizeof(TileInfo) * tiles.size()));   // uploaded after the promotion pass (gn may grow)
     DA_TRY(cudaMalloc(&plan->bitmap, sizeof(uint32_t) * words));
     DA_TRY(cudaMemsetAsync(plan->bitmap, 0, sizeof(uint32_t) * words, s));
     DA_TRY(tmp_alloc(&d_g_node0, sizeof(int32_t) * B, s));
@@ -186,15 +193,104 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     if (ce != cudaSuccess) goto fail;
   }
   DA_TRY(cudaStreamSynchronize(s));
-  {  // degree classes of the residual CSR (node order kept, real nodes before virtual rows)
-    std::vector<int32_t> rp((size_t)num_total + 1), light, heavy;
+  if (plan->n_tiles > 0 && plan->residual.E > 0 && !getenv("DA_NO_PROMOTE")) {
+    // ---- promotion pass (host): residual in-edges of dense-tile rows with multiplicity one move into the bitmap
+    // on extra columns (see DensePlan); the residual CSR is rewritten without them
+    const int64_t Er = plan->residual.E;
+    std::vector<int32_t> rp((size_t)num_total + 1), colv((size_t)Er), new_rp((size_t)num_total + 1), new_col, xs, xslot;
+    std::vector<float> wv((size_t)Er), new_w;
+    std::vector<int64_t> bword;
+    std::vector<uint32_t> bbit;
     DA_TRY(cudaMemcpy(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
+    DA_TRY(cudaMemcpy(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)Er, cudaMemcpyDeviceToHost));
+    DA_TRY(cudaMemcpy(wv.data(), plan->residual.weight, sizeof(float) * (size_t)Er, cudaMemcpyDeviceToHost));
+    new_col.reserve((size_t)Er); new_w.reserve((size_t)Er);
+    std::vector<std::vector<int32_t>> xsrc_of((size_t)B);   // per graph: sources in extra-column order
     for (int i = 0; i < num_total; ++i) {
-      if (i == num_real) { plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size(); }
-      (rp[i + 1] - rp[i] <= 16 ? light : heavy).push_back(i);
+      new_rp[i] = (int32_t)new_col.size();
+      const int g = (i < num_real && B > 0) ? (int)hbatch[i] : -1;
+      const bool dense_row = g >= 0 && g_bm_off[g] >= 0;
+      for (int e = rp[i]; e < rp[i + 1]; ++e) {
+        bool promoted = false;
+        if (dense_row && wv[e] == 1.0f) {
+          std::vector<int32_t>& xv = xsrc_of[g];
+          const int n = g_n[g], cap = (int)(g_bm_words[g] * 32) - n;
+          int idx = -1;
+          for (size_t k = 0; k < xv.size(); ++k) if (xv[k] == colv[e]) { idx = (int)k; break; }
+          if (idx < 0 && (int)xv.size() < cap) { idx = (int)xv.size(); xv.push_back(colv[e]); }
+          if (idx >= 0) {
+            const int colx = n + idx;
+            bword.push_back(g_bm_off[g] + (int64_t)(i - g_node0[g]) * g_bm_words[g] + (colx >> 5));
+            bbit.push_back(1u << (colx & 31));
+            promoted = true;
+          }
+        }
+        if (!promoted) { new_col.push_back(colv[e]); new_w.push_back(wv[e]); }
+      }
     }
-    if (num_total == num_real) { plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size(); }
-    plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size();
+    new_rp[num_total] = (int32_t)new_col.size();
+    if (!bword.empty()) {
+      for (int g = 0; g < B; ++g) {
+        if (xsrc_of[g].empty()) continue;
+        const int n = g_n[g];
+        for (size_t k = 0; k < xsrc_of[g].size(); ++k) { xs.push_back(xsrc_of[g][k]); xslot.push_back(g_tile0[g] * 128 + n + (int)k); }
+        const int ntile = g_bm_words[g] / 4;
+        for (int t = 0; t < ntile; ++t) tiles[g_tile0[g] + t].gn = n + (int)xsrc_of[g].size();
+      }
+      int64_t* d_w = nullptr; uint32_t* d_b = nullptr;
+      DA_TRY(tmp_alloc(&d_w, sizeof(int64_t) * bword.size(), s));
+      DA_TRY(tmp_alloc(&d_b, sizeof(uint32_t) * bbit.size(), s));
+      DA_TRY(cudaMemcpyAsync(d_w, bword.data(), sizeof(int64_t) * bword.size(), cudaMemcpyHostToDevice, s));
+      DA_TRY(cudaMemcpyAsync(d_b, bbit.data(), sizeof(uint32_t) * bbit.size(), cudaMemcpyHostToDevice, s));
+      set_bits_kernel<<<(unsigned)((bword.size() + 255) / 256), 256, 0, s>>>(d_w, d_b, (int)bword.size(), plan->bitmap);
+      DA_TRY(cudaGetLastError());
+      DA_TRY(cudaStreamSynchronize(s));
+      tmp_free(d_w, s); tmp_free(d_b, s);
+      plan->n_extra = (int)xs.size();
+      plan->n_promoted_edges = (int64_t)bword.size();
+      DA_TRY(cudaMalloc(&plan->x_src, sizeof(int32_t) * xs.size()));
+      DA_TRY(cudaMalloc(&plan->x_slot, sizeof(int32_t) * xs.size()));
+      DA_TRY(cudaMemcpy(plan->x_src, xs.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice));
+      DA_TRY(cudaMemcpy(plan->x_slot, xslot.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice));
+      // the rewritten residual is never larger: overwrite in place
+      DA_TRY(cudaMemcpy(plan->residual.rowptr, new_rp.data(), sizeof(int32_t) * new_rp.size(), cudaMemcpyHostToDevice));
+      if (!new_col.empty()) {
+        DA_TRY(cudaMemcpy(plan->residual.col, new_col.data(), sizeof(int32_t) * new_col.size(), cudaMemcpyHostToDevice));
+        DA_TRY(cudaMemcpy(plan->residual.weight, new_w.data(), sizeof(float) * new_w.size(), cudaMemcpyHostToDevice));
+      }
+      plan->residual.E = (int64_t)new_col.size();
+      plan->n_dense_edges += plan->n_promoted_edges;
+    }
+    extra_sources = xs;
+  }
+  if (plan->n_tiles > 0)
+    DA_TRY(cudaMemcpy(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice));
+  {  // degree classes of the residual CSR (node order kept, real nodes before virtual rows)
+    std::vector<int32_t> rp((size_t)num_total + 1), light, heavy, light_nf;
+    std::vector<uint8_t> fused((size_t)num_total, 0);
+    DA_TRY(cudaMemcpy(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
+    plan->n_fused = 0;
+    for (int i = 0; i < num_total; ++i) {
+      if (i == num_real) {
+        plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size();
+        plan->n_light_nf_real = (int)light_nf.size();
+      }
+      const int deg = rp[i + 1] - rp[i];
+      if (deg <= 16) {
+        light.push_back(i);
+        if (node_slot[i] >= 0 && deg <= DA_FUSE_MAX_RESIDUAL) { fused[i] = 1; ++plan->n_fused; }
+        else light_nf.push_back(i);
+      } else heavy.push_back(i);
+    }
+    if (num_total == num_real) {
+      plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size();
+      plan->n_light_nf_real = (int)light_nf.size();
+    }
+    plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size(); plan->n_light_nf = (int)light_nf.size();
+    DA_TRY(cudaMalloc(&plan->row_fused, fused.size() + 1));
+    DA_TRY(cudaMemcpy(plan->row_fused, fused.data(), fused.size(), cudaMemcpyHostToDevice));
+    DA_TRY(cudaMalloc(&plan->light_nf, sizeof(int32_t) * (light_nf.size() + 1)));
+    DA_TRY(cudaMemcpy(plan->light_nf, light_nf.data(), sizeof(int32_t) * light_nf.size(), cudaMemcpyHostToDevice));
     {  // which 128-row tiles contain rows whose fp32 Q / K / V some CSR kernel reads?
       std::vector<int32_t> colv((size_t)(plan->residual.E > 0 ? plan->residual.E : 1));
       if (plan->residual.E > 0)
@@ -204,12 +300,14 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
         std::vector<uint8_t> fl((size_t)n_mt, 0);
         const int n_targets = v == 0 ? num_total : num_real;
         for (int i = 0; i < n_targets; ++i) {
-          if (rp[i + 1] > rp[i]) fl[i >> 7] |= 1;
+          // fused rows take Q from TMEM inside the dense kernel: only the CSR kernels read fp32 Q
+          if (rp[i + 1] > rp[i] && !fused[i]) fl[i >> 7] |= 1;
           // heavy rows read dense-tile sources from the K / V operand images, light rows from the fp32 row
           const bool heavy_row = rp[i + 1] - rp[i] > 16;
           for (int e = rp[i]; e < rp[i + 1]; ++e)
             if (!(heavy_row && node_slot[colv[e]] >= 0)) fl[colv[e] >> 7] |= 2;
         }
+        for (int32_t x : extra_sources) fl[x >> 7] |= 2;   // the per-layer gather reads their fp32 K / V rows
         for (int i = 0; i < num_total; ++i)
           if (node_slot[i] < 0) fl[i >> 7] = 3;   // rows outside the dense tiles are served by the CSR kernels only
         DA_TRY(cudaMalloc(&plan->f32_tile_flags[v], (size_t)n_mt));
