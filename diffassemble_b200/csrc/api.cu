@@ -201,7 +201,6 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     // rows of dense tiles with at most DA_FUSE_MAX_RESIDUAL residual in-edges are finalised by the dense kernel itself
     const bool fuse = dense && attn_csr_rows_supported(c.heads, C) && !alpha_last && h->plan.n_fused > 0 && !h->no_fuse &&
                       attn_dense_can_fuse(C);
-    const bool fold_resid = fuse && last && umma;   // trunk residual folded into the skip columns by the GEMM epilogue
     {
       LinearOut o; o.f32 = h->qkvs.as<float>(); o.ldc = 4 * HC;
       if (dense && umma) {  // Q / K / V operand images straight from the GEMM epilogue
@@ -211,7 +210,6 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
         if (attn_csr_rows_supported(c.heads, C) && !alpha_last && (fuse || h->plan.n_fused == 0))
           o.f32_tile_flags = h->plan.f32_tile_flags[last ? 1 : 0];
       }
-      if (fold_resid) { o.addend = h->combined.as<float>(); o.ld_addend = D; o.addend_col0 = 3 * HC; o.addend_rows = Mr; }
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
       DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
@@ -255,7 +253,6 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
       xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
     }
-    if (fold_resid) a.resid = nullptr;   // already inside the skip columns
     if (dense) {
       AttnDenseArgs da_{};
       da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;

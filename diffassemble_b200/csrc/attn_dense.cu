@@ -248,7 +248,7 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
 // loops are fully unrolled and every operand descriptor is "base + immediate".
 template <int CPAD_T, int ST>
 __global__ void __launch_bounds__(NT)
-attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
+attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int KST = ST, VST = ST;
   const int Cpad = CPAD_T ? CPAD_T : a.Cpad;
@@ -411,8 +411,14 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
     // fused finalisation (see the epilogue): this row's skip values are staged in the K ring, one row per
     // thread, padded by 16 bytes so that the per-row float4 reads are bank-conflict free
     const bool fused = a.row_fused != nullptr && row_valid && a.row_fused[node] != 0;
-    const uint32_t epi_pitch = (uint32_t)a.C * 4u + 16u;
+    // resid_rows_k >= 0: the trunk-residual rows are staged too -- un-padded rows, the first resid_rows_k of them
+    // behind the skip rows in the K ring and the others in the V stage that neither of the last two blocks uses
+    const bool stage_resid = a.resid != nullptr && resid_rows_k >= 0;
+    const uint32_t epi_pitch = (uint32_t)a.C * 4u + (stage_resid ? 0u : 16u);
     const float* epi_row = reinterpret_cast<const float*>(k_sm + (size_t)r * epi_pitch);
+    const float* epi_resid = reinterpret_cast<const float*>(
+        r < resid_rows_k ? k_sm + (size_t)TM * epi_pitch + (size_t)r * a.C * 4
+                         : v_sm + (size_t)(nblk % VST) * 2 * kv_plane + (size_t)(r - resid_rows_k) * a.C * 4);
     float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
     uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
@@ -427,8 +433,12 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
         // S of the LAST block has retired, so no MMA reads the K ring any more: start copying this row's skip
         // values into it now; the copy runs under the last softmax + PV and is waited for in the epilogue
         const uint32_t bytes = fused ? (uint32_t)a.C * 4u : 0u;
-        mbar_expect_tx(&sh->epi_full, bytes);
-        if (fused) bulk_load(const_cast<float*>(epi_row), a.qkvs + (size_t)node * a.ld + 3 * HC + head * a.C, bytes, &sh->epi_full);
+        mbar_expect_tx(&sh->epi_full, stage_resid ? 2 * bytes : bytes);
+        if (fused) {
+          bulk_load(const_cast<float*>(epi_row), a.qkvs + (size_t)node * a.ld + 3 * HC + head * a.C, bytes, &sh->epi_full);
+          // (S_{n-1} was only issued after P_{n-3} V_{n-3} retired, so V stage n % VST is idle as well)
+          if (stage_resid) bulk_load(const_cast<float*>(epi_resid), a.resid + (size_t)node * a.ld_resid + head * a.C, bytes, &sh->epi_full);
+        }
       }
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
       if (j == 0) {  // first block: take its masked max as the reference point
@@ -577,7 +587,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
       for (int e = 0; e < RM; ++e) pe[e] *= inv;
     }
     if (a.row_fused != nullptr) mbar_wait(&sh->epi_full, 0);   // skip rows are in shared memory
-    const float* rsd = a.resid ? a.resid + (size_t)node * a.ld_resid + head * a.C : nullptr;
+    const float* rsd = (a.resid && !stage_resid) ? a.resid + (size_t)node * a.ld_resid + head * a.C : nullptr;   // slow path
     const bool vec = (a.C & 3) == 0;
     for (int c0 = 0; c0 < Cpad; c0 += 16) {
       uint32_t v[16];
@@ -601,7 +611,13 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
             const float4 t = *reinterpret_cast<const float4*>(epi_row + c0 + e4);
             y[e4] = t.x; y[e4 + 1] = t.y; y[e4 + 2] = t.z; y[e4 + 3] = t.w;
           }
-          if (rsd) {
+          if (stage_resid) {
+#pragma unroll
+            for (int e4 = 0; e4 < 16; e4 += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(epi_resid + c0 + e4);
+              y[e4] += t.x; y[e4 + 1] += t.y; y[e4 + 2] += t.z; y[e4 + 3] += t.w;
+            }
+          } else if (rsd) {
 #pragma unroll
             for (int e4 = 0; e4 < 16; e4 += 4) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(rsd + c0 + e4));
@@ -612,25 +628,35 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             y[e] = (c0 + e < a.C) ? epi_row[c0 + e] : 0.f;
-            if (rsd && c0 + e < a.C) y[e] += __ldg(rsd + c0 + e);
+            if (stage_resid && c0 + e < a.C) y[e] += epi_resid[c0 + e];
+            else if (rsd && c0 + e < a.C) y[e] += __ldg(rsd + c0 + e);
           }
         }
-        // reference order: (attention + skip) + resid; the attention term is added to the pre-summed rest
-        float att[16];
+        // the reference adds (attention + skip) + resid; here the attention term joins the pre-summed rest
+        if (n_e > 0) {
+          float att[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) att[e] = __uint_as_float(v[e]) * o_scale;
+          for (int e = 0; e < 16; ++e) att[e] = __uint_as_float(v[e]) * o_scale;
 #pragma unroll
-        for (int ee = 0; ee < RM; ++ee) {
-          if (ee < n_e) {
+          for (int ee = 0; ee < RM; ++ee) {
+            if (ee < n_e) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              att[4 * u] = fmaf(pe[ee], vv[ee][u].x, att[4 * u]); att[4 * u + 1] = fmaf(pe[ee], vv[ee][u].y, att[4 * u + 1]);
-              att[4 * u + 2] = fmaf(pe[ee], vv[ee][u].z, att[4 * u + 2]); att[4 * u + 3] = fmaf(pe[ee], vv[ee][u].w, att[4 * u + 3]);
+              for (int u = 0; u < 4; ++u) {
+                att[4 * u] = fmaf(pe[ee], vv[ee][u].x, att[4 * u]); att[4 * u + 1] = fmaf(pe[ee], vv[ee][u].y, att[4 * u + 1]);
+                att[4 * u + 2] = fmaf(pe[ee], vv[ee][u].z, att[4 * u + 2]); att[4 * u + 3] = fmaf(pe[ee], vv[ee][u].w, att[4 * u + 3]);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int e = 0; e < 16; ++e) y[e] = apply_act_rt(att[e] + y[e], a.act);
+          for (int e = 0; e < 16; ++e) y[e] += att[e];
+        } else {   // the common case after promotion: one FMA per channel
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] = fmaf(__uint_as_float(v[e]), o_scale, y[e]);
+        }
+        if (a.act != ACT_NONE) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) y[e] = apply_act_rt(y[e], a.act);
+        }
         const int nval = (a.C - c0) < 16 ? (a.C - c0) : 16;   // valid channels of this chunk (> 0: Cpad - C < 16)
         if (a.out.f32) {
           float* dst = a.out.f32 + (size_t)node * a.out.ldc + head * a.C + c0;
@@ -751,6 +777,16 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   int cols, st; size_t smem;
   if (!dense_config(Cpad, &cols, &st, &smem)) return cudaErrorInvalidValue;
   if (a.row_fused != nullptr && !attn_dense_can_fuse(a.C)) return cudaErrorInvalidValue;
+  // trunk-residual rows staged next to the skip rows (un-padded): the K ring's remainder + one idle V stage
+  int resid_rows_k = -1;
+  if (a.row_fused != nullptr && a.resid != nullptr && st >= 3) {
+    const size_t row_b = (size_t)a.C * 4, kring = (size_t)st * 2 * TS * Cpad * 2, vstage = (size_t)2 * TS * Cpad * 2;
+    if (kring >= TM * row_b) {
+      size_t r0 = (kring - TM * row_b) / row_b;
+      if (r0 > (size_t)TM) r0 = TM;
+      if ((TM - r0) * row_b <= vstage) resid_rows_k = (int)r0;
+    }
+  }
   const unsigned grid = a.n_tiles * a.H;
 #define DA_LAUNCH(CP, ST_)                                                                                          \
   do {                                                                                                              \
@@ -760,7 +796,7 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
       if (e != cudaSuccess) return e;                                                                               \
       smem_set = smem;                                                                                              \
     }                                                                                                               \
-    attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols);                                                     \
+    attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols, resid_rows_k);                                                     \
   } while (0)
   if (Cpad == 32 && st == 4) DA_LAUNCH(32, 4);
   else if (Cpad == 144 && st == 3) DA_LAUNCH(144, 3);

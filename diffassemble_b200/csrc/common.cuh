@@ -62,11 +62,6 @@ struct LinearOut {
   // optional per-128-row-tile flags (bit 0: some row's fp32 Q is read later, bit 1: some row's fp32 K / V is):
   // tiles whose Q / K / V only feed the tensor-core attention skip those fp32 stores (HBM-write-bound GEMMs).
   const uint8_t* f32_tile_flags = nullptr;
-  // optional: rows [0, addend_rows) of `addend` ([*, ld_addend] fp32) are added to the fp32 output columns
-  // [addend_col0, addend_col0 + ...) after bias / activation.  The last layer folds the trunk residual
-  // `combined` into the skip part this way, so the attention epilogue reads ONE row instead of two.
-  const float* addend = nullptr;
-  int ld_addend = 0, addend_col0 = 0, addend_rows = 0;
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
@@ -294,7 +289,7 @@ struct AttnDenseArgs {
   const uint8_t* row_fused = nullptr;
   const float* qkvs = nullptr; int ld = 0;      // [n, 4*H*C] rows [Q | K | V | skip]
   const int32_t* rowptr = nullptr; const int32_t* col = nullptr; const float* weight = nullptr;   // residual CSR
-  const float* resid = nullptr; int ld_resid = 0;   // optional second addend read straight from global (slow path)
+  const float* resid = nullptr; int ld_resid = 0;   // optional second addend (trunk residual), staged like skip when it fits
   int act = 0;
   LinearOut out;
 };

@@ -135,7 +135,6 @@ struct EpiParams {
   const int32_t* node_slot; __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
   int iH, iC, iCpad, irows;
   const uint8_t* f32_tile_flags;
-  const float* addend; int ld_addend, addend_col0, addend_rows;
 };
 
 template <int BN>
@@ -250,18 +249,6 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         const int col = n0 + c0 + sub_col;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        // optional addend (trunk residual folded into the skip columns): one float4 per (row, lane) of the
-        // read-back mapping below, requested before the TMEM load so its latency overlaps the staging
-        const bool has_ad = p.addend != nullptr && n0 + c0 >= p.addend_col0;
-        float4 ad[8];
-        if (has_ad) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = row_base + i * 4 + sub_row;
-            ad[i] = (row < p.addend_rows) ? __ldg(reinterpret_cast<const float4*>(p.addend + (size_t)row * p.ld_addend + (col - p.addend_col0)))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
@@ -286,7 +273,6 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           float4 v = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + (((lane & 7) ^ (rr & 7)) << 2));
           v.x = apply_act_rt(v.x + b4.x, p.act); v.y = apply_act_rt(v.y + b4.y, p.act);
           v.z = apply_act_rt(v.z + b4.z, p.act); v.w = apply_act_rt(v.w + b4.w, p.act);
-          if (has_ad) { v.x += ad[i].x; v.y += ad[i].y; v.z += ad[i].z; v.w += ad[i].w; }
           if (row < p.M) {
             if (f32_on) *reinterpret_cast<float4*>(p.cf + (size_t)row * p.ldc + col) = v;
             if (p.chi) {
@@ -454,8 +440,7 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
   if ((out.f32 && out.ldc % 4) || (out.hi && out.ld_split % 8)) return cudaErrorInvalidValue;
   EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act,
               out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows,
-              out.img_node_slot ? out.f32_tile_flags : nullptr,
-              out.addend, out.ld_addend, out.addend_col0, out.addend_rows};
+              out.img_node_slot ? out.f32_tile_flags : nullptr};
   if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
   if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
