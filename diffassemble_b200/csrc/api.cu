@@ -262,7 +262,8 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
       if (fuse) {
         da_.row_fused = h->plan.row_fused;
-        da_.qkvs = a.qkvs; da_.ld = a.ld;
+        da_.qkvs = a.qkvs; da_.ld = a.ld; da_.n_rows = Mt; da_.n_rows_resid = Mt;   // combined has Mt rows too
+        da_.n_rows_out = last ? Mr : Mt;   // r_hi / r_lo are [Mr, D], xa / xb planes [Mt, 256]
         da_.rowptr = csr.rowptr; da_.col = csr.col; da_.weight = csr.weight;
         da_.resid = a.resid; da_.ld_resid = a.ld_resid; da_.act = a.act; da_.out = a.out;
       }
@@ -881,7 +882,7 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
       if (ce == cudaSuccess) {
         AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st, nullptr};
         if (fuse) {
-          da_.row_fused = plan.row_fused; da_.qkvs = qkvs; da_.ld = 4 * H * C;
+          da_.row_fused = plan.row_fused; da_.qkvs = qkvs; da_.ld = 4 * H * C; da_.n_rows = n;
           da_.rowptr = plan.residual.rowptr; da_.col = plan.residual.col; da_.weight = plan.residual.weight;
           da_.act = ACT_NONE; da_.out.f32 = y; da_.out.ldc = H * C;
         }

@@ -19,7 +19,12 @@
 //              two passes over the S tile in TMEM (max, then exp + P store), O correction in TMEM
 // The un-normalised O and the (m, l) statistics go to global memory; attn_csr.cu then continues the
 // same online softmax over the residual edges and applies skip / residual / activation.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace da {
 namespace {
@@ -67,6 +72,16 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -248,8 +263,10 @@ __device__ __forceinline__ void tc_mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem,
 // loops are fully unrolled and every operand descriptor is "base + immediate".
 template <int CPAD_T, int ST>
 __global__ void __launch_bounds__(NT)
-attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
-  extern __shared__ __align__(128) uint8_t smem[];
+attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_constant__ CUtensorMap map_resid,
+                  const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo,
+                  AttnDenseArgs a, int tmem_cols, int stage_flags) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int KST = ST, VST = ST;
   const int Cpad = CPAD_T ? CPAD_T : a.Cpad;
   const uint32_t kv_plane = TS * Cpad * 2;                 // bytes
@@ -269,7 +286,7 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
       mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1); }
-    mbar_init(&sh->epi_full, 128);   // one arrive (+ expected bytes) per softmax thread
+    mbar_init(&sh->epi_full, 1);     // the thread that issues the staging copies
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -411,14 +428,30 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
     // fused finalisation (see the epilogue): this row's skip values are staged in the K ring, one row per
     // thread, padded by 16 bytes so that the per-row float4 reads are bank-conflict free
     const bool fused = a.row_fused != nullptr && row_valid && a.row_fused[node] != 0;
-    // resid_rows_k >= 0: the trunk-residual rows are staged too -- un-padded rows, the first resid_rows_k of them
-    // behind the skip rows in the K ring and the others in the V stage that neither of the last two blocks uses
-    const bool stage_resid = a.resid != nullptr && resid_rows_k >= 0;
-    const uint32_t epi_pitch = (uint32_t)a.C * 4u + (stage_resid ? 0u : 16u);
-    const float* epi_row = reinterpret_cast<const float*>(k_sm + (size_t)r * epi_pitch);
-    const float* epi_resid = reinterpret_cast<const float*>(
-        r < resid_rows_k ? k_sm + (size_t)TM * epi_pitch + (size_t)r * a.C * 4
-                         : v_sm + (size_t)(nblk % VST) * 2 * kv_plane + (size_t)(r - resid_rows_k) * a.C * 4);
+    // Staging (stage_flags bit 0: trunk residual staged, bit 1: outputs leave through TMA stores).  Skip / residual
+    // values arrive as TMA boxes of 64 rows x 16 floats with the 64-byte swizzle, so that the row-per-thread float4
+    // reads below are bank-conflict free; a half tile (64 rows) of Cpad/16 boxes is exactly one K / V ring stage:
+    //   skip rows 0..63 -> K stage 0, skip rows 64..127 -> K stage 1, residual rows 0..63 -> K stage 2,
+    //   residual rows 64..127 -> V stage n % ST (idle during the last two blocks).
+    // Each region is requested as soon as the last block that uses its stage has retired its S = Q K^T.
+    const bool stage_resid = a.resid != nullptr && (stage_flags & 1);
+    const uint32_t stage_b = 2 * kv_plane;                  // bytes of one ring stage = (Cpad / 16) boxes of 4 KB
+    const int nbox = Cpad / 16;
+    const int rr = r & 63;
+    const uint32_t row_off = (uint32_t)rr * 64u;
+    const uint32_t swz = (uint32_t)((rr >> 1) & 3);
+    const uint8_t* skip_reg = k_sm + (size_t)(r >> 6) * stage_b;
+    const uint8_t* resid_reg = (r < 64) ? k_sm + (size_t)2 * stage_b : v_sm + (size_t)(nblk % VST) * stage_b;
+    auto staged4 = [&](const uint8_t* reg, int box, int u) -> float4 {   // float4 u of this row's chunk `box`
+      return *reinterpret_cast<const float4*>(reg + (size_t)box * 4096 + row_off + (((uint32_t)u ^ swz) << 4));
+    };
+    auto issue_region = [&](const CUtensorMap* map, uint8_t* dst, int col0, int row0) {
+      for (int bx = 0; bx < nbox; ++bx) tma_load_2d(map, &sh->epi_full, dst + (size_t)bx * 4096, col0 + bx * 16, row0);
+    };
+    auto last_user = [&](int st_) { return st_ < nblk ? (nblk - 1) - ((nblk - 1 - st_) % KST) : 0; };
+    // residual in-edges of a fused row (<= DA_FUSE_MAX_RESIDUAL; none at all once the planner has promoted them)
+    int res_beg = 0, n_e = 0;
+    if (fused) { res_beg = a.rowptr[node]; n_e = a.rowptr[node + 1] - res_beg; }
     float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
     uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
@@ -429,16 +462,19 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 1] = clock64();   // S_j ready
       tc_fence_after();
-      if (a.row_fused != nullptr && j == nblk - 1) {
-        // S of the LAST block has retired, so no MMA reads the K ring any more: start copying this row's skip
-        // values into it now; the copy runs under the last softmax + PV and is waited for in the epilogue
-        const uint32_t bytes = fused ? (uint32_t)a.C * 4u : 0u;
-        mbar_expect_tx(&sh->epi_full, stage_resid ? 2 * bytes : bytes);
-        if (fused) {
-          bulk_load(const_cast<float*>(epi_row), a.qkvs + (size_t)node * a.ld + 3 * HC + head * a.C, bytes, &sh->epi_full);
-          // (S_{n-1} was only issued after P_{n-3} V_{n-3} retired, so V stage n % VST is idle as well)
-          if (stage_resid) bulk_load(const_cast<float*>(epi_resid), a.resid + (size_t)node * a.ld_resid + head * a.C, bytes, &sh->epi_full);
+      if (a.row_fused != nullptr && warp == 2) {
+        // S_j has retired: K stages whose last user is block j (or that are never used) are idle from now on
+        if (elect_one()) {
+          if (j == 0) mbar_expect_tx(&sh->epi_full, (stage_resid ? 4u : 2u) * (uint32_t)nbox * 4096u);   // the one arrival
+          if (j == last_user(0)) issue_region(&map_skip, k_sm, 3 * HC + head * a.C, ti.node0);
+          if (j == last_user(1)) issue_region(&map_skip, k_sm + stage_b, 3 * HC + head * a.C, ti.node0 + 64);
+          if (stage_resid) {
+            if (j == last_user(2)) issue_region(&map_resid, k_sm + 2 * stage_b, head * a.C, ti.node0);
+            // (S_{n-1} was only issued after P_{n-3} V_{n-3} retired, so V stage n % ST is idle by now)
+            if (j == nblk - 1) issue_region(&map_resid, v_sm + (size_t)(nblk % VST) * stage_b, head * a.C, ti.node0 + 64);
+          }
         }
+        __syncwarp();
       }
       const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
       if (j == 0) {  // first block: take its masked max as the reference point
@@ -513,20 +549,20 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 2] = clock64();   // P_j published
     }
     // epilogue
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[120] = clock64();   // last P published
     mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[121] = clock64();   // last PV retired
     // ---- fused finalisation (rows flagged by the planner): continue the online softmax over this row's
     // (<= DA_FUSE_MAX_RESIDUAL) residual in-edges, normalise, + skip (+ trunk residual), activation, store the
     // layer output.  Same arithmetic as attn_csr_rows_kernel, minus the (acc, stats) round trip through HBM.
     // tcgen05.ld / wait are warp-collective, so those are executed by every lane and only the per-row work
     // is predicated.
     constexpr int RM = DA_FUSE_MAX_RESIDUAL;
-    int n_e = 0;
     int src[RM]; float pe[RM], wgt[RM], d[RM];
     float o_scale = 0.f;
     if (fused) {
-      const int beg = a.rowptr[node];
-      n_e = a.rowptr[node + 1] - beg;
+      const int beg = res_beg;
 #pragma unroll
       for (int e = 0; e < RM; ++e) {
         src[e] = (e < n_e) ? a.col[beg + e] : node;
@@ -586,13 +622,19 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
 #pragma unroll
       for (int e = 0; e < RM; ++e) pe[e] *= inv;
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[122] = clock64();   // residual scores done
     if (a.row_fused != nullptr) mbar_wait(&sh->epi_full, 0);   // skip rows are in shared memory
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[123] = clock64();   // staged rows landed
     const float* rsd = (a.resid && !stage_resid) ? a.resid + (size_t)node * a.ld_resid + head * a.C : nullptr;   // slow path
-    const bool vec = (a.C & 3) == 0;
-    for (int c0 = 0; c0 < Cpad; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_o + lane_off + c0, v);
-      float4 vv[RM][4];   // V rows of the residual sources: issued before the TMEM wait
+    // Full tiles leave through two TMA tensor stores (hi / lo planes of 128 rows x C bf16, staged in the two V stages
+    // that are idle now); partial tiles (the last one of a graph) and fp32 outputs are stored by the threads.
+    const bool tma_out = (stage_flags & 2) && a.out.hi != nullptr && ti.rows == TM;
+    uint8_t* ohi_sm = v_sm + (size_t)((nblk + 1) % VST) * stage_b;
+    uint8_t* olo_sm = v_sm + (size_t)((nblk + 2) % VST) * stage_b;
+    const uint32_t orow_b = (uint32_t)a.C * 2u;   // bytes of one staged output row per plane
+    // one 16-channel chunk of this row: v = the chunk of O (already in registers)
+    auto chunk_body = [&](const int c0, const uint32_t (&v)[16]) {
+      float4 vv[RM][4];   // V rows of the residual sources (rare once the planner has promoted them)
 #pragma unroll
       for (int ee = 0; ee < RM; ++ee) {
         if (ee < n_e) {
@@ -602,34 +644,27 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
             vv[ee][u] = (c0 + 4 * u < a.C) ? __ldg(reinterpret_cast<const float4*>(vrow + 4 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      tmem_ld_wait();   // warp-collective as well: keep it outside the per-row branches
       if (fused) {
         float y[16];
-        if (vec && c0 + 16 <= a.C) {
+        const int box = c0 >> 4;
 #pragma unroll
-          for (int e4 = 0; e4 < 16; e4 += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(epi_row + c0 + e4);
-            y[e4] = t.x; y[e4 + 1] = t.y; y[e4 + 2] = t.z; y[e4 + 3] = t.w;
+        for (int u = 0; u < 4; ++u) {
+          const float4 t = staged4(skip_reg, box, u);
+          y[4 * u] = t.x; y[4 * u + 1] = t.y; y[4 * u + 2] = t.z; y[4 * u + 3] = t.w;
+        }
+        if (stage_resid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 t = staged4(resid_reg, box, u);
+            y[4 * u] += t.x; y[4 * u + 1] += t.y; y[4 * u + 2] += t.z; y[4 * u + 3] += t.w;
           }
-          if (stage_resid) {
+        } else if (rsd) {
 #pragma unroll
-            for (int e4 = 0; e4 < 16; e4 += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(epi_resid + c0 + e4);
-              y[e4] += t.x; y[e4 + 1] += t.y; y[e4 + 2] += t.z; y[e4 + 3] += t.w;
+          for (int u = 0; u < 4; ++u) {
+            if (c0 + 4 * u < a.C) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(rsd + c0 + 4 * u));
+              y[4 * u] += t.x; y[4 * u + 1] += t.y; y[4 * u + 2] += t.z; y[4 * u + 3] += t.w;
             }
-          } else if (rsd) {
-#pragma unroll
-            for (int e4 = 0; e4 < 16; e4 += 4) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(rsd + c0 + e4));
-              y[e4] += t.x; y[e4 + 1] += t.y; y[e4 + 2] += t.z; y[e4 + 3] += t.w;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            y[e] = (c0 + e < a.C) ? epi_row[c0 + e] : 0.f;
-            if (stage_resid && c0 + e < a.C) y[e] += epi_resid[c0 + e];
-            else if (rsd && c0 + e < a.C) y[e] += __ldg(rsd + c0 + e);
           }
         }
         // the reference adds (attention + skip) + resid; here the attention term joins the pre-summed rest
@@ -660,12 +695,14 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
         const int nval = (a.C - c0) < 16 ? (a.C - c0) : 16;   // valid channels of this chunk (> 0: Cpad - C < 16)
         if (a.out.f32) {
           float* dst = a.out.f32 + (size_t)node * a.out.ldc + head * a.C + c0;
-          if (vec && nval == 16) {
+          if (nval == 16) {
 #pragma unroll
             for (int e4 = 0; e4 < 16; e4 += 4)
               *reinterpret_cast<float4*>(dst + e4) = make_float4(y[e4], y[e4 + 1], y[e4 + 2], y[e4 + 3]);
           } else {
-            for (int e = 0; e < nval; ++e) dst[e] = y[e];
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < nval) dst[e] = y[e];
           }
         }
         if (a.out.hi) {
@@ -676,20 +713,28 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
             hh[e >> 1] = h2;
             ll[e >> 1] = pack_bf16x2(y[e] - __uint_as_float(h2 << 16), y[e + 1] - __uint_as_float(h2 & 0xffff0000u));
           }
-          __nv_bfloat16* dh = a.out.hi + (size_t)node * a.out.ld_split + head * a.C + c0;
-          __nv_bfloat16* dl = a.out.lo + (size_t)node * a.out.ld_split + head * a.C + c0;
-          if (nval == 16 && (a.C & 7) == 0 && (a.out.ld_split & 7) == 0) {
-            *reinterpret_cast<uint4*>(dh) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<uint4*>(dh + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
-            *reinterpret_cast<uint4*>(dl) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            *reinterpret_cast<uint4*>(dl + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+          if (tma_out) {   // (ti.rows == 128 implies C == Cpad chunks are whole: a.C % 16 == 0 is checked on the host)
+            uint4* dh = reinterpret_cast<uint4*>(ohi_sm + (size_t)r * orow_b + (size_t)c0 * 2);
+            uint4* dl = reinterpret_cast<uint4*>(olo_sm + (size_t)r * orow_b + (size_t)c0 * 2);
+            dh[0] = make_uint4(hh[0], hh[1], hh[2], hh[3]); dh[1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            dl[0] = make_uint4(ll[0], ll[1], ll[2], ll[3]); dl[1] = make_uint4(ll[4], ll[5], ll[6], ll[7]);
           } else {
-            for (int e = 0; e < nval; ++e) {
-              const uint32_t hw = hh[e >> 1], lw = ll[e >> 1];
-              const unsigned short hb = (e & 1) ? (unsigned short)(hw >> 16) : (unsigned short)(hw & 0xffffu);
-              const unsigned short lb = (e & 1) ? (unsigned short)(lw >> 16) : (unsigned short)(lw & 0xffffu);
-              reinterpret_cast<unsigned short*>(dh)[e] = hb;
-              reinterpret_cast<unsigned short*>(dl)[e] = lb;
+            __nv_bfloat16* dh = a.out.hi + (size_t)node * a.out.ld_split + head * a.C + c0;
+            __nv_bfloat16* dl = a.out.lo + (size_t)node * a.out.ld_split + head * a.C + c0;
+            if (nval == 16 && (a.C & 7) == 0 && (a.out.ld_split & 7) == 0) {
+              *reinterpret_cast<uint4*>(dh) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+              *reinterpret_cast<uint4*>(dh + 8) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+              *reinterpret_cast<uint4*>(dl) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+              *reinterpret_cast<uint4*>(dl + 8) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {   // compile-time indices: hh / ll stay in registers
+                if (e < nval) {
+                  const uint32_t hw = hh[e >> 1], lw = ll[e >> 1];
+                  reinterpret_cast<unsigned short*>(dh)[e] = (e & 1) ? (unsigned short)(hw >> 16) : (unsigned short)(hw & 0xffffu);
+                  reinterpret_cast<unsigned short*>(dl)[e] = (e & 1) ? (unsigned short)(lw >> 16) : (unsigned short)(lw & 0xffffu);
+                }
+              }
             }
           }
         }
@@ -708,7 +753,32 @@ attn_dense_kernel(AttnDenseArgs a, int tmem_cols, int resid_rows_k) {
           }
         }
       }
+    };
+    // tcgen05.ld / wait are warp-collective: issued by every lane, outside the per-row branches of chunk_body.
+    // (Software-pipelining the TMEM loads across chunks was measured slower: the unrolled bodies cost more in
+    // instruction fetch and registers than the ~100-cycle TMEM latency they hide.)
+    for (int c0 = 0; c0 < Cpad; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_o + lane_off + c0, v);
+      tmem_ld_wait();
+      chunk_body(c0, v);
     }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[125] = clock64();   // chunk loop done
+    if (tma_out) {
+      // generic-proxy writes -> async proxy, all 128 epilogue threads (named barrier 1), then one thread stores both planes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2) {
+        if (elect_one()) {
+          tma_store_2d(&map_ohi, ohi_sm, head * a.C, ti.node0);
+          tma_store_2d(&map_olo, olo_sm, head * a.C, ti.node0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+        }
+        __syncwarp();
+      }
+    }
+    if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[124] = clock64();   // outputs stored
     if (row_valid && !fused) {
       float* st = a.stats + ((size_t)node * a.H + head) * 2;
       st[0] = (m == -INFINITY) ? -INFINITY : m / sqrtf((float)a.C);  // natural-log units of the scaled score
@@ -767,8 +837,9 @@ bool attn_dense_can_fuse(int C) {
   const int Cpad = (C + 15) / 16 * 16;
   int cols, st; size_t smem;
   if ((C & 3) || !dense_config(Cpad, &cols, &st, &smem)) return false;
-  // 128 staged skip rows of (4 C + 16) bytes must fit the K ring (st stages of 2 planes of 64 x Cpad bf16)
-  return (size_t)TM * ((size_t)C * 4 + 16) <= (size_t)st * 2 * TS * Cpad * 2;
+  // 128 skip rows + 64 trunk-residual rows of C floats in the K ring (3 stages of 2 planes of 64 x Cpad bf16 hold
+  // exactly that when C == Cpad), the other 64 residual rows in an idle V stage
+  return st >= 3;
 }
 
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
@@ -777,15 +848,20 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   int cols, st; size_t smem;
   if (!dense_config(Cpad, &cols, &st, &smem)) return cudaErrorInvalidValue;
   if (a.row_fused != nullptr && !attn_dense_can_fuse(a.C)) return cudaErrorInvalidValue;
-  // trunk-residual rows staged next to the skip rows (un-padded): the K ring's remainder + one idle V stage
-  int resid_rows_k = -1;
-  if (a.row_fused != nullptr && a.resid != nullptr && st >= 3) {
-    const size_t row_b = (size_t)a.C * 4, kring = (size_t)st * 2 * TS * Cpad * 2, vstage = (size_t)2 * TS * Cpad * 2;
-    if (kring >= TM * row_b) {
-      size_t r0 = (kring - TM * row_b) / row_b;
-      if (r0 > (size_t)TM) r0 = TM;
-      if ((TM - r0) * row_b <= vstage) resid_rows_k = (int)r0;
-    }
+  // skip (and trunk-residual) values are staged by TMA boxes of 64 rows x 16 floats (64-byte swizzle); full tiles
+  // leave through TMA stores of 128 rows x C bf16 per plane
+  CUtensorMap map_skip, map_resid, map_ohi, map_olo;
+  memset(&map_skip, 0, sizeof(map_skip)); memset(&map_resid, 0, sizeof(map_resid));
+  memset(&map_ohi, 0, sizeof(map_ohi)); memset(&map_olo, 0, sizeof(map_olo));
+  int stage_flags = 0;
+  if (a.row_fused != nullptr) {
+    if (!get_tensor_map_2d(a.qkvs, 4, a.n_rows, a.ld, a.ld, 64, 16, 1, &map_skip)) return cudaErrorInvalidValue;
+    if (a.resid != nullptr && get_tensor_map_2d(a.resid, 4, a.n_rows_resid, a.ld_resid, a.ld_resid, 64, 16, 1, &map_resid))
+      stage_flags |= 1;
+    if (a.out.hi != nullptr && a.C % 16 == 0 && a.C <= 256 && a.out.ld_split % 8 == 0 &&
+        get_tensor_map_2d(a.out.hi, 2, a.n_rows_out, a.out.ld_split, a.out.ld_split, 128, a.C, 0, &map_ohi) &&
+        get_tensor_map_2d(a.out.lo, 2, a.n_rows_out, a.out.ld_split, a.out.ld_split, 128, a.C, 0, &map_olo))
+      stage_flags |= 2;
   }
   const unsigned grid = a.n_tiles * a.H;
 #define DA_LAUNCH(CP, ST_)                                                                                          \
@@ -796,7 +872,7 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
       if (e != cudaSuccess) return e;                                                                               \
       smem_set = smem;                                                                                              \
     }                                                                                                               \
-    attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols, resid_rows_k);                                                     \
+    attn_dense_kernel<CP, ST_><<<grid, NT, smem, s>>>(map_skip, map_resid, map_ohi, map_olo, a, cols, stage_flags);                                                     \
   } while (0)
   if (Cpad == 32 && st == 4) DA_LAUNCH(32, 4);
   else if (Cpad == 144 && st == 3) DA_LAUNCH(144, 3);

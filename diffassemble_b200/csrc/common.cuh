@@ -287,7 +287,8 @@ struct AttnDenseArgs {
   // (fp32 Q / K / V rows of `qkvs`), normalises, adds skip (+ resid), applies `act` and writes the layer
   // output itself -- no (acc, stats) round trip through HBM and no CSR continuation launch for those rows.
   const uint8_t* row_fused = nullptr;
-  const float* qkvs = nullptr; int ld = 0;      // [n, 4*H*C] rows [Q | K | V | skip]
+  const float* qkvs = nullptr; int ld = 0;      // [n_rows, 4*H*C] rows [Q | K | V | skip]
+  int n_rows = 0, n_rows_resid = 0, n_rows_out = 0;   // allocated rows of qkvs / resid / out.hi (tensor-map bounds)
   const int32_t* rowptr = nullptr; const int32_t* col = nullptr; const float* weight = nullptr;   // residual CSR
   const float* resid = nullptr; int ld_resid = 0;   // optional second addend (trunk residual), staged like skip when it fits
   int act = 0;

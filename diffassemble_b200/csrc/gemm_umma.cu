@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -398,6 +399,40 @@ bool get_tensor_map(const __nv_bfloat16* ptr, int rows, int cols, int ld, int bo
   *out = m;
   return true;
 }
+
+}  // namespace
+
+bool get_tensor_map_2d(const void* ptr, int elem_bytes, int rows, int cols, int ld, int box_rows, int box_cols, int swizzle,
+                       void* out) {
+  struct Key { const void* p; int e, r, c, l, br, bc, sw; bool operator==(const Key& o) const { return p == o.p && e == o.e && r == o.r && c == o.c && l == o.l && br == o.br && bc == o.bc && sw == o.sw; } };
+  struct KeyHash { size_t operator()(const Key& k) const { size_t h = std::hash<const void*>()(k.p); for (int v : {k.e, k.r, k.c, k.l, k.br, k.bc, k.sw}) h = h * 1000003u ^ std::hash<int>()(v); return h; } };
+  static std::unordered_map<Key, CUtensorMap, KeyHash> cache;
+  static std::mutex mu;
+  Key key{ptr, elem_bytes, rows, cols, ld, box_rows, box_cols, swizzle};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { memcpy(out, &it->second, sizeof(CUtensorMap)); return true; }
+  auto enc = get_encode();
+  if (!enc || box_cols > 256 || box_rows > 256 || (elem_bytes != 4 && elem_bytes != 2)) return false;
+  if (((size_t)box_cols * elem_bytes) % 16 || ((size_t)ld * elem_bytes) % 16 || (reinterpret_cast<uintptr_t>(ptr) & 15)) return false;
+  if (swizzle == 1 && box_cols * elem_bytes != 64) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  memcpy(out, &m, sizeof(CUtensorMap));
+  return true;
+}
+
+namespace {
 
 int num_sms() {
   static int n = 0;

@@ -11,4 +11,11 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
                                const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo, int ldw, const float* bias,
                                const LinearOut& out, int M, int N, int K, int act, cudaStream_t s);
 
+// Row-major 2-D tensor map [rows, cols] of 4-byte (fp32) or 2-byte (bf16) elements, row stride ld elements,
+// box = [box_rows, box_cols], swizzle 0 = none / 1 = 64-byte.  Used by the dense attention epilogue (staging of
+// skip / trunk-residual values, tensor stores of the layer output).  `out` receives a 128-byte CUtensorMap
+// (cached per argument tuple).
+bool get_tensor_map_2d(const void* ptr, int elem_bytes, int rows, int cols, int ld, int box_rows, int box_cols, int swizzle,
+                       void* out);
+
 }  // namespace da

@@ -25,3 +25,5 @@ for j in range(15):
     mm = [t[j*4+k]-base if t[j*4+k] else -1 for k in range(3)]
     sm = [t[64+j*4+k]-base if t[64+j*4+k] else -1 for k in range(3)]
     print(j, mm, sm)
+e = [t[120 + k] - base if t[120 + k] else -1 for k in range(6)]
+print("epilogue: last P published, last PV retired, residual scores done, staged rows landed, outputs stored, (chunk loop done):", e)
