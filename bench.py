@@ -223,16 +223,23 @@ def run_b200(args):
             dist.barrier()
         loop_s = []
 
+        state = {"next": mod.prefetch(feats_h, ei_h, batch_h)}
+
         def one_loop():
-            ei_d = ei_h.to(device, non_blocking=True)
-            batch_d = batch_h.to(device, non_blocking=True)
-            feats_d = feats_h.to(device, non_blocking=True)
-            imgs, _ = mod.p_sample_loop((M, 4), feats_d, ei_d, batch_d)
+            # batch i: the whole 30-step loop is enqueued (no host sync inside) ...
+            ta = time.perf_counter()
+            imgs, _ = mod.p_sample_loop((M, 4), *state["next"])
+            tb = time.perf_counter()
+            # ... and while the GPU samples it, batch i + 1 is uploaded from pinned host memory and planned on a side
+            # stream into the spare engine (one upload + one da_set_graph + one da_set_features per loop, as before)
+            state["next"] = mod.prefetch(feats_h, ei_h, batch_h)
+            tc = time.perf_counter()
             for s_, img in enumerate(imgs):
                 host_out[s_].copy_(img, non_blocking=True)
             if world > 1:
                 sharding.gather_poses(imgs[-1], [M] * world)
             torch.cuda.synchronize()
+            state["phases"] = [round(tb - ta, 4), round(tc - tb, 4), round(time.perf_counter() - tc, 4)]
 
         for _ in range(2):  # untimed warm-up loops (first-use allocations / allocator cache, like the W warm-up steps)
             one_loop()
@@ -251,9 +258,11 @@ def run_b200(args):
         nsteps = loops * len(sched)
         h2d = (ei_h.numel() * 8 + batch_h.numel() * 8 + feats_h.numel() * 4) / len(sched)
         e2e = {"value": w["B"] * world * nsteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(M * 4 * 4), "api": "GNN_Diffusion.p_sample_loop (DDIM, 30 steps/loop): pinned host topology + features uploaded and the "
-                      "graph re-planned every loop, every step's x_t read back to pinned host memory",
-               "loops": loops, "loop_seconds": [round(x, 4) for x in loop_s]}
+               "d2h_bytes_per_step": int(M * 4 * 4), "api": "GNN_Diffusion.prefetch + p_sample_loop (DDIM, 30 steps/loop): every loop uploads its pinned host "
+                      "topology + features and re-plans the graph (on a side stream into the spare engine, overlapping the "
+                      "previous loop's sampling); every step's x_t is read back to pinned host memory",
+               "loops": loops, "loop_seconds": [round(x, 4) for x in loop_s],
+               "host_phases_s": {"enqueue_loop": state["phases"][0], "prefetch_next": state["phases"][1], "drain": state["phases"][2]}}
 
     if rank != 0:
         if world > 1:

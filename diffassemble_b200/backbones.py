@@ -125,6 +125,12 @@ class _EngineMixin:
         self._weights_key = None
         self._graph_key = None
         self._feats_key = None
+        # double buffering (prefetch): a second engine that a side stream fills with the NEXT batch
+        self._spare: Optional[DenoiserEngine] = None
+        self._spare_weights_key = None
+        self._spare_last_use = None      # event on the compute stream after the spare engine's last launch
+        self._prefetch_stream = None
+        self._prefetched = None
 
     def _denoiser_state(self):
         skip = ("visual_backbone.", "pcd_backbone.", "linear1.", "linear2.")
@@ -159,6 +165,8 @@ class _EngineMixin:
     def invalidate(self):
         """Force weights / graph / features to be re-sent on the next call."""
         self._weights_key = self._graph_key = self._feats_key = None
+        self._spare_weights_key = None
+        self._prefetched = None
 
     def _bind(self, eng: DenoiserEngine, edge_index: Tensor, feats: Optional[Tensor], batch: Tensor):
         gkey = (self._tensor_key(edge_index), self._tensor_key(batch))
@@ -174,10 +182,81 @@ class _EngineMixin:
             self._feats_key = fkey
         return eng
 
+    def _weights_state_key(self):
+        return tuple((k, v.data_ptr(), v._version) for k, v in self._denoiser_state().items())
+
+    def prefetch(self, edge_index: Tensor, feats: Tensor, batch: Tensor, device=None):
+        """Stage the NEXT batch while the current one computes (double buffering).
+
+        The host -> device copies of ``edge_index`` / ``feats`` / ``batch`` (pinned host tensors copy
+        asynchronously), the virtual-node wiring, ``da_set_graph`` (edge classification, bitmaps, residual CSR)
+        and ``da_set_features`` (the step-invariant hoist GEMM) all run on a side stream into a second engine
+        handle; none of it touches the stream or the handle the running sampling loop uses.  Returns the
+        device tensors ``(edge_index, feats, batch)``: pass exactly these to ``p_sample_loop`` /
+        ``forward_with_feats`` / ``p_sample`` next -- that call switches to the prepared engine after waiting
+        (on the device, not the host) for the side stream.  The reference has no counterpart: it re-uploads and
+        re-wires inside every step."""
+        dev = torch.device(device if device is not None else (feats.device if feats.is_cuda else "cuda"))
+        dev = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        main = torch.cuda.current_stream(dev)
+        if self._prefetch_stream is None or self._prefetch_stream.device != dev:
+            self._prefetch_stream = torch.cuda.Stream(dev)
+        st = self._prefetch_stream
+        if self._spare is None or self._spare.device != dev:
+            if self._spare is not None:
+                self._spare.close()
+            self._spare = self._make_engine(dev)
+            self._spare_weights_key, self._spare_last_use = None, None
+        eng = self._spare
+        with torch.cuda.stream(st):
+            if self._spare_last_use is not None:
+                st.wait_event(self._spare_last_use)   # its buffers may still be read by launches of the previous batch
+            wkey = self._weights_state_key()
+            if wkey != self._spare_weights_key:
+                st.wait_stream(main)                  # parameters may have been written on the compute stream
+                eng.load_weights(self._denoiser_state())
+                self._spare_weights_key = wkey
+            ei = edge_index.to(dev, non_blocking=True)
+            b = batch.to(dev, non_blocking=True)
+            f = feats.to(dev, non_blocking=True)
+            ext, num_total, virt_ids = self.gnn_backbone.extend_graph(ei, b)
+            eng.set_graph(ext, b, num_real=len(b), num_total=num_total, virt_ids=virt_ids)
+            eng.set_features(f)
+            ready = torch.cuda.Event()
+            ready.record(st)
+        for t in (ei, b, f, ext):
+            t.record_stream(main)   # allocated on the side stream, consumed on the compute stream
+        self._prefetched = dict(gkey=(self._tensor_key(ei), self._tensor_key(b)), fkey=self._tensor_key(f), ready=ready,
+                                ext=ext, wkey=wkey)
+        return ei, f, b
+
+    def _take_prefetched(self, edge_index: Tensor, feats: Optional[Tensor], batch: Tensor) -> bool:
+        pf = self._prefetched
+        if pf is None or feats is None:
+            return False
+        if pf["gkey"] != (self._tensor_key(edge_index), self._tensor_key(batch)) or pf["fkey"] != self._tensor_key(feats):
+            return False
+        if pf["wkey"] != self._weights_state_key():
+            self._prefetched = None   # weights changed since the batch was staged: fall back to the normal path
+            return False
+        main = torch.cuda.current_stream(edge_index.device)
+        main.wait_event(pf["ready"])
+        done = torch.cuda.Event()
+        done.record(main)             # everything launched so far on the engine that now becomes the spare
+        self._engine, self._spare = self._spare, self._engine
+        self._weights_key, self._spare_weights_key = pf["wkey"], self._weights_key
+        self._spare_last_use = done
+        self._graph_key, self._feats_key = pf["gkey"], pf["fkey"]
+        self._ext_edge_index = pf["ext"]
+        self._prefetched = None
+        return True
+
     def engine_for(self, edge_index: Tensor, feats: Optional[Tensor], batch: Tensor) -> DenoiserEngine:
         """Engine with this graph and these features bound (used by the fused sampler steps)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and feats is not None and feats.requires_grad:
             raise NotImplementedError("autograd through the CUDA denoiser is not implemented (scope row N1)")
+        if self._prefetched is not None and self._take_prefetched(edge_index, feats, batch):
+            return self._engine
         eng = self._get_engine(edge_index.device)
         return self._bind(eng, edge_index, feats, batch)
 

@@ -541,8 +541,8 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
   const int c_hid = hid / c.heads, c_last = D / c.heads;
   const int cpad_max = ((c_hid > c_last ? c_hid : c_last) + 15) / 16 * 16;
   h->use_plan = (c.attn_mode == DA_ATTN_AUTO) && batch != nullptr && (c_hid % 8 == 0) && (c_last % 8 == 0) && cpad_max <= 144;
-  free_csr(&h->csr);
-  free_plan(&h->plan);
+  free_csr(&h->csr, s);
+  free_plan(&h->plan, s);
   if (h->use_plan) ce = build_dense_plan(edge_src, edge_dst, E, batch, num_real, num_total, &h->plan, s, &why);
   else ce = build_csr(edge_src, edge_dst, E, num_total, &h->csr, s, &why);
   if (ce != cudaSuccess) {

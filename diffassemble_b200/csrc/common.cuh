@@ -169,6 +169,12 @@ inline cudaError_t tmp_alloc(void** p, size_t bytes, cudaStream_t s) {
 template <typename T>
 inline cudaError_t tmp_alloc(T** p, size_t bytes, cudaStream_t s) { return tmp_alloc(reinterpret_cast<void**>(p), bytes, s); }
 inline void tmp_free(void* p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+// copy on `s` and wait for `s` only: unlike cudaMemcpy it does not serialise with the legacy default stream, so a
+// batch can be prepared on a side stream while another handle computes (GNN_Diffusion.prefetch)
+inline cudaError_t copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
 
 // graph structure
 struct CsrGraph {
@@ -184,7 +190,7 @@ cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, 
                       const char** err);
 cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
                                  const char** err);
-void free_csr(CsrGraph* g);
+void free_csr(CsrGraph* g, cudaStream_t s = nullptr);   // stream-ordered (cudaFreeAsync on s)
 
 // greedy assignment metric (scope row N2): out [sum n, 3] int64 = (row, column, int64(distance)) in greedy order
 cudaError_t launch_greedy_assign(const float* pos1, int ld1, const float* pos2, int ld2, const int32_t* graph_ptr,
@@ -258,7 +264,7 @@ struct DensePlan {
   // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
   uint8_t* f32_tile_flags[2] = {nullptr, nullptr};
 };
-void free_plan(DensePlan* p);
+void free_plan(DensePlan* p, cudaStream_t s = nullptr);   // stream-ordered (cudaFreeAsync on s)
 // Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.
 cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
                              int num_total, DensePlan* plan, cudaStream_t s, const char** err);

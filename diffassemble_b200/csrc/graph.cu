@@ -42,9 +42,9 @@ __global__ void rowptr_kernel(const int32_t* __restrict__ sorted_dst, int64_t E,
 
 }  // namespace
 
-void free_csr(CsrGraph* g) {
+void free_csr(CsrGraph* g, cudaStream_t s) {
   if (!g) return;
-  cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->eid); cudaFree(g->weight);
+  tmp_free(g->rowptr, s); tmp_free(g->col, s); tmp_free(g->eid, s); tmp_free(g->weight, s);
   *g = CsrGraph();
 }
 
@@ -73,7 +73,7 @@ __global__ void unpack_runs_kernel(const unsigned long long* __restrict__ ukey, 
 cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
                                  const char** err) {
   *err = "";
-  free_csr(g);
+  free_csr(g, s);
   if (E >= (int64_t)1 << 31) { *err = "edge count exceeds int32 range"; return cudaErrorInvalidValue; }
   cudaError_t ce;
 #define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
@@ -84,11 +84,11 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
   int32_t bad_h = 0, nruns_h = 0;
   int bits = 1;
   g->n = n;
-  DA_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1)));
+  DA_TRY(tmp_alloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1), s));
   if (E == 0) {
     g->E = 0;
-    DA_TRY(cudaMalloc(&g->col, sizeof(int32_t)));
-    DA_TRY(cudaMalloc(&g->weight, sizeof(float)));
+    DA_TRY(tmp_alloc(&g->col, sizeof(int32_t), s));
+    DA_TRY(tmp_alloc(&g->weight, sizeof(float), s));
     DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
     return cudaSuccess;
   }
@@ -114,8 +114,8 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
   DA_TRY(cudaStreamSynchronize(s));
   if (bad_h) { *err = "edge_index entry outside [0, num_total)"; ce = cudaErrorInvalidValue; goto fail; }
   g->E = nruns_h;
-  DA_TRY(cudaMalloc(&g->col, sizeof(int32_t) * (size_t)nruns_h));
-  DA_TRY(cudaMalloc(&g->weight, sizeof(float) * (size_t)nruns_h));
+  DA_TRY(tmp_alloc(&g->col, sizeof(int32_t) * (size_t)nruns_h, s));
+  DA_TRY(tmp_alloc(&g->weight, sizeof(float) * (size_t)nruns_h, s));
   unpack_runs_kernel<<<(nruns_h + 255) / 256, 256, 0, s>>>(ukey, cnt, nruns, g->col, g->weight, udst);
   DA_TRY(cudaGetLastError());
   rowptr_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(udst, nruns_h, n, g->rowptr);
@@ -125,7 +125,7 @@ cudaError_t build_csr_compressed(const int64_t* src, const int64_t* dst, int64_t
   return cudaSuccess;
 fail:
   tmp_free(key, s); tmp_free(key_sorted, s); tmp_free(ukey, s); tmp_free(cnt, s); tmp_free(udst, s); tmp_free(nruns, s); tmp_free(bad, s); tmp_free(tmp, s);
-  free_csr(g);
+  free_csr(g, s);
   return ce;
 #undef DA_TRY
 }
@@ -133,7 +133,7 @@ fail:
 cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, CsrGraph* g, cudaStream_t s,
                       const char** err) {
   *err = "";
-  free_csr(g);
+  free_csr(g, s);
   if (E >= (int64_t)1 << 31) { *err = "edge count exceeds int32 range"; return cudaErrorInvalidValue; }
   cudaError_t ce;
 #define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
@@ -143,9 +143,9 @@ cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, 
   int32_t bad_h = 0;
   int bits = 1;
   g->n = n; g->E = E;
-  DA_TRY(cudaMalloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1)));
-  DA_TRY(cudaMalloc(&g->col, sizeof(int32_t) * (size_t)(E > 0 ? E : 1)));
-  DA_TRY(cudaMalloc(&g->eid, sizeof(int32_t) * (size_t)(E > 0 ? E : 1)));
+  DA_TRY(tmp_alloc(&g->rowptr, sizeof(int32_t) * (size_t)(n + 1), s));
+  DA_TRY(tmp_alloc(&g->col, sizeof(int32_t) * (size_t)(E > 0 ? E : 1), s));
+  DA_TRY(tmp_alloc(&g->eid, sizeof(int32_t) * (size_t)(E > 0 ? E : 1), s));
   if (E == 0) {
     DA_TRY(cudaMemsetAsync(g->rowptr, 0, sizeof(int32_t) * (size_t)(n + 1), s));
     return cudaSuccess;
@@ -168,11 +168,11 @@ cudaError_t build_csr(const int64_t* src, const int64_t* dst, int64_t E, int n, 
   DA_TRY(cudaMemcpyAsync(&bad_h, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   DA_TRY(cudaStreamSynchronize(s));
   tmp_free(key, s); tmp_free(val, s); tmp_free(key_sorted, s); tmp_free(bad, s); tmp_free(tmp, s);
-  if (bad_h) { *err = "edge_index entry outside [0, num_total)"; free_csr(g); return cudaErrorInvalidValue; }
+  if (bad_h) { *err = "edge_index entry outside [0, num_total)"; free_csr(g, s); return cudaErrorInvalidValue; }
   return cudaSuccess;
 fail:
   tmp_free(key, s); tmp_free(val, s); tmp_free(key_sorted, s); tmp_free(bad, s); tmp_free(tmp, s);
-  free_csr(g);
+  free_csr(g, s);
   return ce;
 #undef DA_TRY
 }

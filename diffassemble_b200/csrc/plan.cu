@@ -22,12 +22,20 @@ constexpr int DENSITY_DIV = 16;       // dense if in-graph edges >= n^2 / 16
 __global__ void count_ingraph_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
                                            const int64_t* __restrict__ batch, int num_real,
                                            unsigned long long* __restrict__ cnt) {
+  // one atomic per (warp, graph) instead of one per edge: PyG batches keep a graph's edges together, so an
+  // un-aggregated version fires ~E atomics at a few dozen addresses -- slow by itself and, when the plan is built
+  // on a side stream (prefetch), a storm that stalls the memory traffic of the sampling kernels running next to it
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  int64_t s = src[e], d = dst[e];
-  if (s < 0 || d < 0 || s >= num_real || d >= num_real) return;
-  int64_t g = batch[d];
-  if (batch[s] == g) atomicAdd(&cnt[g], 1ull);
+  long long g = -1;
+  if (e < E) {
+    int64_t s = src[e], d = dst[e];
+    if (s >= 0 && d >= 0 && s < num_real && d < num_real) {
+      int64_t gd = batch[d];
+      if (batch[s] == gd) g = (long long)gd;
+    }
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, g);
+  if (g >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cnt[g], (unsigned long long)__popc(peers));
 }
 
 // flag[e] = 1 -> residual edge (goes to the CSR), 0 -> recorded in the bitmap
@@ -67,10 +75,10 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 
 }  // namespace
 
-void free_plan(DensePlan* p) {
+void free_plan(DensePlan* p, cudaStream_t s) {
   if (!p) return;
-  cudaFree(p->tiles); cudaFree(p->node_slot); cudaFree(p->bitmap); cudaFree(p->light); cudaFree(p->heavy); cudaFree(p->row_fused); cudaFree(p->light_nf); cudaFree(p->x_src); cudaFree(p->x_slot); cudaFree(p->f32_tile_flags[0]); cudaFree(p->f32_tile_flags[1]);
-  free_csr(&p->residual);
+  tmp_free(p->tiles, s); tmp_free(p->node_slot, s); tmp_free(p->bitmap, s); tmp_free(p->light, s); tmp_free(p->heavy, s); tmp_free(p->row_fused, s); tmp_free(p->light_nf, s); tmp_free(p->x_src, s); tmp_free(p->x_slot, s); tmp_free(p->f32_tile_flags[0], s); tmp_free(p->f32_tile_flags[1], s);
+  free_csr(&p->residual, s);
   *p = DensePlan();
 }
 
@@ -79,7 +87,7 @@ size_t dense_image_elems(int n_tiles, int H, int Cpad) { return (size_t)n_tiles 
 cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
                              int num_total, DensePlan* plan, cudaStream_t s, const char** err) {
   *err = "";
-  free_plan(plan);
+  free_plan(plan, s);
   cudaError_t ce = cudaSuccess;
 #define DA_TRY(x) do { ce = (x); if (ce != cudaSuccess) { *err = #x; goto fail; } } while (0)
   std::vector<int64_t> hbatch(num_real);
@@ -154,11 +162,11 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   }
   plan->n_tiles = (int)tiles.size();
   plan->bitmap_words = words;
-  DA_TRY(cudaMalloc(&plan->node_slot, sizeof(int32_t) * (size_t)num_total));
+  DA_TRY(tmp_alloc(&plan->node_slot, sizeof(int32_t) * (size_t)num_total, s));
   DA_TRY(cudaMemcpyAsync(plan->node_slot, node_slot.data(), sizeof(int32_t) * (size_t)num_total, cudaMemcpyHostToDevice, s));
   if (plan->n_tiles > 0) {
-    DA_TRY(cudaMalloc(&plan->tiles, sizeof(TileInfo) * tiles.size()));   // uploaded after the promotion pass (gn may grow)
-    DA_TRY(cudaMalloc(&plan->bitmap, sizeof(uint32_t) * words));
+    DA_TRY(tmp_alloc(&plan->tiles, sizeof(TileInfo) * tiles.size(), s));   // uploaded after the promotion pass (gn may grow)
+    DA_TRY(tmp_alloc(&plan->bitmap, sizeof(uint32_t) * words, s));
     DA_TRY(cudaMemsetAsync(plan->bitmap, 0, sizeof(uint32_t) * words, s));
     DA_TRY(tmp_alloc(&d_g_node0, sizeof(int32_t) * B, s));
     DA_TRY(tmp_alloc(&d_g_bm_words, sizeof(int32_t) * B, s));
@@ -201,9 +209,9 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     std::vector<float> wv((size_t)Er), new_w;
     std::vector<int64_t> bword;
     std::vector<uint32_t> bbit;
-    DA_TRY(cudaMemcpy(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
-    DA_TRY(cudaMemcpy(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)Er, cudaMemcpyDeviceToHost));
-    DA_TRY(cudaMemcpy(wv.data(), plan->residual.weight, sizeof(float) * (size_t)Er, cudaMemcpyDeviceToHost));
+    DA_TRY(copy_sync(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost, s));
+    DA_TRY(copy_sync(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)Er, cudaMemcpyDeviceToHost, s));
+    DA_TRY(copy_sync(wv.data(), plan->residual.weight, sizeof(float) * (size_t)Er, cudaMemcpyDeviceToHost, s));
     new_col.reserve((size_t)Er); new_w.reserve((size_t)Er);
     std::vector<std::vector<int32_t>> xsrc_of((size_t)B);   // per graph: sources in extra-column order
     for (int i = 0; i < num_total; ++i) {
@@ -248,15 +256,15 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
       tmp_free(d_w, s); tmp_free(d_b, s);
       plan->n_extra = (int)xs.size();
       plan->n_promoted_edges = (int64_t)bword.size();
-      DA_TRY(cudaMalloc(&plan->x_src, sizeof(int32_t) * xs.size()));
-      DA_TRY(cudaMalloc(&plan->x_slot, sizeof(int32_t) * xs.size()));
-      DA_TRY(cudaMemcpy(plan->x_src, xs.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice));
-      DA_TRY(cudaMemcpy(plan->x_slot, xslot.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice));
+      DA_TRY(tmp_alloc(&plan->x_src, sizeof(int32_t) * xs.size(), s));
+      DA_TRY(tmp_alloc(&plan->x_slot, sizeof(int32_t) * xs.size(), s));
+      DA_TRY(copy_sync(plan->x_src, xs.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice, s));
+      DA_TRY(copy_sync(plan->x_slot, xslot.data(), sizeof(int32_t) * xs.size(), cudaMemcpyHostToDevice, s));
       // the rewritten residual is never larger: overwrite in place
-      DA_TRY(cudaMemcpy(plan->residual.rowptr, new_rp.data(), sizeof(int32_t) * new_rp.size(), cudaMemcpyHostToDevice));
+      DA_TRY(copy_sync(plan->residual.rowptr, new_rp.data(), sizeof(int32_t) * new_rp.size(), cudaMemcpyHostToDevice, s));
       if (!new_col.empty()) {
-        DA_TRY(cudaMemcpy(plan->residual.col, new_col.data(), sizeof(int32_t) * new_col.size(), cudaMemcpyHostToDevice));
-        DA_TRY(cudaMemcpy(plan->residual.weight, new_w.data(), sizeof(float) * new_w.size(), cudaMemcpyHostToDevice));
+        DA_TRY(copy_sync(plan->residual.col, new_col.data(), sizeof(int32_t) * new_col.size(), cudaMemcpyHostToDevice, s));
+        DA_TRY(copy_sync(plan->residual.weight, new_w.data(), sizeof(float) * new_w.size(), cudaMemcpyHostToDevice, s));
       }
       plan->residual.E = (int64_t)new_col.size();
       plan->n_dense_edges += plan->n_promoted_edges;
@@ -264,11 +272,11 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     extra_sources = xs;
   }
   if (plan->n_tiles > 0)
-    DA_TRY(cudaMemcpy(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice));
+    DA_TRY(copy_sync(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, s));
   {  // degree classes of the residual CSR (node order kept, real nodes before virtual rows)
     std::vector<int32_t> rp((size_t)num_total + 1), light, heavy, light_nf;
     std::vector<uint8_t> fused((size_t)num_total, 0);
-    DA_TRY(cudaMemcpy(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost));
+    DA_TRY(copy_sync(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost, s));
     plan->n_fused = 0;
     for (int i = 0; i < num_total; ++i) {
       if (i == num_real) {
@@ -287,14 +295,14 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
       plan->n_light_nf_real = (int)light_nf.size();
     }
     plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size(); plan->n_light_nf = (int)light_nf.size();
-    DA_TRY(cudaMalloc(&plan->row_fused, fused.size() + 1));
-    DA_TRY(cudaMemcpy(plan->row_fused, fused.data(), fused.size(), cudaMemcpyHostToDevice));
-    DA_TRY(cudaMalloc(&plan->light_nf, sizeof(int32_t) * (light_nf.size() + 1)));
-    DA_TRY(cudaMemcpy(plan->light_nf, light_nf.data(), sizeof(int32_t) * light_nf.size(), cudaMemcpyHostToDevice));
+    DA_TRY(tmp_alloc(&plan->row_fused, fused.size() + 1, s));
+    DA_TRY(copy_sync(plan->row_fused, fused.data(), fused.size(), cudaMemcpyHostToDevice, s));
+    DA_TRY(tmp_alloc(&plan->light_nf, sizeof(int32_t) * (light_nf.size() + 1), s));
+    DA_TRY(copy_sync(plan->light_nf, light_nf.data(), sizeof(int32_t) * light_nf.size(), cudaMemcpyHostToDevice, s));
     {  // which 128-row tiles contain rows whose fp32 Q / K / V some CSR kernel reads?
       std::vector<int32_t> colv((size_t)(plan->residual.E > 0 ? plan->residual.E : 1));
       if (plan->residual.E > 0)
-        DA_TRY(cudaMemcpy(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)plan->residual.E, cudaMemcpyDeviceToHost));
+        DA_TRY(copy_sync(colv.data(), plan->residual.col, sizeof(int32_t) * (size_t)plan->residual.E, cudaMemcpyDeviceToHost, s));
       const int n_mt = (num_total + 127) / 128;
       for (int v = 0; v < 2; ++v) {
         std::vector<uint8_t> fl((size_t)n_mt, 0);
@@ -310,14 +318,14 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
         for (int32_t x : extra_sources) fl[x >> 7] |= 2;   // the per-layer gather reads their fp32 K / V rows
         for (int i = 0; i < num_total; ++i)
           if (node_slot[i] < 0) fl[i >> 7] = 3;   // rows outside the dense tiles are served by the CSR kernels only
-        DA_TRY(cudaMalloc(&plan->f32_tile_flags[v], (size_t)n_mt));
-        DA_TRY(cudaMemcpy(plan->f32_tile_flags[v], fl.data(), (size_t)n_mt, cudaMemcpyHostToDevice));
+        DA_TRY(tmp_alloc(&plan->f32_tile_flags[v], (size_t)n_mt, s));
+        DA_TRY(copy_sync(plan->f32_tile_flags[v], fl.data(), (size_t)n_mt, cudaMemcpyHostToDevice, s));
       }
     }
-    DA_TRY(cudaMalloc(&plan->light, sizeof(int32_t) * (light.size() + 1)));
-    DA_TRY(cudaMalloc(&plan->heavy, sizeof(int32_t) * (heavy.size() + 1)));
-    DA_TRY(cudaMemcpy(plan->light, light.data(), sizeof(int32_t) * light.size(), cudaMemcpyHostToDevice));
-    DA_TRY(cudaMemcpy(plan->heavy, heavy.data(), sizeof(int32_t) * heavy.size(), cudaMemcpyHostToDevice));
+    DA_TRY(tmp_alloc(&plan->light, sizeof(int32_t) * (light.size() + 1), s));
+    DA_TRY(tmp_alloc(&plan->heavy, sizeof(int32_t) * (heavy.size() + 1), s));
+    DA_TRY(copy_sync(plan->light, light.data(), sizeof(int32_t) * light.size(), cudaMemcpyHostToDevice, s));
+    DA_TRY(copy_sync(plan->heavy, heavy.data(), sizeof(int32_t) * heavy.size(), cudaMemcpyHostToDevice, s));
   }
   tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
   tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
@@ -325,7 +333,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
 fail:
   tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
   tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
-  free_plan(plan);
+  free_plan(plan, s);
   return ce;
 #undef DA_TRY
 }

@@ -268,6 +268,21 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             return cond  # already encoder features
         return self.visual_features(cond)
 
+    def prefetch(self, cond, edge_index, batch, device=None):
+        """Stage the next batch (host or device tensors; ``cond`` = pre-computed node features) on a side stream
+        into the spare engine while the current batch is being sampled -- see ``Eff_GAT.prefetch``.  Returns the
+        device tensors ``(cond, edge_index, batch)`` to hand to ``p_sample_loop`` next::
+
+            nxt = model.prefetch(*first_batch)
+            for following in batches:
+                imgs, _ = model.p_sample_loop(shape, *nxt)      # enqueues the whole loop, returns immediately
+                nxt = model.prefetch(*following)                # uploads + plans while the GPU samples
+        """
+        if cond is None or cond.dim() != 2 or cond.shape[1] != self.model.combined_features_dim - 64:
+            raise ValueError("prefetch needs pre-computed node features [M, %d] as cond" % (self.model.combined_features_dim - 64))
+        ei, f, b = self.model.prefetch(edge_index, cond, batch, device)
+        return f, ei, b
+
     # -- forward diffusion (training-side helpers; forward only) -----------------------------------
     def q_sample(self, x_start, t, noise=None):  # :421-430
         if noise is None:

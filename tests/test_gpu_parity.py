@@ -480,3 +480,35 @@ def test_constructor_variants(kw):
         got, _ = mod.p_sample(x.to(DEV), t.to(DEV), i, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV),
                               batch=batch.to(DEV))
         assert rel_err(got, want) < TOL, (kw, i)
+
+
+def test_prefetch_double_buffering_matches_plain_path():
+    """``GNN_Diffusion.prefetch`` (side-stream upload + planning into the spare engine) gives bit-identical
+    trajectories to the plain path, across alternating engines and changing batch shapes."""
+    ref, mod = make_pair_2d(seed=3, steps=40, sampling="DDIM", architecture="exophormer", virt_nodes=4,
+                            model_mean_type="START_X", inference_ratio=10, gemm_mode="bf16x3", attn_mode="auto",
+                            noise_weight=1.0)
+    mod = mod.to(DEV)
+    batches = []
+    for k, sizes in enumerate([[64, 100], [144], [80, 64, 48], [64, 100]]):
+        ei, batch = synth_graph_batch(sizes, kind="expander", seed=10 * k)
+        g = torch.Generator().manual_seed(k)
+        feats = torch.randn(len(batch), 1088, generator=g)
+        batches.append((feats.pin_memory(), ei.pin_memory(), batch.pin_memory()))
+    gen = lambda k: torch.Generator(device=DEV).manual_seed(100 + k)
+    want = []
+    for k, (f, ei, b) in enumerate(batches):   # plain path
+        imgs, _ = mod.p_sample_loop((len(b), 4), f.to(DEV), ei.to(DEV), b.to(DEV), generator=gen(k))
+        want.append(imgs[-1].clone())
+    nxt = mod.prefetch(*batches[0])
+    got = []
+    for k in range(len(batches)):
+        cur = nxt
+        imgs, _ = mod.p_sample_loop((len(cur[2]), 4), *cur, generator=gen(k))
+        if k + 1 < len(batches):
+            nxt = mod.prefetch(*batches[k + 1])   # overlaps with the loop just enqueued
+        got.append(imgs[-1])
+    torch.cuda.synchronize()
+    for k, (a, bb) in enumerate(zip(got, want)):
+        assert torch.equal(a, bb), k
+    assert mod.model._spare is not None and mod.model._engine is not mod.model._spare
