@@ -68,6 +68,11 @@ struct da_handle {
   // development switches (environment, read once per handle): DA_NO_FUSE=1 keeps the un-fused
   // dense -> (acc, stats) -> CSR-continuation pipeline for A/B measurements
   bool no_fuse = getenv("DA_NO_FUSE") != nullptr && getenv("DA_NO_FUSE")[0] == '1';
+  bool no_side = getenv("DA_NO_SIDE") != nullptr && getenv("DA_NO_SIDE")[0] == '1';
+  bool no_vrows = getenv("DA_NO_VROWS") != nullptr && getenv("DA_NO_VROWS")[0] == '1';
+  // side stream: the CSR kernels of rows outside every dense tile (virtual nodes) run next to the dense kernel
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   void* dbg_trace = nullptr;   // development aid: clock64 trace buffer for the dense attention kernel
   DevBuf qimg, kimg, vimg, qimg_l, kimg_l, vimg_l, dacc, dstats;   // operand images: hidden layers / last layer
   // activations / workspace
@@ -253,6 +258,56 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
       xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
     }
+    const bool rows_path = h->use_plan && attn_csr_rows_supported(c.heads, C) && !a.scores;
+    AttnCsrArgs hv = a, lt = a;
+    if (rows_path) {
+      // residual edges: low-degree rows on the warp-per-node kernel, heavy rows (virtual nodes) edge-parallel
+      const DensePlan& pl = h->plan;
+      hv.node_list = pl.heavy; hv.n_targets = last ? pl.n_heavy_real : pl.n_heavy;
+      if (dense && umma) { hv.img_slot = pl.node_slot; hv.kimg = kimg; hv.vimg = vimg; hv.img_Cpad = Cpad; }
+      if (fuse) { lt.node_list = pl.light_nf; lt.n_targets = last ? pl.n_light_nf_real : pl.n_light_nf; }
+      else { lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light; }
+    }
+    // hidden layers (32-channel heads), every CSR-served row outside the tiles: one lane-per-edge launch
+    const bool vrows = rows_path && dense && fuse && !last && h->plan.csr_rows_independent && attn_csr_vrows_supported(c.heads, C) &&
+                       !(dense && umma && Cpad != 32) && !h->no_vrows;
+    auto launch_rows = [&](cudaStream_t st) -> cudaError_t {
+      cudaError_t e = cudaSuccess;
+      if (vrows) {
+        if (h->plan.n_csr_rows > 0) {
+          AttnCsrArgs vr = hv;
+          vr.node_list = h->plan.csr_rows; vr.n_targets = h->plan.n_csr_rows;
+          vr.init_acc = nullptr; vr.init_stats = nullptr; vr.init_slot = nullptr;
+          Scoped sc(h, st, TAG_ATTN_HIDDEN);
+          e = launch_attn_csr_vrows(vr, st);
+        }
+        return e;
+      }
+      if (hv.n_targets > 0) {
+        Scoped sc(h, st, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
+        e = launch_attn_csr_heavy(hv, st);
+      }
+      if (e == cudaSuccess && lt.n_targets > 0) {
+        Scoped sc(h, st, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
+        e = launch_attn_csr_rows(lt, st);
+      }
+      return e;
+    };
+    // With every in-tile row finalised by the dense kernel, the CSR kernels only serve rows outside the tiles
+    // (virtual nodes): they depend on the GEMM alone and run on a side stream next to the dense kernel.
+    const bool side_rows = rows_path && dense && fuse && h->plan.csr_rows_independent && !h->no_side &&
+                           (hv.n_targets > 0 || lt.n_targets > 0);
+    if (side_rows) {
+      if (!h->side) {
+        DA_CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking), "side stream");
+        DA_CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "side stream");
+        DA_CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "side stream");
+      }
+      DA_CK(cudaEventRecord(h->ev_fork, s), "fork");
+      DA_CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork");
+      DA_CK(launch_rows(h->side), "graph attention (rows outside the dense tiles)");
+      DA_CK(cudaEventRecord(h->ev_join, h->side), "join");
+    }
     if (dense) {
       AttnDenseArgs da_{};
       da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;
@@ -270,22 +325,10 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
       DA_CK(launch_attn_dense(da_, s), "dense attention");
     }
-    if (h->use_plan && attn_csr_rows_supported(c.heads, C) && !a.scores) {
-      // residual edges: low-degree rows on the warp-per-node kernel, heavy rows (virtual nodes) edge-parallel
-      const DensePlan& pl = h->plan;
-      AttnCsrArgs hv = a, lt = a;
-      hv.node_list = pl.heavy; hv.n_targets = last ? pl.n_heavy_real : pl.n_heavy;
-      if (dense && umma) { hv.img_slot = pl.node_slot; hv.kimg = kimg; hv.vimg = vimg; hv.img_Cpad = Cpad; }
-      if (fuse) { lt.node_list = pl.light_nf; lt.n_targets = last ? pl.n_light_nf_real : pl.n_light_nf; }
-      else { lt.node_list = pl.light; lt.n_targets = last ? pl.n_light_real : pl.n_light; }
-      if (hv.n_targets > 0) {
-        Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
-        DA_CK(launch_attn_csr_heavy(hv, s), "graph attention (heavy rows)");
-      }
-      if (lt.n_targets > 0) {
-        Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
-        DA_CK(launch_attn_csr_rows(lt, s), "graph attention (light rows)");
-      }
+    if (side_rows) {
+      DA_CK(cudaStreamWaitEvent(s, h->ev_join, 0), "join");
+    } else if (rows_path) {
+      DA_CK(launch_rows(s), "graph attention (residual rows)");
     } else {
       Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
       DA_CK(launch_attn_csr(a, s), "graph attention");
@@ -391,6 +434,9 @@ void da_destroy(da_handle* h) {
   for (auto* b : all) b->release();
   free_csr(&h->csr);
   free_plan(&h->plan);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 

@@ -273,6 +273,122 @@ attn_csr_heavy_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __r
   }
 }
 
+// Lane-per-edge variant for 32-channel heads (the hidden layers): one CTA owns one (target, head) of a row that is
+// NOT part of a dense tile (virtual nodes: a few hub rows with ~1000 in-edges, many rows with a handful).  Each
+// lane fetches the whole K row and V row of ITS edge up front (16 independent 16-byte loads: one memory latency per
+// 32-edge chunk instead of one per 4 edges), computes its score alone, and the 32 weighted V rows of a chunk are
+// summed by a transposing butterfly (31 shuffles) that leaves channel c in lane c.
+constexpr int VROW_WARPS = 8;
+
+__device__ __forceinline__ void load_row32(const float* __restrict__ fp32_row, const __nv_bfloat16* __restrict__ img_row,
+                                           size_t lo_off, float* out) {
+  if (img_row != nullptr) {   // split-bf16 operand image: 4 chunks of 8 channels, 512 elements apart; lo plane at lo_off
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const uint4 hi = __ldg(reinterpret_cast<const uint4*>(img_row + (size_t)ch * 512));
+      const uint4 lo = __ldg(reinterpret_cast<const uint4*>(img_row + lo_off + (size_t)ch * 512));
+      out[8 * ch + 0] = bf_lo(hi.x) + bf_lo(lo.x); out[8 * ch + 1] = bf_hi(hi.x) + bf_hi(lo.x);
+      out[8 * ch + 2] = bf_lo(hi.y) + bf_lo(lo.y); out[8 * ch + 3] = bf_hi(hi.y) + bf_hi(lo.y);
+      out[8 * ch + 4] = bf_lo(hi.z) + bf_lo(lo.z); out[8 * ch + 5] = bf_hi(hi.z) + bf_hi(lo.z);
+      out[8 * ch + 6] = bf_lo(hi.w) + bf_lo(lo.w); out[8 * ch + 7] = bf_hi(hi.w) + bf_hi(lo.w);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(fp32_row + c));
+      out[c] = t.x; out[c + 1] = t.y; out[c + 2] = t.z; out[c + 3] = t.w;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(VROW_WARPS * 32)
+attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
+                       const int32_t* __restrict__ col, const float* __restrict__ weight,
+                       const int32_t* __restrict__ node_list, int H, float scale,
+                       const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
+                       __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
+                       const int32_t* __restrict__ img_slot, const __nv_bfloat16* __restrict__ kimg,
+                       const __nv_bfloat16* __restrict__ vimg, int Cpad) {
+  constexpr int C = 32;
+  __shared__ float acc_s[VROW_WARPS][C];
+  __shared__ float m_s[VROW_WARPS], l_s[VROW_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int node = node_list[blockIdx.x / H], head = blockIdx.x % H;
+  const int HC = H * C;
+  float q[C];
+  {
+    const float* qrow = qkvs + (size_t)node * ld + head * C;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(qrow + c));
+      q[c] = t.x * scale; q[c + 1] = t.y * scale; q[c + 2] = t.z * scale; q[c + 3] = t.w * scale;
+    }
+  }
+  const int beg = rowptr[node], end = rowptr[node + 1];
+  const size_t lo_off = (size_t)64 * Cpad;
+  float m = -INFINITY, l = 0.f, acc = 0.f;   // acc: channel `lane` of this warp's partial sum
+  for (int base = beg + warp * 32; base < end; base += 32 * VROW_WARPS) {
+    const int e = base + lane;
+    const bool valid = e < end;
+    const int j = valid ? col[e] : node;
+    const float w = (valid && weight != nullptr) ? weight[e] : 1.f;
+    const int sj = (img_slot != nullptr) ? __ldg(img_slot + j) : -1;
+    const __nv_bfloat16* kb = sj >= 0 ? kimg + ((size_t)(sj >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (sj & 63) * 8 : nullptr;
+    const __nv_bfloat16* vb = sj >= 0 ? vimg + ((size_t)(sj >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (sj & 63) * 8 : nullptr;
+    float kf[C], vf[C];
+    load_row32(qkvs + (size_t)j * ld + HC + head * C, kb, lo_off, kf);
+    load_row32(qkvs + (size_t)j * ld + 2 * HC + head * C, vb, lo_off, vf);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c += 4) {
+      d0 = fmaf(kf[c], q[c], d0); d1 = fmaf(kf[c + 1], q[c + 1], d1);
+      d2 = fmaf(kf[c + 2], q[c + 2], d2); d3 = fmaf(kf[c + 3], q[c + 3], d3);
+    }
+    const float s = valid ? (d0 + d1) + (d2 + d3) : -INFINITY;
+    const float m_new = fmaxf(m, warp_max(s));
+    const float p = valid ? w * expf(s - m_new) : 0.f;
+    const float rescale = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    l = l * rescale + warp_sum(p);
+    m = m_new;
+    // sum over the 32 lanes of p * v[c], channel c ending up in lane c: halve the vector at every step
+#pragma unroll
+    for (int c = 0; c < C; ++c) vf[c] *= p;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float keep = upper ? vf[i + off] : vf[i];
+        const float give = upper ? vf[i] : vf[i + off];
+        vf[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+      }
+    }
+    acc = fmaf(acc, rescale, vf[0]);
+  }
+  if (lane == 0) { m_s[warp] = m; l_s[warp] = l; }
+  acc_s[warp][lane] = acc;
+  __syncthreads();
+  if (warp != 0) return;
+  const float mw = lane < VROW_WARPS ? m_s[lane] : -INFINITY, lw = lane < VROW_WARPS ? l_s[lane] : 0.f;
+  const float M = warp_max(mw);
+  const float fw = (mw == -INFINITY) ? 0.f : expf(mw - M);
+  const float L = warp_sum(lw * fw);
+  const float inv = 1.f / (L + 1e-16f);
+  float a = 0.f;
+#pragma unroll
+  for (int w2 = 0; w2 < VROW_WARPS; ++w2) a = fmaf(acc_s[w2][lane], __shfl_sync(0xffffffffu, fw, w2), a);
+  float v = a * inv + __ldg(qkvs + (size_t)node * ld + 3 * HC + head * C + lane);
+  if (resid) v += resid[(size_t)node * ld_resid + head * C + lane];
+  v = apply_act_rt(v, act);
+  const size_t o = (size_t)head * C + lane;
+  if (yf) yf[(size_t)node * ldc + o] = v;
+  if (yhi) {
+    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+    yhi[(size_t)node * ldsp + o] = hb;
+    ylo[(size_t)node * ldsp + o] = __float2bfloat16_rn(v - __bfloat162float(hb));
+  }
+}
+
 // Row-parallel variant for low-degree targets (the residual edges of a dense-tile plan: typically one
 // virtual->real edge per node).  One warp owns one target node and ALL heads: lane l holds the VPL =
 // H*C/32 contiguous channels [l*VPL, (l+1)*VPL) of the row, which belong to head l / (32/H); every
@@ -412,6 +528,19 @@ cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s) {
   else if (R <= 13) DA_LAUNCH(13);
   else return cudaErrorInvalidValue;  // head dims above 416 (resnet50 trunk) are not built
 #undef DA_LAUNCH
+  return cudaGetLastError();
+}
+
+bool attn_csr_vrows_supported(int H, int C) { return C == 32 && H > 0; }
+
+cudaError_t launch_attn_csr_vrows(const AttnCsrArgs& a, cudaStream_t s) {
+  if (a.n_targets <= 0) return cudaSuccess;
+  if (!a.node_list || a.scores || a.stats || a.init_acc || a.C != 32 || (a.ld & 3)) return cudaErrorInvalidValue;
+  if (a.img_slot != nullptr && (a.kimg == nullptr || a.vimg == nullptr || a.img_Cpad != 32)) return cudaErrorInvalidValue;
+  const float scale = 1.0f / sqrtf((float)a.C);
+  attn_csr_vrow32_kernel<<<(unsigned)a.n_targets * a.H, VROW_WARPS * 32, 0, s>>>(
+      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.H, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc,
+      a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad);
   return cudaGetLastError();
 }
 

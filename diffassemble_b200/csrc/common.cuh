@@ -105,6 +105,9 @@ bool attn_csr_rows_supported(int H, int C);
 cudaError_t launch_attn_csr_rows(const AttnCsrArgs& a, cudaStream_t s);
 // CTA-per-(node, head) variant for rows with hundreds of in-edges (needs node_list)
 cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s);
+// lane-per-edge CTA-per-(node, head) variant for 32-channel heads and rows OUTSIDE the dense tiles (no init state)
+bool attn_csr_vrows_supported(int H, int C);
+cudaError_t launch_attn_csr_vrows(const AttnCsrArgs& a, cudaStream_t s);
 
 // alpha[eid[p], h] = exp(scores[p,h] - max) / (sum + 1e-16)
 cudaError_t launch_alpha_normalize(const float* scores, const float* stats, const int32_t* rowptr,
@@ -260,6 +263,10 @@ struct DensePlan {
   int32_t* x_slot = nullptr;       // [n_extra] device: destination image row (tile * 128 + r)
   int64_t n_promoted_edges = 0;
   int32_t* light_nf = nullptr; int n_light_nf = 0, n_light_nf_real = 0;
+  // true when no row handled by the CSR kernels (heavy rows, un-fused light rows) lies inside a dense tile: those
+  // kernels then neither read the dense kernel's (acc, stats) nor race with its output rows, and can run next to it
+  bool csr_rows_independent = false;
+  int32_t* csr_rows = nullptr; int n_csr_rows = 0, n_csr_rows_real = 0;   // heavy rows then un-fused light rows, one list
   // per 128-row tile of the node index space: bit 0 = a row has residual in-edges (its fp32 Q is read),
   // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
   uint8_t* f32_tile_flags[2] = {nullptr, nullptr};

@@ -77,7 +77,7 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 
 void free_plan(DensePlan* p, cudaStream_t s) {
   if (!p) return;
-  tmp_free(p->tiles, s); tmp_free(p->node_slot, s); tmp_free(p->bitmap, s); tmp_free(p->light, s); tmp_free(p->heavy, s); tmp_free(p->row_fused, s); tmp_free(p->light_nf, s); tmp_free(p->x_src, s); tmp_free(p->x_slot, s); tmp_free(p->f32_tile_flags[0], s); tmp_free(p->f32_tile_flags[1], s);
+  tmp_free(p->tiles, s); tmp_free(p->node_slot, s); tmp_free(p->bitmap, s); tmp_free(p->light, s); tmp_free(p->heavy, s); tmp_free(p->row_fused, s); tmp_free(p->light_nf, s); tmp_free(p->csr_rows, s); tmp_free(p->x_src, s); tmp_free(p->x_slot, s); tmp_free(p->f32_tile_flags[0], s); tmp_free(p->f32_tile_flags[1], s);
   free_csr(&p->residual, s);
   *p = DensePlan();
 }
@@ -295,6 +295,18 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
       plan->n_light_nf_real = (int)light_nf.size();
     }
     plan->n_light = (int)light.size(); plan->n_heavy = (int)heavy.size(); plan->n_light_nf = (int)light_nf.size();
+    plan->csr_rows_independent = true;
+    for (int32_t i : heavy) if (node_slot[i] >= 0) plan->csr_rows_independent = false;
+    for (int32_t i : light_nf) if (node_slot[i] >= 0) plan->csr_rows_independent = false;
+    {
+      std::vector<int32_t> rows(heavy);   // long rows first
+      rows.insert(rows.end(), light_nf.begin(), light_nf.end());
+      plan->n_csr_rows = (int)rows.size();
+      plan->n_csr_rows_real = 0;
+      for (int32_t i : rows) if (i < num_real) plan->n_csr_rows_real++;
+      DA_TRY(tmp_alloc(&plan->csr_rows, sizeof(int32_t) * (rows.size() + 1), s));
+      DA_TRY(copy_sync(plan->csr_rows, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice, s));
+    }
     DA_TRY(tmp_alloc(&plan->row_fused, fused.size() + 1, s));
     DA_TRY(copy_sync(plan->row_fused, fused.data(), fused.size(), cudaMemcpyHostToDevice, s));
     DA_TRY(tmp_alloc(&plan->light_nf, sizeof(int32_t) * (light_nf.size() + 1), s));
