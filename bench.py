@@ -153,6 +153,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version / debug lines to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     w = WORKLOADS[args.workload]
     from diffassemble_b200 import _cabi, sharding
@@ -290,11 +292,14 @@ def run_b200(args):
         "qkvs_gemm_mid": gemm_entry(Mt, 4 * hid, hid, 4),
         "qkvs_gemm_last": gemm_entry(Mt, 4 * D, hid, 4),
         "head_gemm": gemm_entry(M, 32, D, 4),
-        "pack_hidden": {"flops": 0.0, "bytes": 4.0 * M * 3 * hid * 2, "bound": "hbm"},
-        "pack_last": {"flops": 0.0, "bytes": 4.0 * M * 3 * D * 2, "bound": "hbm"},
+        # tcgen05 GEMM mode: these tags are the per-layer gather of the promoted extra sources (16 per graph at c3,
+        # K and V rows read in fp32 and written as split bf16); exact-fp32 mode: the full image repack
+        "pack_hidden": {"flops": 0.0, "bytes": (8.0 * 16 * w["B"] * 2 * hid) if args.gemm != "fp32" else 4.0 * M * 3 * hid * 2, "bound": "hbm"},
+        "pack_last": {"flops": 0.0, "bytes": (8.0 * 16 * w["B"] * 2 * D) if args.gemm != "fp32" else 4.0 * M * 3 * D * 2, "bound": "hbm"},
         # edge FLOPs of the reference formulation (2C for the score + 2C for the aggregate, per edge and head)
-        "attn_dense_hidden": {"flops": 4.0 * E_dense * hid, "bytes": 4.0 * M * hid * 4 + 8.0 * M * 8, "bound": "tensor"},
-        "attn_dense_last": {"flops": 4.0 * E_dense * D, "bytes": 4.0 * M * D * 4 + 8.0 * M * 8, "bound": "tensor"},
+        # HBM bytes: Q / K / V operand images + skip (+ trunk residual on the last layer) in, output planes out
+        "attn_dense_hidden": {"flops": 4.0 * E_dense * hid, "bytes": 4.0 * M * hid * 5, "bound": "tensor"},
+        "attn_dense_last": {"flops": 4.0 * E_dense * D, "bytes": 4.0 * M * D * 6, "bound": "tensor"},
         "attn_hidden": {"flops": 4.0 * (E_csr if E_dense else E_tot) * hid,
                         "bytes": 4.0 * Mt * hid * 4 + 4.0 * (E_csr if E_dense else E_tot) * (2 * hid + 1), "bound": "hbm"},
         "attn_last": {"flops": 4.0 * (E_csr if E_dense else E_tot) * D,
@@ -309,7 +314,7 @@ def run_b200(args):
         w_ = work[name]
         nl = layers_of.get(name, 1)
         ms_step = v["ms"] / nprof
-        ms_layer = ms_step / nl          # attn_hidden / attn_last are two launches (heavy + light rows) per layer
+        ms_layer = ms_step / nl          # (attn_hidden: rows outside the dense tiles, on a side stream NEXT TO the dense kernel)
         ent = {"ms_per_launch": round(v["ms"] / v["launches"], 4), "launches_per_step": v["launches"] / nprof,
                "ms_per_step": round(ms_step, 4), "share_of_step": round(ms_step / step_ms_prof, 4), "bound": w_["bound"]}
         if w_["bound"] == "tensor":
