@@ -18,6 +18,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -477,6 +478,10 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
               out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows,
               out.img_node_slot ? out.f32_tile_flags : nullptr};
   if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
+  // short-K GEMMs (K <= 256) are bound by the L2 -> SM operand traffic (a 128 x 128 tile loads 256 KB of split-bf16
+  // operands for 2.7 us of MMAs): 256-wide tiles re-use the A block twice as often
+  static const bool wide = !(getenv("DA_GEMM_BN256") && getenv("DA_GEMM_BN256")[0] == '0');
+  if (wide && N % 256 == 0 && K <= 256 && M >= 4096) return launch_bn<256>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
   return launch_bn<32>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);

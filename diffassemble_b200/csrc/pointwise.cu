@@ -13,7 +13,7 @@ namespace {
 //   here: h = act(P + W1[:, Dv:Dv+64] @ [pos(32), temb(32)]) with P = feats @ W1[:, :Dv]^T + b1
 //   hoisted out of the step loop by da_set_features (it does not depend on x or t).
 // ---------------------------------------------------------------------------------------------
-constexpr int PRO_NB = 32;     // nodes per CTA
+constexpr int PRO_NB = 64;     // nodes per CTA
 constexpr int PRO_NT = 256;
 
 __global__ void __launch_bounds__(PRO_NT)
@@ -21,15 +21,15 @@ prologue_kernel(PrologueArgs a) {
   extern __shared__ __align__(16) float pro_sm[];   // w1pt_T [64][Hm] staged once per CTA
   __shared__ float xs[PRO_NB][8];
   __shared__ float hid[PRO_NB][16];
-  __shared__ float f64[PRO_NB][64];
+  __shared__ __align__(16) float f64t[64][PRO_NB];   // the 64 pose + time features, TRANSPOSED: [feature][node]
   __shared__ int ts[PRO_NB];
   const int tid = threadIdx.x;
   const int node0 = blockIdx.x * PRO_NB;
   const int Hm = a.Hm;
   for (int i = tid * 4; i < 64 * Hm; i += PRO_NT * 4)
     *reinterpret_cast<float4*>(pro_sm + i) = __ldg(reinterpret_cast<const float4*>(a.w1pt_T + i));
-  {
-    int nb = tid / 8, c = tid % 8, node = node0 + nb;   // PRO_NB * 8 == PRO_NT
+  for (int idx = tid; idx < PRO_NB * 8; idx += PRO_NT) {
+    const int nb = idx / 8, c = idx % 8, node = node0 + nb;
     xs[nb][c] = (node < a.M && c < a.C_in) ? a.x[(size_t)node * a.C_in + c] : 0.f;
     if (c == 0) {
       int tt = a.t_uniform;
@@ -50,27 +50,30 @@ prologue_kernel(PrologueArgs a) {
     float s = a.pos_b2[v];
 #pragma unroll
     for (int u = 0; u < 16; ++u) s = fmaf(a.pos_w2[v * 16 + u], hid[nb][u], s);
-    f64[nb][v] = s;
-    f64[nb][32 + v] = a.time_emb[(size_t)ts[nb] * 32 + v];
+    f64t[v][nb] = s;
+    f64t[32 + v][nb] = a.time_emb[(size_t)ts[nb] * 32 + v];
   }
   __syncthreads();
-  // each thread: one output column n for 4 nodes at a time (weights from smem, node features broadcast)
-  for (int idx = tid; idx < (PRO_NB / 4) * Hm; idx += PRO_NT) {
-    const int n = idx % Hm, nb0 = (idx / Hm) * 4;
-    float s[4];
+  // each thread: one output column n for 8 nodes at a time.  Per k: one weight word (lanes = consecutive columns)
+  // and two broadcast float4 of node features for 8 FMAs -- the loop is FMA-issue bound, not shared-memory bound.
+  for (int idx = tid; idx < (PRO_NB / 8) * Hm; idx += PRO_NT) {
+    const int n = idx % Hm, nb0 = (idx / Hm) * 8;
+    float s[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int node = node0 + nb0 + q;
-      s[q] = (a.P && node < a.M) ? a.P[(size_t)node * Hm + n] : a.b1[n];
+      s[q] = (a.P && node < a.M) ? __ldg(a.P + (size_t)node * Hm + n) : a.b1[n];
     }
 #pragma unroll 8
     for (int k = 0; k < 64; ++k) {
       const float w = pro_sm[k * Hm + n];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) s[q] = fmaf(w, f64[nb0 + q][k], s[q]);
+      const float4 f0 = *reinterpret_cast<const float4*>(&f64t[k][nb0]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&f64t[k][nb0 + 4]);
+      s[0] = fmaf(w, f0.x, s[0]); s[1] = fmaf(w, f0.y, s[1]); s[2] = fmaf(w, f0.z, s[2]); s[3] = fmaf(w, f0.w, s[3]);
+      s[4] = fmaf(w, f1.x, s[4]); s[5] = fmaf(w, f1.y, s[5]); s[6] = fmaf(w, f1.z, s[6]); s[7] = fmaf(w, f1.w, s[7]);
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int node = node0 + nb0 + q;
       if (node >= a.M) continue;
       const float v = apply_act_rt(s[q], a.act);
@@ -211,7 +214,7 @@ cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
   if (a.C_in > 8) return cudaErrorInvalidValue;
   const size_t smem = (size_t)64 * a.Hm * sizeof(float);
   static size_t smem_set = 0;
-  if (smem > 48 * 1024 - 12 * 1024 && smem > smem_set) {
+  if (smem > smem_set) {   // static (23 KB) + dynamic shared memory exceeds the 48 KB default
     cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
