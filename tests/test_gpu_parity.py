@@ -512,3 +512,34 @@ def test_prefetch_double_buffering_matches_plain_path():
     for k, (a, bb) in enumerate(zip(got, want)):
         assert torch.equal(a, bb), k
     assert mod.model._spare is not None and mod.model._engine is not mod.model._spare
+
+
+@pytest.mark.parametrize("sizes,C", [([128, 256], 32), ([128, 130, 64], 144), ([384], 32), ([250, 6, 128], 24)])
+def test_dense_tiles_full_and_partial_with_residual_mix(sizes, C):
+    """Full 128-row tiles (no padding rows: nothing can be promoted), partial tiles, and rows with 0..6 residual
+    in-edges (cross-graph sources, duplicates) in the SAME tile: rows finalised by the dense kernel and rows that
+    go through (acc, stats) + the CSR continuation must both match the edge-list formulation."""
+    from diffassemble_b200 import op_graph_attention_dense
+    from oracle.transformer_conv import segment_softmax
+
+    H = 8
+    g = torch.Generator().manual_seed(sum(sizes) + C)
+    n = sum(sizes)
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    parts, off = [], 0
+    for sz in sizes:
+        m = torch.rand(sz, sz, generator=g) < 0.5
+        parts.append(m.nonzero().t() + off)
+        off += sz
+    extra = torch.randint(0, n, (2, 2 * n), generator=g)               # ~2 extra in-edges per row on average
+    dup = parts[0][:, torch.randperm(parts[0].shape[1], generator=g)[: n]]   # second copies of in-graph edges
+    ei = torch.cat(parts + [extra, dup, dup[:, : n // 2]], 1)          # some edges appear three times
+    ei = ei[:, torch.randperm(ei.shape[1], generator=g)]
+    qkvs = torch.randn(n, 4 * H * C, generator=g)
+    q, k, v, s = [t.reshape(n, H, C) for t in qkvs.double().split(H * C, dim=1)]
+    a = (q[ei[1]] * k[ei[0]]).sum(-1) / C ** 0.5
+    alpha = segment_softmax(a, ei[1], n)
+    ref = (torch.zeros(n, H, C, dtype=torch.float64).index_add_(0, ei[1], v[ei[0]] * alpha[..., None]) + s).reshape(n, H * C)
+    y, n_dense = op_graph_attention_dense(qkvs.to(DEV), ei.to(DEV), batch.to(DEV), H)
+    assert n_dense > 0
+    assert rel_err(y, ref) < 2e-5
