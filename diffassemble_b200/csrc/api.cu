@@ -276,7 +276,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       if (vrows) {
         if (h->plan.n_csr_rows > 0) {
           AttnCsrArgs vr = hv;
-          vr.node_list = h->plan.csr_rows; vr.n_targets = h->plan.n_csr_rows;
+          vr.node_list = h->plan.csr_rows; vr.n_targets = h->plan.n_csr_rows; vr.n_coop = h->plan.n_heavy;   // hubs first
           vr.init_acc = nullptr; vr.init_stats = nullptr; vr.init_slot = nullptr;
           Scoped sc(h, st, TAG_ATTN_HIDDEN);
           e = launch_attn_csr_vrows(vr, st);
@@ -303,10 +303,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
         DA_CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "side stream");
         DA_CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "side stream");
       }
-      DA_CK(cudaEventRecord(h->ev_fork, s), "fork");
-      DA_CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork");
-      DA_CK(launch_rows(h->side), "graph attention (rows outside the dense tiles)");
-      DA_CK(cudaEventRecord(h->ev_join, h->side), "join");
+      DA_CK(cudaEventRecord(h->ev_fork, s), "fork");   // the GEMM (and the gather) of this layer
     }
     if (dense) {
       AttnDenseArgs da_{};
@@ -324,6 +321,11 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       }
       Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
       DA_CK(launch_attn_dense(da_, s), "dense attention");
+    }
+    if (side_rows) {   // launched AFTER the dense kernel so that its CTAs fill the slots the dense grid leaves in its tail
+      DA_CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork");
+      DA_CK(launch_rows(h->side), "graph attention (rows outside the dense tiles)");
+      DA_CK(cudaEventRecord(h->ev_join, h->side), "join");
     }
     if (side_rows) {
       DA_CK(cudaStreamWaitEvent(s, h->ev_join, 0), "join");

@@ -301,10 +301,13 @@ __device__ __forceinline__ void load_row32(const float* __restrict__ fp32_row, c
   }
 }
 
+// Launch shape: the first n_coop rows of node_list (hubs with hundreds of in-edges) get one CTA per (row, head), its
+// 8 warps sharing the edge list; the remaining rows (a handful of in-edges) get one WARP per (row, head), 8 pairs
+// per CTA -- 224 instead of 1792 CTAs for the light virtual rows of the c3 batch.
 __global__ void __launch_bounds__(VROW_WARPS * 32)
 attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __restrict__ rowptr,
                        const int32_t* __restrict__ col, const float* __restrict__ weight,
-                       const int32_t* __restrict__ node_list, int H, float scale,
+                       const int32_t* __restrict__ node_list, int n_rows, int n_coop, int H, float scale,
                        const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                        __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
                        const int32_t* __restrict__ img_slot, const __nv_bfloat16* __restrict__ kimg,
@@ -313,8 +316,12 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
   __shared__ float acc_s[VROW_WARPS][C];
   __shared__ float m_s[VROW_WARPS], l_s[VROW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int node = node_list[blockIdx.x / H], head = blockIdx.x % H;
+  const bool coop = (int)blockIdx.x < n_coop * H;
+  int pair = coop ? (int)blockIdx.x : n_coop * H + ((int)blockIdx.x - n_coop * H) * VROW_WARPS + warp;
+  if (pair >= n_rows * H) return;   // (warp mode only: whole warps leave, no barrier follows for them)
+  const int node = node_list[pair / H], head = pair % H;
   const int HC = H * C;
+  const int wstart = coop ? warp : 0, wstep = coop ? VROW_WARPS : 1;
   float q[C];
   {
     const float* qrow = qkvs + (size_t)node * ld + head * C;
@@ -327,7 +334,7 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
   const int beg = rowptr[node], end = rowptr[node + 1];
   const size_t lo_off = (size_t)64 * Cpad;
   float m = -INFINITY, l = 0.f, acc = 0.f;   // acc: channel `lane` of this warp's partial sum
-  for (int base = beg + warp * 32; base < end; base += 32 * VROW_WARPS) {
+  for (int base = beg + wstart * 32; base < end; base += 32 * wstep) {
     const int e = base + lane;
     const bool valid = e < end;
     const int j = valid ? col[e] : node;
@@ -365,18 +372,24 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
     }
     acc = fmaf(acc, rescale, vf[0]);
   }
-  if (lane == 0) { m_s[warp] = m; l_s[warp] = l; }
-  acc_s[warp][lane] = acc;
-  __syncthreads();
-  if (warp != 0) return;
-  const float mw = lane < VROW_WARPS ? m_s[lane] : -INFINITY, lw = lane < VROW_WARPS ? l_s[lane] : 0.f;
-  const float M = warp_max(mw);
-  const float fw = (mw == -INFINITY) ? 0.f : expf(mw - M);
-  const float L = warp_sum(lw * fw);
-  const float inv = 1.f / (L + 1e-16f);
-  float a = 0.f;
+  float a, inv;
+  if (coop) {   // merge the 8 partial states of this (row, head)
+    if (lane == 0) { m_s[warp] = m; l_s[warp] = l; }
+    acc_s[warp][lane] = acc;
+    __syncthreads();
+    if (warp != 0) return;
+    const float mw = lane < VROW_WARPS ? m_s[lane] : -INFINITY, lw = lane < VROW_WARPS ? l_s[lane] : 0.f;
+    const float M = warp_max(mw);
+    const float fw = (mw == -INFINITY) ? 0.f : expf(mw - M);
+    const float L = warp_sum(lw * fw);
+    inv = 1.f / (L + 1e-16f);
+    a = 0.f;
 #pragma unroll
-  for (int w2 = 0; w2 < VROW_WARPS; ++w2) a = fmaf(acc_s[w2][lane], __shfl_sync(0xffffffffu, fw, w2), a);
+    for (int w2 = 0; w2 < VROW_WARPS; ++w2) a = fmaf(acc_s[w2][lane], __shfl_sync(0xffffffffu, fw, w2), a);
+  } else {
+    a = acc;
+    inv = 1.f / (l + 1e-16f);
+  }
   float v = a * inv + __ldg(qkvs + (size_t)node * ld + 3 * HC + head * C + lane);
   if (resid) v += resid[(size_t)node * ld_resid + head * C + lane];
   v = apply_act_rt(v, act);
@@ -538,8 +551,11 @@ cudaError_t launch_attn_csr_vrows(const AttnCsrArgs& a, cudaStream_t s) {
   if (!a.node_list || a.scores || a.stats || a.init_acc || a.C != 32 || (a.ld & 3)) return cudaErrorInvalidValue;
   if (a.img_slot != nullptr && (a.kimg == nullptr || a.vimg == nullptr || a.img_Cpad != 32)) return cudaErrorInvalidValue;
   const float scale = 1.0f / sqrtf((float)a.C);
-  attn_csr_vrow32_kernel<<<(unsigned)a.n_targets * a.H, VROW_WARPS * 32, 0, s>>>(
-      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.H, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc,
+  const int n_coop = a.n_coop < a.n_targets ? a.n_coop : a.n_targets;
+  const int light_pairs = (a.n_targets - n_coop) * a.H;
+  const unsigned grid = (unsigned)(n_coop * a.H + (light_pairs + VROW_WARPS - 1) / VROW_WARPS);
+  attn_csr_vrow32_kernel<<<grid, VROW_WARPS * 32, 0, s>>>(
+      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, n_coop, a.H, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc,
       a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad);
   return cudaGetLastError();
 }

@@ -92,6 +92,7 @@ struct AttnCsrArgs {
   const float* init_stats;    // [n, H, 2] (m, l)
   const int32_t* init_slot;   // [n] >= 0 where the init state is valid
   const int32_t* node_list;   // optional: the n_targets target ids to process (null = 0 .. n_targets-1)
+  int n_coop = 0;             // launch_attn_csr_vrows: the first n_coop rows of node_list get a whole CTA per head
   // heavy-row kernel only: sources with img_slot[j] >= 0 are read from the split-bf16 K / V operand images
   // (hi + lo) instead of the fp32 row, so the GEMM can skip the fp32 K / V stores of dense-tile rows
   const int32_t* img_slot = nullptr;

@@ -54,34 +54,46 @@ prologue_kernel(PrologueArgs a) {
     f64t[32 + v][nb] = a.time_emb[(size_t)ts[nb] * 32 + v];
   }
   __syncthreads();
-  // each thread: one output column n for 8 nodes at a time.  Per k: one weight word (lanes = consecutive columns)
-  // and two broadcast float4 of node features for 8 FMAs -- the loop is FMA-issue bound, not shared-memory bound.
-  for (int idx = tid; idx < (PRO_NB / 8) * Hm; idx += PRO_NT) {
-    const int n = idx % Hm, nb0 = (idx / Hm) * 8;
-    float s[8];
+  // each thread: TWO output columns (n, n + Hm/2) for 8 nodes at a time.  Per k: two weight words (lanes = consecutive
+  // columns) and two broadcast float4 of node features for 16 FMAs -- the loop is FMA-issue bound.
+  const int Hh = Hm >> 1;
+  for (int idx = tid; idx < (PRO_NB / 8) * Hh; idx += PRO_NT) {
+    const int n = idx % Hh, nb0 = (idx / Hh) * 8;
+    float s0[8], s1[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int node = node0 + nb0 + q;
-      s[q] = (a.P && node < a.M) ? __ldg(a.P + (size_t)node * Hm + n) : a.b1[n];
+      const bool ok = a.P && node < a.M;
+      s0[q] = ok ? __ldg(a.P + (size_t)node * Hm + n) : a.b1[n];
+      s1[q] = ok ? __ldg(a.P + (size_t)node * Hm + n + Hh) : a.b1[n + Hh];
     }
+    const float* wp = pro_sm + n;
+    const float* fp = &f64t[0][nb0];
 #pragma unroll 8
     for (int k = 0; k < 64; ++k) {
-      const float w = pro_sm[k * Hm + n];
-      const float4 f0 = *reinterpret_cast<const float4*>(&f64t[k][nb0]);
-      const float4 f1 = *reinterpret_cast<const float4*>(&f64t[k][nb0 + 4]);
-      s[0] = fmaf(w, f0.x, s[0]); s[1] = fmaf(w, f0.y, s[1]); s[2] = fmaf(w, f0.z, s[2]); s[3] = fmaf(w, f0.w, s[3]);
-      s[4] = fmaf(w, f1.x, s[4]); s[5] = fmaf(w, f1.y, s[5]); s[6] = fmaf(w, f1.z, s[6]); s[7] = fmaf(w, f1.w, s[7]);
+      const float w0 = wp[0], w1 = wp[Hh];
+      const float4 f0 = *reinterpret_cast<const float4*>(fp);
+      const float4 f1 = *reinterpret_cast<const float4*>(fp + 4);
+      wp += Hm; fp += PRO_NB;
+      s0[0] = fmaf(w0, f0.x, s0[0]); s0[1] = fmaf(w0, f0.y, s0[1]); s0[2] = fmaf(w0, f0.z, s0[2]); s0[3] = fmaf(w0, f0.w, s0[3]);
+      s0[4] = fmaf(w0, f1.x, s0[4]); s0[5] = fmaf(w0, f1.y, s0[5]); s0[6] = fmaf(w0, f1.z, s0[6]); s0[7] = fmaf(w0, f1.w, s0[7]);
+      s1[0] = fmaf(w1, f0.x, s1[0]); s1[1] = fmaf(w1, f0.y, s1[1]); s1[2] = fmaf(w1, f0.z, s1[2]); s1[3] = fmaf(w1, f0.w, s1[3]);
+      s1[4] = fmaf(w1, f1.x, s1[4]); s1[5] = fmaf(w1, f1.y, s1[5]); s1[6] = fmaf(w1, f1.z, s1[6]); s1[7] = fmaf(w1, f1.w, s1[7]);
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int node = node0 + nb0 + q;
       if (node >= a.M) continue;
-      const float v = apply_act_rt(s[q], a.act);
-      if (a.out.f32) a.out.f32[(size_t)node * a.out.ldc + n] = v;
-      if (a.out.hi) {
-        __nv_bfloat16 h = __float2bfloat16_rn(v);
-        a.out.hi[(size_t)node * a.out.ld_split + n] = h;
-        a.out.lo[(size_t)node * a.out.ld_split + n] = __float2bfloat16_rn(v - __bfloat162float(h));
+#pragma unroll
+      for (int hsel = 0; hsel < 2; ++hsel) {
+        const int col = n + hsel * Hh;
+        const float v = apply_act_rt(hsel ? s1[q] : s0[q], a.act);
+        if (a.out.f32) a.out.f32[(size_t)node * a.out.ldc + col] = v;
+        if (a.out.hi) {
+          __nv_bfloat16 h = __float2bfloat16_rn(v);
+          a.out.hi[(size_t)node * a.out.ld_split + col] = h;
+          a.out.lo[(size_t)node * a.out.ld_split + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
       }
     }
   }
