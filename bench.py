@@ -278,7 +278,8 @@ def run_b200(args):
     E_tot = eng.num_edges
     E_dense, E_csr = stats["dense_edges"], stats["csr_edges"]
     hid, D, Hm = 256, 1152, 128
-    step_ms_prof = sum(v["ms"] for v in prof.values()) / nprof
+    overlapped = {"attn_hidden"} if (stats["dense_edges"] and args.attn == "auto") else set()
+    step_ms_prof = sum(v["ms"] for k, v in prof.items() if k not in overlapped) / nprof
     passes = 3 if args.gemm == "bf16x3" else 1
 
     def gemm_entry(Mg, N, K, out_bytes_per_elt):
@@ -325,8 +326,12 @@ def run_b200(args):
             ent["peak"], ent["unit"] = pk["hbm"], "GB/s"
         ent["frac"] = ent["achieved"] / ent["peak"]
         ent["hbm_gbs_algorithmic"] = w_["bytes"] / (ms_layer * 1e-3) / 1e9
+        if name == "attn_hidden" and E_dense and args.attn == "auto":
+            # rows outside the dense tiles (virtual nodes): launched on a side stream NEXT TO the dense kernel of the same
+            # layer, so this span overlaps attn_dense_hidden and is not part of the critical path
+            ent["overlapped_with"] = "attn_dense_hidden"
         kernels[name] = ent
-    dom_name = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    dom_name = max((k for k in kernels if "overlapped_with" not in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom_name]
     roof = {"bound": dk["bound"], "kernel": dom_name, "achieved": dk["achieved"], "peak": dk["peak"], "unit": dk["unit"],
             "frac": dk["frac"], "traffic": None,
