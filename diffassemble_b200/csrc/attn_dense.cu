@@ -1,24 +1,29 @@
-// Masked dense graph attention on tcgen05 tensor cores (attn_mode = DA_ATTN_AUTO).
+// Masked dense graph attention on tcgen05 tensor cores (attn_mode = DA_ATTN_AUTO), with the layer epilogue fused.
 //
 // For the graphs selected by the planner (plan.cu) the TransformerConv message/softmax/aggregate
 // stage is evaluated as flash-style tiled attention restricted by the
 // graph's adjacency bitmap:
 //     S = Q K^T               128 targets x 64 sources per tile, fp32 accumulators in TMEM
-//     P = exp(scale*S - m)    only where bitmap(i, j) = 1 (online running max / sum per target row)
-//     O += P V                fp32 accumulator in TMEM, rescaled when the running max moves
+//     P = exp(scale*S - m)    only where bitmap(i, j) = 1 (online running reference point / sum per target row)
+//     O += P V                fp32 accumulator in TMEM, rescaled when the reference point moves
 // Both products use the 3-pass split-bf16 scheme of gemm_umma.cu (hi*hi + hi*lo + lo*hi) so the
-// result stays within ~1e-5 of fp32.  The operands come from "images" written by pack_images_kernel:
-// per (tile, head) contiguous blocks already in the canonical no-swizzle K-major core-matrix layout
-// of tcgen05.mma (8 rows x 16 bytes per core matrix), so a K or V^T block is ONE cp.async.bulk.
+// result stays within ~1e-5 of fp32.  The operands come from "images" written by the QKVS GEMM's epilogue
+// (pack_images_kernel in exact-fp32 mode): per (tile, head) contiguous blocks already in the canonical
+// no-swizzle K-major core-matrix layout of tcgen05.mma (8 rows x 16 bytes per core matrix), so a K or V
+// block is ONE cp.async.bulk.  The planner's promoted residual edges are bitmap bits on extra columns whose
+// K / V rows gather_extra_kernel copies into the padding rows of the images.
 //
 // CTA = (128-row target tile, head).  Warp roles:
-//   warp 0     bulk-copy producer (Q image once, then K / V^T blocks through mbarrier rings)
+//   warp 0     bulk-copy producer (K / V blocks through mbarrier rings)
 //   warp 1     TMEM allocation, single-thread tcgen05.mma issue (S_{j+1} is issued before P_j V_j
 //              so the tensor core works while the softmax warps are busy)
 //   warps 2-5  softmax: thread == target row (TMEM lane), so the row max / sum need no shuffles;
-//              two passes over the S tile in TMEM (max, then exp + P store), O correction in TMEM
-// The un-normalised O and the (m, l) statistics go to global memory; attn_csr.cu then continues the
-// same online softmax over the residual edges and applies skip / residual / activation.
+//              Q parked in TMEM once, one pass over each S tile, P written back into the S columns;
+//              then the epilogue: O / l + skip (+ trunk residual) -> activation -> bf16 hi / lo split.
+//              skip / residual rows arrive as swizzled TMA boxes in ring stages that have gone idle,
+//              full tiles leave through TMA tensor stores.
+// Rows the kernel cannot finalise (more than DA_FUSE_MAX_RESIDUAL residual in-edges) get their un-normalised O and
+// (m, l) written to global memory instead; attn_csr.cu continues the same online softmax for them.
 #include <cuda.h>
 
 #include <cstring>
