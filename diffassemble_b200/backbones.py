@@ -344,8 +344,14 @@ class Eff_GAT_3d(nn.Module, _EngineMixin):
             raise NotImplementedError("only the 3 + 3 (translation, axis-angle) head is built")
         if backbone not in self.FEAT_DIM:
             raise Exception(f"Backbone not implemented {backbone}")
-        self.pcd_backbone = None
         feat_dim = self.FEAT_DIM[backbone]
+        # efficient_gat_3d.py:77-79: the plain PointNet encoder runs on the CUDA operators (pointnet.py, scope row N4);
+        # the other encoders (vn_dgcnn, pointnet_plus ...) stay upstream: attach one or pass pcd_feats
+        self.pcd_backbone = None
+        if backbone == "pointnet":
+            from .pointnet import PointNet
+
+            self.pcd_backbone = PointNet(feat_dim=feat_dim)
         self.combined_features_dim = feat_dim + 32 + 32
         self.gnn_feat_dim = self.combined_features_dim
         self.input_channels = input_channels

@@ -899,6 +899,12 @@ int da_op_linear_wgrad(const float* dy, const float* x, float* dw, float* db, in
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+int da_op_segment_max(const float* x, int32_t ld, const int32_t* seg_ptr, int32_t n_seg, int32_t cols, float* out, void* stream) {
+  if (!x || !seg_ptr || !out || n_seg < 0 || cols <= 0 || ld < cols) return DA_ERR_INVALID;
+  cudaError_t ce = launch_segment_max(x, ld, seg_ptr, n_seg, cols, out, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

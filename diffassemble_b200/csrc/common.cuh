@@ -9,7 +9,7 @@
 
 namespace da {
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_RELU = 3 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() / F.gelu default = exact erf form (efficient_gat.py:89,95,100; Transformer_GNN.py:36)
@@ -21,11 +21,13 @@ template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   if (ACT == ACT_GELU) return gelu_erf(x);
   if (ACT == ACT_LRELU) return lrelu02(x);
+  if (ACT == ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
 __device__ __forceinline__ float apply_act_rt(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
   if (act == ACT_LRELU) return lrelu02(x);
+  if (act == ACT_RELU) return fmaxf(x, 0.f);
   return x;
 }
 
@@ -211,6 +213,9 @@ cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, floa
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);
+// out[g, c] = max over rows seg_ptr[g] .. seg_ptr[g + 1] of x[row, c] (PointNet's global max pool, pointnet.py:40)
+cudaError_t launch_segment_max(const float* x, int ld, const int32_t* seg_ptr, int n_seg, int cols, float* out,
+                               cudaStream_t s);
 
 }  // namespace da
 

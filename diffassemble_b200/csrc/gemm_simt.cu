@@ -164,6 +164,7 @@ cudaError_t launch_linear_simt(const float* a, int lda, const float* w, int ldw,
     case ACT_NONE: DA_LAUNCH(ACT_NONE); break;
     case ACT_GELU: DA_LAUNCH(ACT_GELU); break;
     case ACT_LRELU: DA_LAUNCH(ACT_LRELU); break;
+    case ACT_RELU: DA_LAUNCH(ACT_RELU); break;
     default: return cudaErrorInvalidValue;
   }
 #undef DA_LAUNCH

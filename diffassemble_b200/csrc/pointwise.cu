@@ -260,6 +260,36 @@ cudaError_t launch_sampler_update(const float* x_in, const float* model_out, flo
   return cudaGetLastError();
 }
 
+namespace {
+// one CTA per segment; threadIdx.x strides the columns (coalesced row reads), threadIdx.y strides the rows
+__global__ void segment_max_kernel(const float* __restrict__ x, int ld, const int32_t* __restrict__ seg_ptr, int cols,
+                                   float* __restrict__ out) {
+  __shared__ float part[8][128];
+  const int g = blockIdx.x, beg = seg_ptr[g], end = seg_ptr[g + 1];
+  for (int c0 = 0; c0 < cols; c0 += 128) {
+    const int c = c0 + threadIdx.x;
+    float m = -INFINITY;
+    if (c < cols)
+      for (int r = beg + threadIdx.y; r < end; r += 8) m = fmaxf(m, __ldg(x + (size_t)r * ld + c));
+    part[threadIdx.y][threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+#pragma unroll
+      for (int y = 1; y < 8; ++y) m = fmaxf(m, part[y][threadIdx.x]);
+      out[(size_t)g * cols + c] = m;
+    }
+    __syncthreads();
+  }
+}
+}  // namespace
+
+cudaError_t launch_segment_max(const float* x, int ld, const int32_t* seg_ptr, int n_seg, int cols, float* out,
+                               cudaStream_t s) {
+  if (n_seg <= 0 || cols <= 0) return cudaSuccess;
+  segment_max_kernel<<<n_seg, dim3(128, 8), 0, s>>>(x, ld, seg_ptr, cols, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s) {
   size_t total = (size_t)rows * cols;

@@ -201,6 +201,21 @@ def op_linear(a, w, bias=None, act=0, mode="fp32"):
     return y
 
 
+def op_segment_max(x, seg_ptr):
+    """``out[g] = x[seg_ptr[g]:seg_ptr[g + 1]].max(0)`` on the device (PointNet's global max pool)."""
+    lib = _cabi.load_library()
+    _require_cuda(x, "x")
+    x = x.float().contiguous()
+    sp = seg_ptr.to(device=x.device, dtype=torch.int32).contiguous()
+    n_seg = sp.numel() - 1
+    out = torch.empty((n_seg, x.shape[1]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = lib.da_op_segment_max(_ptr(x), x.shape[1], _ptr(sp), n_seg, x.shape[1], _ptr(out), _stream(x.device))
+    if st != _cabi.DA_OK:
+        raise DiffAssembleError(st, "da_op_segment_max failed")
+    return out
+
+
 def op_graph_attention(qkvs, edge_index, heads, return_alpha=False):
     lib = _cabi.load_library()
     _require_cuda(qkvs, "qkvs")

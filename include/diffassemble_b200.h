@@ -186,10 +186,15 @@ int da_get_profile(da_handle* h, double* ms_out, int64_t* launches_out, int32_t 
 const char* da_profile_tag_name(int32_t i);
 
 /* Stand-alone operator entry points (unit-level parity tests and micro-benchmarks).
- * y[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]); act: 0 none, 1 GELU(erf), 2 LeakyReLU(0.2).
+ * y[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]); act: 0 none, 1 GELU(erf), 2 LeakyReLU(0.2), 3 ReLU.
  * mode = DA_GEMM_*; all pointers device fp32. */
 int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y,
                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* Segment-wise column maximum: out[g, c] = max_{seg_ptr[g] <= r < seg_ptr[g+1]} x[r, c]  (x fp32 [rows, ld], out fp32
+ * [n_seg, cols]).  The global max pool of the PointNet fragment encoder (puzzle_diff/model/backbones/pointnet.py:39-40),
+ * scope row N4; the point-wise layers of that encoder are da_op_linear calls with eval-mode BatchNorm folded in. */
+int da_op_segment_max(const float* x, int32_t ld, const int32_t* seg_ptr, int32_t n_seg, int32_t cols, float* out,
+                      void* stream);
 /* Same operator with caller-provided scratch (split-bf16 operand planes): no allocation, no synchronisation. */
 size_t da_op_linear_workspace_bytes(int32_t mode, int32_t M, int32_t N, int32_t K);
 int da_op_linear_ws(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,

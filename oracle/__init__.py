@@ -47,3 +47,4 @@ from .topology import (  # noqa: F401
     batch_graphs,
 )
 from .assignment import greedy_cost_assignment_ref  # noqa: F401,E402
+from .pointnet import PointNetRef  # noqa: F401,E402

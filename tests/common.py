@@ -96,3 +96,20 @@ def reseed_parameters(module, seed=0, gain=1.5, qk_gain=1.5):
                     v = v * qk_gain
             p.copy_(v.to(p.dtype))
     return module
+
+
+def pointnet_fixture_weights(module, seed):
+    """Parameters AND BatchNorm running statistics of a PointNet exactly as tests/golden/make_reference_golden.py
+    (case_pointnet) set them on the reference module."""
+    from torch import nn
+
+    reseed_parameters(module, seed, gain=1.0, qk_gain=1.0)
+    with torch.no_grad():
+        for k in range(1, 6):
+            getattr(module, f"bn{k}").weight.add_(1.0)
+        g = torch.Generator().manual_seed(4242 + seed)
+        for name, m in sorted(module.named_modules()):
+            if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                m.running_mean.copy_(0.2 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    return module

@@ -383,8 +383,45 @@ def case_training(sd2, name, sizes, architecture, virt_nodes, mean_type, kind="d
     print(f"ref_train_{name}: loss={loss.item():.6f} params with grad={len(grads)}")
 
 
+def randomize_batchnorm(module, seed=0):
+    """Non-trivial running statistics for every BatchNorm (a fresh module has mean 0 / var 1)."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    for name, m in sorted(module.named_modules()):
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.running_mean.copy_(0.2 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+    return module
+
+
+def case_pointnet():
+    """``PointNet`` fragment encoder (backbones/pointnet.py:8-43, N4) in eval mode, executed from the reference file."""
+    from common import reseed_parameters
+    from model.backbones.pointnet import PointNet
+
+    d = {}
+    for feat_dim, B, N, seed in ((128, 5, 200, 0), (128, 3, 1000, 1), (64, 2, 37, 2)):
+        torch.manual_seed(seed)
+        ref = PointNet(feat_dim=feat_dim).eval()
+        reseed_parameters(ref, seed, gain=1.0, qk_gain=1.0)
+        with torch.no_grad():
+            for k in range(1, 6):   # BatchNorm scale / shift as a trained network has them (reseed gives +-1/4 uniform)
+                getattr(ref, f"bn{k}").weight.add_(1.0)
+        randomize_batchnorm(ref, seed)
+        g = torch.Generator().manual_seed(seed + 1)
+        x = torch.randn(B, N, 3, generator=g)
+        with torch.no_grad():
+            out = ref(x)
+        d[f"{feat_dim}/{B}/{N}/{seed}"] = dict(x=x, out=out)
+    torch.save(d, HERE / "ref_pointnet.pt")
+    print("ref_pointnet:", {k: tuple(v["out"].shape) for k, v in d.items()})
+
+
 if __name__ == "__main__":
     sd2, sd3 = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "pointnet":
+        case_pointnet()
+        sys.exit(0)
+    case_pointnet()
     case_assignment(sd2)
     case_training(sd2, "dense", [36, 25], "transformer", 0, "EPSILON")
     case_training(sd2, "exph_v4", [36, 64], "exophormer", 4, "START_X", kind="expander", seed=1)

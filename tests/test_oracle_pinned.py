@@ -167,3 +167,17 @@ def test_oracle_training_loss_and_gradients_match_reference(name):
     loss.backward()
     n = check_grads({k: p.grad for k, p in ref.named_parameters()}, d["grads"], 2e-5)
     assert n >= 38
+
+
+def test_oracle_pointnet_matches_reference():
+    """N4 (3-D side): the PointNet fragment encoder against the reference class itself (eval-mode BatchNorm)."""
+    from common import pointnet_fixture_weights
+
+    d = torch.load(G / "ref_pointnet.pt")
+    for key, c in d.items():
+        feat_dim, B, N, seed = (int(v) for v in key.split("/"))
+        ref = pointnet_fixture_weights(oracle.PointNetRef(feat_dim=feat_dim).eval(), seed)
+        with torch.no_grad():
+            out = ref(c["x"])
+        assert out.shape == c["out"].shape
+        assert rel_err(out, c["out"]) < EXACT, key
