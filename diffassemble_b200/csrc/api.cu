@@ -899,6 +899,13 @@ int da_op_linear_wgrad(const float* dy, const float* x, float* dw, float* db, in
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+int da_adafactor_step(const da_adafactor_param* params, int32_t n, float eps1, float eps2, float clip_threshold,
+                      float weight_decay, void* stream) {
+  if (n < 0 || (n > 0 && !params) || clip_threshold <= 0.f) return DA_ERR_INVALID;
+  cudaError_t ce = launch_adafactor(params, n, eps1, eps2, clip_threshold, weight_decay, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_segment_max(const float* x, int32_t ld, const int32_t* seg_ptr, int32_t n_seg, int32_t cols, float* out, void* stream) {
   if (!x || !seg_ptr || !out || n_seg < 0 || cols <= 0 || ld < cols) return DA_ERR_INVALID;
   cudaError_t ce = launch_segment_max(x, ld, seg_ptr, n_seg, cols, out, (cudaStream_t)stream);

@@ -209,6 +209,8 @@ cudaError_t launch_expander_edges(const int32_t* perm, int n, int degree, int n_
 // training (scope row N1)
 cudaError_t launch_attn_backward(const float* qkvs, const float* dO, const CsrGraph& by_target, const CsrGraph& by_source,
                                  const float* stats, int n, int H, int C, float* dqkvs, float* delta, cudaStream_t s);
+cudaError_t launch_adafactor(const da_adafactor_param* params_dev, int n, float eps1, float eps2, float clip, float weight_decay,
+                             cudaStream_t s);
 cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t s);
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,

@@ -215,12 +215,130 @@ __global__ void colsum_kernel(const float* __restrict__ dY, int ldy, float* __re
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m_beg = blockIdx.y * m_chunk, m_end = min(M, m_beg + m_chunk);
-  float s = 0.f;
-  for (int m = m_beg; m < m_end; ++m) s += dY[(size_t)m * ldy + n];
-  atomicAdd(db + n, s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // independent chains: the loads of a chunk are all in flight
+  int m = m_beg;
+  for (; m + 4 <= m_end; m += 4) {
+    s0 += dY[(size_t)m * ldy + n]; s1 += dY[(size_t)(m + 1) * ldy + n];
+    s2 += dY[(size_t)(m + 2) * ldy + n]; s3 += dY[(size_t)(m + 3) * ldy + n];
+  }
+  for (; m < m_end; ++m) s0 += dY[(size_t)m * ldy + n];
+  atomicAdd(db + n, (s0 + s1) + (s2 + s3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused Adafactor (transformers.optimization.Adafactor.step with its default arguments: factored second
+// moments for matrices, relative step, parameter scaling, update clipping, no first moment).  One CTA per
+// parameter tensor walks the whole update: the stock implementation issues ~30 small kernels and one host
+// synchronisation (`max(eps, RMS)` on a device scalar) per tensor.
+// ---------------------------------------------------------------------------------------------
+constexpr int AF_NT = 1024;
+
+__device__ __forceinline__ float af_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < AF_NT / 32) ? red[threadIdx.x] : 0.f;
+  if (warp == 0) {
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__global__ void __launch_bounds__(AF_NT)
+adafactor_kernel(const da_adafactor_param* __restrict__ params, float eps1, float eps2, float clip, float weight_decay) {
+  __shared__ float red[33];
+  const da_adafactor_param q = params[blockIdx.x];
+  const int R = q.rows, C = q.cols;
+  const size_t n = (size_t)R * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float beta = q.beta2t, omb = 1.f - q.beta2t;
+  float pp = 0.f;   // ||p||^2
+  float uu = 0.f;   // ||update||^2
+  float row_mean_all = 1.f;
+  const bool factored = q.sq_row != nullptr;
+  if (factored) {
+    // pass A: column means of g^2 + eps1 (thread per column, coalesced rows)
+    for (int c = threadIdx.x; c < C; c += AF_NT) {
+      float s0 = 0.f, s1 = 0.f;
+      int r = 0;
+      for (; r + 2 <= R; r += 2) {
+        const float g0 = q.g[(size_t)r * C + c], g1 = q.g[(size_t)(r + 1) * C + c];
+        s0 += g0 * g0 + eps1; s1 += g1 * g1 + eps1;
+      }
+      if (r < R) { const float g0 = q.g[(size_t)r * C + c]; s0 += g0 * g0 + eps1; }
+      q.sq_col[c] = beta * q.sq_col[c] + omb * ((s0 + s1) / (float)R);
+    }
+    // pass B: row means (warp per row) and ||p||^2
+    float rsum = 0.f;
+    for (int r = warp; r < R; r += AF_NT / 32) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float g = q.g[(size_t)r * C + c], p = q.p[(size_t)r * C + c];
+        s += g * g + eps1;
+        pp += p * p;
+      }
+      s = warp_sum(s);
+      const float nr = beta * q.sq_row[r] + omb * (s / (float)C);
+      if (lane == 0) { q.sq_row[r] = nr; rsum += nr; }
+    }
+    row_mean_all = af_block_sum(rsum, red) / (float)R;
+    pp = af_block_sum(pp, red);
+    // pass C: ||update||^2 with update = g * rsqrt(row / mean(row)) * rsqrt(col)
+    for (int r = warp; r < R; r += AF_NT / 32) {
+      const float rf = rsqrtf(q.sq_row[r] / row_mean_all);
+      for (int c = lane; c < C; c += 32) {
+        const float u = q.g[(size_t)r * C + c] * rf * rsqrtf(q.sq_col[c]);
+        uu += u * u;
+      }
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += AF_NT) {
+      const float g = q.g[i], p = q.p[i];
+      const float v = beta * q.sq[i] + omb * (g * g + eps1);
+      q.sq[i] = v;
+      const float u = g * rsqrtf(v);
+      uu += u * u;
+      pp += p * p;
+    }
+    pp = af_block_sum(pp, red);
+  }
+  uu = af_block_sum(uu, red);
+  const float rms_p = sqrtf(pp) / sqrtf((float)n);
+  const float rms_u = sqrtf(uu) / sqrtf((float)n);
+  const float lr = fmaxf(eps2, rms_p) * q.rel_step;
+  const float scale = lr / fmaxf(1.f, rms_u / clip);
+  if (threadIdx.x == 0 && q.rms_out) *q.rms_out = rms_p;
+  if (factored) {
+    for (int r = warp; r < R; r += AF_NT / 32) {
+      const float rf = rsqrtf(q.sq_row[r] / row_mean_all) * scale;
+      for (int c = lane; c < C; c += 32) {
+        const size_t i = (size_t)r * C + c;
+        float p = q.p[i];
+        if (weight_decay != 0.f) p += p * (-weight_decay * lr);
+        q.p[i] = p - q.g[i] * rf * rsqrtf(q.sq_col[c]);
+      }
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += AF_NT) {
+      float p = q.p[i];
+      if (weight_decay != 0.f) p += p * (-weight_decay * lr);
+      q.p[i] = p - q.g[i] * rsqrtf(q.sq[i]) * scale;
+    }
+  }
 }
 
 }  // namespace
+
+cudaError_t launch_adafactor(const da_adafactor_param* params_dev, int n, float eps1, float eps2, float clip, float weight_decay,
+                             cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  adafactor_kernel<<<n, AF_NT, 0, s>>>(params_dev, eps1, eps2, clip, weight_decay);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_attn_backward(const float* qkvs, const float* dO, const CsrGraph& by_target, const CsrGraph& by_source,
                                  const float* stats, int n, int H, int C, float* dqkvs, float* delta, cudaStream_t s) {
@@ -262,8 +380,9 @@ cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, floa
   if (db) {
     e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, s);
     if (e != cudaSuccess) return e;
-    dim3 g2((N + 255) / 256, (M + m_chunk - 1) / m_chunk);
-    colsum_kernel<<<g2, 256, 0, s>>>(dY, N, db, M, N, m_chunk);
+    const int c_chunk = 64;   // short row chunks: thousands of CTAs instead of a few dozen latency-bound ones
+    dim3 g2((N + 255) / 256, (M + c_chunk - 1) / c_chunk);
+    colsum_kernel<<<g2, 256, 0, s>>>(dY, N, db, M, N, c_chunk);
   }
   return cudaGetLastError();
 }

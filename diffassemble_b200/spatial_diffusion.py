@@ -454,10 +454,10 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
                                   edge_index=edge_index, batch=batch)
 
     # -- Lightning hooks on the sampling path ------------------------------------------------------
-    def configure_optimizers(self):  # spatial_diffusion.py:701-705
-        from transformers.optimization import Adafactor
+    def configure_optimizers(self):  # spatial_diffusion.py:701-705: Adafactor(self.parameters()), default arguments
+        from .training import FusedAdafactor
 
-        return Adafactor(self.parameters())
+        return FusedAdafactor(self.parameters())
 
     @torch.no_grad()
     def prediction_step(self, batch, batch_idx):  # :768-773

@@ -174,3 +174,96 @@ def allreduce_gradients(parameters, world_size: int, group=None):
     for g in grads:
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused Adafactor
+# ---------------------------------------------------------------------------------------------
+def _adafactor_base():
+    from transformers.optimization import Adafactor
+
+    return Adafactor
+
+
+def FusedAdafactor(params, **kwargs):
+    """``transformers.optimization.Adafactor`` (the reference's optimizer, ``spatial_diffusion.py:701-705``) with its
+    ``step`` replaced by ONE launch of ``da_adafactor_step`` for every fp32 CUDA parameter of rank <= 2 (all of the
+    denoiser's).  Same constructor arguments, same state entries (``step``, ``exp_avg_sq_row``, ``exp_avg_sq_col``,
+    ``exp_avg_sq``, ``RMS``), so optimizer checkpoints are interchangeable.  Parameters the kernel does not cover
+    (rank > 2, first-moment runs, CPU) take the stock code path inside the same ``step`` call."""
+    import ctypes as C
+    import math
+
+    import numpy as np
+
+    from . import _cabi
+
+    Base = _adafactor_base()
+
+    class _FusedAdafactor(Base):
+        _DESC = np.dtype([("p", "<u8"), ("g", "<u8"), ("sq_row", "<u8"), ("sq_col", "<u8"), ("sq", "<u8"), ("rms", "<u8"),
+                          ("rows", "<i4"), ("cols", "<i4"), ("beta2t", "<f4"), ("rel_step", "<f4")])
+
+        @torch.no_grad()
+        def step(self, closure=None):
+            loss = closure() if closure is not None else None
+            lib = _cabi.load_library()
+            stash = []
+            for group in self.param_groups:
+                fused = []
+                for p in group["params"]:
+                    g = p.grad
+                    ok = (g is not None and p.is_cuda and p.dtype == torch.float32 and g.dtype == torch.float32 and p.dim() <= 2
+                          and p.dim() >= 1 and group["beta1"] is None and group["relative_step"] and group["scale_parameter"]
+                          and not group["warmup_init"] and p.is_contiguous() and not g.is_sparse)
+                    if ok:
+                        fused.append(p)
+                if not fused:
+                    continue
+                dev = fused[0].device
+                desc = np.zeros(len(fused), dtype=self._DESC)
+                for k, p in enumerate(fused):
+                    g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                    st = self.state[p]
+                    if len(st) == 0:
+                        st["step"] = 0
+                        if p.dim() == 2:
+                            st["exp_avg_sq_row"] = torch.zeros(p.shape[0], dtype=torch.float32, device=dev)
+                            st["exp_avg_sq_col"] = torch.zeros(p.shape[1], dtype=torch.float32, device=dev)
+                        else:
+                            st["exp_avg_sq"] = torch.zeros_like(p)
+                        st["RMS"] = torch.zeros((), dtype=torch.float32, device=dev)
+                    if not torch.is_tensor(st["RMS"]):
+                        st["RMS"] = torch.zeros((), dtype=torch.float32, device=dev)
+                    st["step"] += 1
+                    d = desc[k]
+                    d["p"], d["g"], d["rms"] = p.data_ptr(), g.data_ptr(), st["RMS"].data_ptr()
+                    if p.dim() == 2:
+                        d["sq_row"], d["sq_col"] = st["exp_avg_sq_row"].data_ptr(), st["exp_avg_sq_col"].data_ptr()
+                        d["rows"], d["cols"] = p.shape
+                    else:
+                        d["sq"] = st["exp_avg_sq"].data_ptr()
+                        d["rows"], d["cols"] = 1, p.numel()
+                    d["beta2t"] = 1.0 - math.pow(st["step"], group["decay_rate"])
+                    d["rel_step"] = min(1e-2, 1.0 / math.sqrt(st["step"]))
+                    stash.append((p, p.grad, g))
+                table = torch.from_numpy(desc.view(np.uint8).reshape(-1).copy()).to(dev, non_blocking=True)
+                with torch.cuda.device(dev):
+                    stt = lib.da_adafactor_step(C.c_void_p(table.data_ptr()), len(fused), float(group["eps"][0]),
+                                                float(group["eps"][1]), float(group["clip_threshold"]),
+                                                float(group["weight_decay"]), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                if stt != _cabi.DA_OK:
+                    raise _cabi.DiffAssembleError(stt, "da_adafactor_step failed")
+                table.record_stream(torch.cuda.current_stream(dev))
+            # everything else: the stock implementation, with the fused parameters' gradients hidden from it
+            for p, grad, _ in stash:
+                p.grad = None
+            try:
+                if any(q.grad is not None for group in self.param_groups for q in group["params"]):
+                    super().step()
+            finally:
+                for p, grad, _ in stash:
+                    p.grad = grad
+            return loss
+
+    return _FusedAdafactor(params, **kwargs)

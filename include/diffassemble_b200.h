@@ -190,6 +190,24 @@ const char* da_profile_tag_name(int32_t i);
  * mode = DA_GEMM_*; all pointers device fp32. */
 int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y,
                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
+/* Fused Adafactor step (scope row N1).  Replaces transformers.optimization.Adafactor.step -- the optimizer the reference
+ * instantiates with default arguments (spatial_diffusion.py:701-705) -- for fp32 parameters of rank <= 2:
+ * factored second moments (sq_row [rows], sq_col [cols]) for matrices, a full one (sq [rows*cols]) for vectors
+ * (then sq_row = sq_col = NULL), relative step, parameter scaling, update clipping, no first moment.
+ * `params` is an array of n descriptors IN DEVICE MEMORY; beta2t = 1 - step^decay_rate and
+ * rel_step = min(1e-2, 1/sqrt(step)) are computed by the caller per tensor; rms_out (optional) receives RMS(p). */
+typedef struct da_adafactor_param {
+  float* p;
+  const float* g;
+  float* sq_row;
+  float* sq_col;
+  float* sq;
+  float* rms_out;
+  int32_t rows, cols;
+  float beta2t, rel_step;
+} da_adafactor_param;
+int da_adafactor_step(const da_adafactor_param* params, int32_t n, float eps1, float eps2, float clip_threshold,
+                      float weight_decay, void* stream);
 /* Segment-wise column maximum: out[g, c] = max_{seg_ptr[g] <= r < seg_ptr[g+1]} x[r, c]  (x fp32 [rows, ld], out fp32
  * [n_seg, cols]).  The global max pool of the PointNet fragment encoder (puzzle_diff/model/backbones/pointnet.py:39-40),
  * scope row N4; the point-wise layers of that encoder are da_op_linear calls with eval-mode BatchNorm folded in. */

@@ -543,3 +543,33 @@ def test_dense_tiles_full_and_partial_with_residual_mix(sizes, C):
     y, n_dense = op_graph_attention_dense(qkvs.to(DEV), ei.to(DEV), batch.to(DEV), H)
     assert n_dense > 0
     assert rel_err(y, ref) < 2e-5
+
+
+def test_fused_adafactor_matches_transformers_adafactor():
+    """Scope row N1: ``da_adafactor_step`` against the reference's optimizer (transformers Adafactor, default
+    arguments) over several steps: parameters and every state tensor."""
+    from transformers.optimization import Adafactor
+
+    from diffassemble_b200.training import FusedAdafactor
+
+    g = torch.Generator().manual_seed(0)
+    shapes = [(256, 1152), (1152, 128), (4, 16), (300, 32), (1, 7), (1152,), (32,), (1,), (8, 1152), (3, 5, 2)]
+    base = [torch.randn(s, generator=g) * (0.05 if len(s) > 1 else 1.0) for s in shapes]
+    a = [torch.nn.Parameter(t.clone().to(DEV)) for t in base]
+    b = [torch.nn.Parameter(t.clone().to(DEV)) for t in base]
+    opt_a, opt_b = Adafactor(a), FusedAdafactor(b)
+    for step in range(5):
+        for pa, pb in zip(a, b):
+            gr = (torch.randn(pa.shape, generator=g) * (10.0 ** (step - 2))).to(DEV)   # wide range: clipping on and off
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        opt_a.step(); opt_b.step()
+        for k, (pa, pb) in enumerate(zip(a, b)):
+            assert rel_err(pb, pa) < 1e-5, (step, shapes[k])
+    for pa, pb in zip(a, b):
+        sa, sb = opt_a.state[pa], opt_b.state[pb]
+        assert sa["step"] == sb["step"] == 5
+        for key in ("exp_avg_sq_row", "exp_avg_sq_col", "exp_avg_sq"):
+            assert (key in sa) == (key in sb), key
+            if key in sa:
+                assert rel_err(sb[key], sa[key]) < 1e-5, key
+        assert abs(float(sb["RMS"]) - float(sa["RMS"])) <= 1e-5 * abs(float(sa["RMS"])) + 1e-12
