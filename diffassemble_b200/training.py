@@ -105,7 +105,14 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wt = w.detach().t().contiguous()   # [K, N]: dx = dy @ w  ==  linear(dy, w^T)
             dx = op_linear(dy, wt, None, act=0, mode=_linear_mode(ctx.mode, wt.shape[0], wt.shape[1]))
-        dw, db = op_linear_wgrad(dy, x, with_bias=ctx.has_bias)
+        M, N, K = dy.shape[0], dy.shape[1], x.shape[1]
+        if ctx.mode == "bf16x3" and M % 64 == 0 and K % 32 == 0 and N >= 32:
+            # weight gradient on the tensor cores: dW[N, K] = dY^T X is the same linear operator with the node
+            # dimension as its reduction axis (3-pass split-bf16, ~1e-5 relative); the two transposes are the only glue
+            dw = op_linear(dy.t().contiguous(), x.t().contiguous(), None, act=0, mode="bf16x3")
+            db = dy.sum(0) if ctx.has_bias else None
+        else:
+            dw, db = op_linear_wgrad(dy, x, with_bias=ctx.has_bias)
         return dx, dw, db, None
 
 

@@ -333,8 +333,9 @@ def test_expander_topology_on_device_is_bit_identical(n, degree, B):
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-3), ("bf16x3", 1e-3)])
-@pytest.mark.parametrize("arch,V", [("transformer", 0), ("exophormer", 4)])
-def test_training_step_gradients_match_oracle_autograd(arch, V, mode, tol):
+@pytest.mark.parametrize("arch,V,sizes", [("transformer", 0, [36, 25, 16]), ("exophormer", 4, [36, 25, 16]),
+                                          ("transformer", 0, [64, 36, 28])])   # 128 nodes: tensor-core weight gradients
+def test_training_step_gradients_match_oracle_autograd(arch, V, sizes, mode, tol):
     """Scope row N1: loss and every parameter gradient of one p_losses step against torch autograd
     through the CPU oracle (identical weights, inputs, t and noise).  Tolerance 1e-3 relative per tensor
     (max|g - g_ref| / max|g_ref|): several gradients (query/key biases of the last layer) are ~1e-10 sums of
@@ -343,13 +344,13 @@ def test_training_step_gradients_match_oracle_autograd(arch, V, mode, tol):
                             gemm_mode=mode, attn_mode="csr")
     mod = mod.to(DEV)
     ref.train(); mod.train()
-    ei, batch = synth_graph_batch([36, 25, 16])
+    ei, batch = synth_graph_batch(sizes)
     M = len(batch)
     g = torch.Generator().manual_seed(0)
     feats = torch.randn(M, 1088, generator=g)
     x0 = torch.rand(M, 4, generator=g) * 2 - 1
     noise = torch.randn(M, 4, generator=g)
-    t = torch.randint(0, 50, (3,), generator=g)[batch]
+    t = torch.randint(0, 50, (len(sizes),), generator=g)[batch]
     loss_ref = ref.p_losses(x0, t, noise=noise, loss_type="huber", edge_index=ei, patch_feats=feats, batch=batch)
     loss_ref.backward()
     loss = mod.p_losses(x0.to(DEV), t.to(DEV), noise=noise.to(DEV), loss_type="huber", cond=feats.to(DEV),
