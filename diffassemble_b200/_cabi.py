@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "da_set_features", "da_forward", "da_ddpm_step", "da_ddim_step", "da_ddim_update", "da_workspace_bytes",
     "da_launch_count", "da_graph_stats", "da_set_profiling", "da_get_profile", "da_profile_tag_name",
     "da_op_linear", "da_op_graph_attention", "da_op_graph_attention_dense", "da_greedy_cost_assignment", "da_expander_edge_index", "da_graph_create", "da_graph_destroy",
-    "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws", "da_op_segment_max", "da_adafactor_step",
+    "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws", "da_op_segment_max", "da_adafactor_step", "da_graph_set_batch",
     "da_op_linear_workspace_bytes",
 ]
 
@@ -102,6 +102,7 @@ def load_library():
     lib.da_op_graph_attention.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]
     lib.da_op_graph_attention_dense.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(i64), vp]
     lib.da_graph_create.argtypes = [C.POINTER(vp), vp, vp, i64, i32, vp]
+    lib.da_graph_set_batch.argtypes = [vp, vp, vp, vp, vp]
     lib.da_graph_destroy.argtypes = [vp]
     lib.da_graph_destroy.restype = None
     lib.da_op_graph_attention_fwd.argtypes = [vp, vp, i32, i32, vp, vp, vp]

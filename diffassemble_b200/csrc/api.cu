@@ -853,6 +853,13 @@ struct da_graph {
   CsrGraph by_target, by_source;
   int n = 0;
   int64_t E = 0;
+  // optional dense-tile plan (da_graph_set_batch): when every edge of the batch lands in a bitmap -- the dense
+  // puzzle graphs of the training configs -- the forward runs on the tensor-core kernel and only the backward
+  // walks the edge lists
+  DensePlan plan;
+  bool dense_ok = false;
+  DevBuf qimg, kimg, vimg, acc;
+  int img_h = 0, img_cpad = 0;
 };
 
 int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n, void* stream) {
@@ -869,15 +876,71 @@ int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge
   return DA_OK;
 }
 
+int da_graph_set_batch(da_graph* g, const int64_t* edge_src, const int64_t* edge_dst, const int64_t* batch, void* stream) {
+  if (!g || !batch || (g->E > 0 && (!edge_src || !edge_dst))) return DA_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const char* why = "";
+  g->dense_ok = false;
+  cudaError_t ce = build_dense_plan(edge_src, edge_dst, g->E, batch, g->n, g->n, &g->plan, s, &why);
+  if (ce != cudaSuccess) return ce == cudaErrorInvalidValue ? DA_ERR_INVALID : DA_ERR_CUDA;
+  // usable when the bitmaps hold the WHOLE multiset and every node sits in a tile: then the dense kernel's
+  // (m, l) are the final softmax statistics the backward needs
+  bool all_in_tiles = g->plan.n_tiles > 0 && g->plan.residual.E == 0;
+  if (all_in_tiles) {
+    std::vector<int32_t> slot((size_t)g->n);
+    if (copy_sync(slot.data(), g->plan.node_slot, sizeof(int32_t) * slot.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      return DA_ERR_CUDA;
+    for (int32_t v : slot) if (v < 0) { all_in_tiles = false; break; }
+  }
+  g->dense_ok = all_in_tiles;
+  return DA_OK;
+}
+
 void da_graph_destroy(da_graph* g) {
   if (!g) return;
   free_csr(&g->by_target); free_csr(&g->by_source);
+  free_plan(&g->plan);
+  g->qimg.release(); g->kimg.release(); g->vimg.release(); g->acc.release();
   delete g;
 }
 
-int da_op_graph_attention_fwd(const da_graph* g, const float* qkvs, int32_t H, int32_t C, float* y, float* stats, void* stream) {
+int da_op_graph_attention_fwd(const da_graph* gc, const float* qkvs, int32_t H, int32_t C, float* y, float* stats, void* stream) {
+  da_graph* g = const_cast<da_graph*>(gc);   // (lazily sized scratch images live in the graph object)
   if (!g || !qkvs || !y || !stats || H <= 0 || C <= 0) return DA_ERR_INVALID;
   if ((C + 31) / 32 > 13) return DA_ERR_UNSUPPORTED;
+  const int Cpad = (C + 15) / 16 * 16;
+  if (g->dense_ok && C % 8 == 0 && Cpad <= 144 && attn_csr_rows_supported(H, C)) {
+    // tensor-core forward: repack -> bitmap-masked dense attention (un-fused: it leaves (acc, m, l)) -> normalise + skip.
+    // The statistics land directly in `stats` in the (max, sum) convention of the CSR kernel.
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t img = dense_image_elems(g->plan.n_tiles, H, Cpad) * sizeof(__nv_bfloat16);
+    if (g->img_h != H || g->img_cpad != Cpad || g->qimg.bytes < img) {
+      if (g->qimg.ensure(img) != cudaSuccess || g->kimg.ensure(img) != cudaSuccess || g->vimg.ensure(img) != cudaSuccess)
+        return DA_ERR_CUDA;
+      cudaMemsetAsync(g->qimg.p, 0, g->qimg.bytes, s); cudaMemsetAsync(g->kimg.p, 0, g->kimg.bytes, s);
+      cudaMemsetAsync(g->vimg.p, 0, g->vimg.bytes, s);
+      g->img_h = H; g->img_cpad = Cpad;
+    }
+    if (g->acc.ensure((size_t)g->n * H * C * sizeof(float)) != cudaSuccess) return DA_ERR_CUDA;
+    PackArgs pa{qkvs, 4 * H * C, g->plan.node_slot, g->n, H, C, Cpad, g->qimg.as<__nv_bfloat16>(), g->kimg.as<__nv_bfloat16>(),
+                g->vimg.as<__nv_bfloat16>()};
+    cudaError_t ce = launch_pack_images(pa, s);
+    if (ce == cudaSuccess) ce = launch_gather_extra(pa, g->plan.x_src, g->plan.x_slot, g->plan.n_extra, s);
+    if (ce == cudaSuccess) {
+      AttnDenseArgs da_{pa.qimg, pa.kimg, pa.vimg, g->plan.tiles, g->plan.n_tiles, g->plan.bitmap, H, C, Cpad, g->acc.as<float>(),
+                        stats, nullptr};
+      ce = launch_attn_dense(da_, s);
+    }
+    if (ce == cudaSuccess) {
+      AttnCsrArgs a{};
+      a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = g->plan.residual.rowptr; a.col = g->plan.residual.col;
+      a.weight = g->plan.residual.weight; a.n_targets = g->n; a.H = H; a.C = C; a.act = ACT_NONE;
+      a.out.f32 = y; a.out.ldc = H * C;
+      a.init_acc = g->acc.as<float>(); a.init_stats = stats; a.init_slot = g->plan.node_slot;
+      ce = launch_attn_csr_rows(a, s);
+    }
+    return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+  }
   AttnCsrArgs a{};
   a.qkvs = qkvs; a.ld = 4 * H * C; a.rowptr = g->by_target.rowptr; a.col = g->by_target.col; a.n_targets = g->n; a.H = H; a.C = C;
   a.act = ACT_NONE; a.out.f32 = y; a.out.ldc = H * C; a.stats = stats;

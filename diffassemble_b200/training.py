@@ -44,7 +44,7 @@ def op_linear_wgrad(dy: torch.Tensor, x: torch.Tensor, with_bias: bool = True):
 class TrainGraph:
     """CSR-by-target + CSR-by-source of one batch's edge multiset (``da_graph``), built once per batch."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, batch: Optional[torch.Tensor] = None):
         _require_cuda(edge_index, "edge_index")
         self._lib = _cabi.load_library()
         ei = edge_index.to(torch.int64).contiguous()
@@ -55,6 +55,13 @@ class TrainGraph:
         if st != _cabi.DA_OK:
             raise DiffAssembleError(st, "da_graph_create failed (edge index out of range?)")
         self._h = h
+        if batch is not None and batch.numel() == self.n:
+            # dense-tile plan: lets the forward attention of dense puzzle graphs run on the tensor cores
+            b = batch.to(device=self.device, dtype=torch.int64).contiguous()
+            with torch.cuda.device(self.device):
+                st = self._lib.da_graph_set_batch(self._h, _ptr(ei[0]), _ptr(ei[1]), _ptr(b), _stream(self.device))
+            if st != _cabi.DA_OK:
+                raise DiffAssembleError(st, "da_graph_set_batch failed")
 
     def __del__(self):
         try:
@@ -145,7 +152,8 @@ def denoiser_forward_train(model, xy_pos, time, edge_index, patch_feats, batch, 
     num_real = len(batch)
     if graph is None:
         ext, num_total, virt_ids = gnn.extend_graph(edge_index, batch)
-        graph = TrainGraph(ext, num_total)
+        # (the dense-tile forward needs every node in a graph's tile: batches without virtual rows)
+        graph = TrainGraph(ext, num_total, batch if (num_total == num_real and model.attn_mode == "auto") else None)
         graph.virt_ids = virt_ids
     time_feats = F.embedding(time, model.time_emb.weight)                               # efficient_gat.py:131
     pos_feats = linear(F.gelu(linear(xy_pos, model.pos_mlp[0], mode)), model.pos_mlp[2], mode)   # :132

@@ -254,6 +254,10 @@ int da_expander_edge_index(const int32_t* perm, int32_t n, int32_t degree, int32
  * edge multiset (built once per batch). */
 typedef struct da_graph da_graph;
 int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n, void* stream);
+/* optional: also build the dense-tile plan of the batch (`batch` int64 [n], PyG collation order; same edge arrays as
+ * da_graph_create).  When every edge lands in a bitmap (the dense puzzle graphs of the training configs) the forward
+ * below runs on the tensor-core attention kernel; otherwise nothing changes. */
+int da_graph_set_batch(da_graph* g, const int64_t* edge_src, const int64_t* edge_dst, const int64_t* batch, void* stream);
 void da_graph_destroy(da_graph* g);
 /* forward of the TransformerConv attention stage, also returning the per-(node, head) softmax statistics
  * stats[n, H, 2] = (max, sum) that the backward needs;  y[n, H*C] = aggregate + skip */

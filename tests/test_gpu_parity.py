@@ -574,3 +574,39 @@ def test_fused_adafactor_matches_transformers_adafactor():
             if key in sa:
                 assert rel_err(sb[key], sa[key]) < 1e-5, key
         assert abs(float(sb["RMS"]) - float(sa["RMS"])) <= 1e-5 * abs(float(sa["RMS"])) + 1e-12
+
+
+@pytest.mark.parametrize("mode", GEMM_MODES)
+def test_training_gradients_with_dense_tile_forward(mode):
+    """Scope row N1 with ``attn_mode="auto"``: on dense puzzle graphs the forward attention runs on the tensor-core
+    kernel (its (m, l) feed the edge-list backward); loss and gradients still match oracle autograd."""
+    ref, mod = make_pair_2d(seed=7, steps=50, sampling="DDIM", architecture="transformer", virt_nodes=0,
+                            model_mean_type="EPSILON", gemm_mode=mode, attn_mode="auto")
+    mod = mod.to(DEV)
+    ref.train(); mod.train()
+    sizes = [64, 64]
+    ei, batch = synth_graph_batch(sizes)
+    M = len(batch)
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(M, 1088, generator=g)
+    x0 = torch.rand(M, 4, generator=g) * 2 - 1
+    noise = torch.randn(M, 4, generator=g)
+    t = torch.randint(0, 50, (len(sizes),), generator=g)[batch]
+    loss_ref = ref.p_losses(x0, t, noise=noise, loss_type="huber", edge_index=ei, patch_feats=feats, batch=batch)
+    loss_ref.backward()
+    loss = mod.p_losses(x0.to(DEV), t.to(DEV), noise=noise.to(DEV), loss_type="huber", cond=feats.to(DEV),
+                        edge_index=ei.to(DEV), batch=batch.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    ref_grads = dict(ref.named_parameters())
+    checked = 0
+    for name, p in mod.named_parameters():
+        gr = ref_grads[name].grad
+        if gr is None or gr.abs().max() < 1e-9:
+            continue
+        assert p.grad is not None, name
+        assert rel_err(p.grad, gr) < 1e-3, (name, rel_err(p.grad, gr))
+        checked += 1
+    assert checked >= 30
+    graph = mod._train_graph[1]
+    assert graph._lib is not None   # the TrainGraph was built with the batch vector (dense plan attached)
