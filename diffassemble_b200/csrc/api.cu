@@ -860,6 +860,9 @@ struct da_graph {
   bool dense_ok = false;
   DevBuf qimg, kimg, vimg, acc;
   int img_h = 0, img_cpad = 0;
+  // per-graph descriptors {node0, n, bm_words, pad, bm_off} for the shared-memory backward
+  DevBuf graphs;
+  int n_graphs = 0, n_max = 0, bm_words_max = 0;
 };
 
 int da_graph_create(da_graph** out, const int64_t* edge_src, const int64_t* edge_dst, int64_t E, int32_t n, void* stream) {
@@ -893,6 +896,24 @@ int da_graph_set_batch(da_graph* g, const int64_t* edge_src, const int64_t* edge
     for (int32_t v : slot) if (v < 0) { all_in_tiles = false; break; }
   }
   g->dense_ok = all_in_tiles;
+  g->n_graphs = 0;
+  if (all_in_tiles) {   // one descriptor per graph, from the first tile of each
+    std::vector<TileInfo> tiles((size_t)g->plan.n_tiles);
+    if (copy_sync(tiles.data(), g->plan.tiles, sizeof(TileInfo) * tiles.size(), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      return DA_ERR_CUDA;
+    struct GD { int32_t node0, n, bm_words, pad; int64_t bm_off; };
+    std::vector<GD> gds;
+    g->n_max = 0; g->bm_words_max = 0;
+    for (const TileInfo& t : tiles) {
+      if (t.row0 != 0) continue;
+      gds.push_back(GD{t.node0, t.gn, t.bm_words, 0, t.bm_off});
+      if (t.gn > g->n_max) g->n_max = t.gn;
+      if (t.bm_words > g->bm_words_max) g->bm_words_max = t.bm_words;
+    }
+    if (g->graphs.ensure(sizeof(GD) * gds.size()) != cudaSuccess) return DA_ERR_CUDA;
+    if (copy_sync(g->graphs.p, gds.data(), sizeof(GD) * gds.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) return DA_ERR_CUDA;
+    g->n_graphs = (int)gds.size();
+  }
   return DA_OK;
 }
 
@@ -900,7 +921,7 @@ void da_graph_destroy(da_graph* g) {
   if (!g) return;
   free_csr(&g->by_target); free_csr(&g->by_source);
   free_plan(&g->plan);
-  g->qimg.release(); g->kimg.release(); g->vimg.release(); g->acc.release();
+  g->qimg.release(); g->kimg.release(); g->vimg.release(); g->acc.release(); g->graphs.release();
   delete g;
 }
 
@@ -952,7 +973,12 @@ int da_op_graph_attention_bwd(const da_graph* g, const float* qkvs, const float*
                               float* dqkvs, float* delta_ws, void* stream) {
   if (!g || !qkvs || !stats || !dy || !dqkvs || !delta_ws || H <= 0 || C <= 0) return DA_ERR_INVALID;
   if ((C + 31) / 32 > 13) return DA_ERR_UNSUPPORTED;
-  cudaError_t ce = launch_attn_backward(qkvs, dy, g->by_target, g->by_source, stats, g->n, H, C, dqkvs, delta_ws, (cudaStream_t)stream);
+  cudaError_t ce;
+  if (g->dense_ok && g->n_graphs > 0 && attn_backward_dense_fits(g->n_max, C, g->bm_words_max) && !getenv("DA_NO_DENSE_BWD"))
+    ce = launch_attn_backward_dense(qkvs, dy, g->graphs.p, g->n_graphs, g->n_max, g->bm_words_max, g->plan.bitmap, stats, g->n, H,
+                                    C, dqkvs, delta_ws, (cudaStream_t)stream);
+  else
+    ce = launch_attn_backward(qkvs, dy, g->by_target, g->by_source, stats, g->n, H, C, dqkvs, delta_ws, (cudaStream_t)stream);
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 

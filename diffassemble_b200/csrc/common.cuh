@@ -209,6 +209,11 @@ cudaError_t launch_expander_edges(const int32_t* perm, int n, int degree, int n_
 // training (scope row N1)
 cudaError_t launch_attn_backward(const float* qkvs, const float* dO, const CsrGraph& by_target, const CsrGraph& by_source,
                                  const float* stats, int n, int H, int C, float* dqkvs, float* delta, cudaStream_t s);
+// per-graph shared-memory backward for batches whose edges all sit in the dense plan's bitmaps (train.cu)
+bool attn_backward_dense_fits(int n_max, int C, int bm_words_max);
+cudaError_t launch_attn_backward_dense(const float* qkvs, const float* dO, const void* graphs_dev, int n_graphs, int n_max,
+                                       int bm_words_max, const uint32_t* bitmap, const float* stats, int n, int H, int C,
+                                       float* dqkvs, float* delta, cudaStream_t s);
 cudaError_t launch_adafactor(const da_adafactor_param* params_dev, int n, float eps1, float eps2, float clip, float weight_decay,
                              cudaStream_t s);
 cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t s);

@@ -158,6 +158,129 @@ attn_bwd_source_kernel(const float* __restrict__ qkvs, int ld, const float* __re
   }
 }
 
+// ---- dense puzzle graphs: one CTA per (graph, head), operands of the whole graph staged in shared memory -------
+// The edge-list kernels above gather K / V (or Q / dO) rows from L2 once per EDGE: 144 times per row on a
+// dense 12x12 puzzle, which makes them L2-gather bound (12.5 of the 16.8 ms of a c5 training step).  When a
+// graph's whole edge multiset sits in its adjacency bitmap (DensePlan, no residual edges) and its [n, C] operands
+// fit in shared memory, the same two passes run out of shared memory: rows are padded to C + 4 floats so that
+// lane-per-neighbour dot products (float4 reads at stride C + 4: 8 lanes per phase hit 8 distinct bank groups for
+// C = 32 and 144) and lane-per-channel updates (stride 1) are both conflict free.  (Requires C % 4 == 0.)
+struct GraphDesc { int32_t node0, n, bm_words, pad; int64_t bm_off; };
+
+__device__ __forceinline__ bool bm_bit(const uint32_t* bm, int bm_words, int i, int j) {
+  return (bm[i * bm_words + (j >> 5)] >> (j & 31)) & 1u;
+}
+
+// MODE 0: by target (A = K, B = V staged; per row i: delta_i, dq_i).  MODE 1: by source (A = Q, B = dO staged; per
+// row j: dk_j, dv_j).
+template <int MODE>
+__global__ void __launch_bounds__(TW * 32)
+attn_bwd_graph_kernel(const float* __restrict__ qkvs, int ld, const float* __restrict__ dO, int ldo,
+                      const GraphDesc* __restrict__ graphs, const uint32_t* __restrict__ bitmap,
+                      const float* __restrict__ stats, float* __restrict__ delta, int H, int C, float scale,
+                      float* __restrict__ dqkvs, int ldg) {
+  extern __shared__ __align__(16) float sm[];
+  const GraphDesc gd = graphs[blockIdx.x];
+  const int head = blockIdx.y, n = gd.n, HC = H * C, P = C + 4;
+  float* A = sm;                          // [n][P]
+  float* B = A + (size_t)n * P;           // [n][P]
+  const int n4 = (n + 3) & ~3;            // (16-byte aligned per-warp vectors)
+  float* wbuf = B + (size_t)n * P;        // per warp: a[C] | b[C] | w1[n4] | w2[n4]
+  uint32_t* bm = reinterpret_cast<uint32_t*>(wbuf + (size_t)TW * (2 * C + 2 * n4));   // [n][bm_words]
+  float* mrow = reinterpret_cast<float*>(bm + (size_t)n * gd.bm_words);               // [n] max
+  float* lrow = mrow + n;                                                             // [n] 1 / (l + 1e-16)
+  float* drow = lrow + n;                                                             // [n] delta (MODE 1)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int offA = (MODE == 0 ? HC : 0) + head * C;        // K (by target) or Q (by source)
+  for (int idx = threadIdx.x; idx < n * C; idx += TW * 32) {
+    const int r = idx / C, c = idx - r * C;
+    const size_t node = (size_t)(gd.node0 + r);
+    A[r * P + c] = qkvs[node * ld + offA + c];
+    B[r * P + c] = MODE == 0 ? qkvs[node * ld + 2 * HC + head * C + c] : dO[node * ldo + head * C + c];
+  }
+  for (int idx = threadIdx.x; idx < n * gd.bm_words; idx += TW * 32) bm[idx] = bitmap[gd.bm_off + idx];
+  for (int r = threadIdx.x; r < n; r += TW * 32) {
+    const size_t sidx = ((size_t)(gd.node0 + r) * H + head) * 2;
+    mrow[r] = stats[sidx];
+    lrow[r] = 1.f / (stats[sidx + 1] + 1e-16f);
+    if (MODE == 1) drow[r] = delta[(size_t)(gd.node0 + r) * H + head];
+  }
+  __syncthreads();
+  float* a = wbuf + (size_t)warp * (2 * C + 2 * n4);
+  float* b = a + C;
+  float* w1 = b + C;     // MODE 0: alpha * dp   | MODE 1: ds
+  float* w2 = w1 + n4;   // MODE 0: alpha        | MODE 1: alpha
+  for (int r = warp; r < n; r += TW) {
+    const size_t node = (size_t)(gd.node0 + r);
+    for (int c = lane; c < C; c += 32) {
+      if (MODE == 0) { a[c] = qkvs[node * ld + head * C + c] * scale; b[c] = dO[node * ldo + head * C + c]; }
+      else { a[c] = qkvs[node * ld + HC + head * C + c]; b[c] = qkvs[node * ld + 2 * HC + head * C + c]; }
+    }
+    __syncwarp();
+    float dsum = 0.f;
+    for (int base = 0; base < n; base += 32) {
+      const int o = base + lane;   // the other end of the edge: source j (MODE 0) / target i (MODE 1)
+      const bool valid = o < n && (MODE == 0 ? bm_bit(bm, gd.bm_words, r, o) : bm_bit(bm, gd.bm_words, o, r));
+      float x1 = 0.f, x2 = 0.f;
+      if (valid) {
+        const float* ar = A + o * P;
+        const float* br = B + o * P;
+        // float4 reads: the per-lane row reads cost the same shared-memory bandwidth, the broadcast reads of the
+        // row's own vector a quarter; four independent FMA chains per dot product
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 2
+        for (int c = 0; c < C; c += 4) {
+          const float4 av = *reinterpret_cast<const float4*>(ar + c), bv = *reinterpret_cast<const float4*>(br + c);
+          const float4 aa = *reinterpret_cast<const float4*>(a + c), bb = *reinterpret_cast<const float4*>(b + c);
+          s0 = fmaf(av.x, aa.x, s0); s1 = fmaf(av.y, aa.y, s1); s2 = fmaf(av.z, aa.z, s2); s3 = fmaf(av.w, aa.w, s3);
+          d0 = fmaf(bv.x, bb.x, d0); d1 = fmaf(bv.y, bb.y, d1); d2 = fmaf(bv.z, bb.z, d2); d3 = fmaf(bv.w, bb.w, d3);
+        }
+        const float s = (s0 + s1) + (s2 + s3), dp = (d0 + d1) + (d2 + d3);
+        if (MODE == 0) {
+          const float alpha = expf(s - mrow[r]) * lrow[r];
+          x1 = alpha * dp; x2 = alpha;
+        } else {
+          const float alpha = expf(s * scale - mrow[o]) * lrow[o];
+          x1 = alpha * (dp - drow[o]); x2 = alpha;
+        }
+      }
+      if (o < n) { w1[o] = x1; w2[o] = x2; }
+      if (MODE == 0) dsum += warp_sum(x1);
+    }
+    __syncwarp();
+    // lane-per-channel accumulation over the row's neighbours (zeros for absent edges)
+    for (int c = lane; c < C; c += 32) {
+      float acc1 = 0.f, acc2 = 0.f, acc1b = 0.f, acc2b = 0.f;
+      int o = 0;
+      for (; o + 4 <= n; o += 4) {   // the per-neighbour weights are broadcast four at a time
+        const float4 x1 = *reinterpret_cast<const float4*>(w1 + o), x2 = *reinterpret_cast<const float4*>(w2 + o);
+        const float a0 = A[o * P + c], a1 = A[(o + 1) * P + c], a2 = A[(o + 2) * P + c], a3 = A[(o + 3) * P + c];
+        acc1 = fmaf(x1.x, a0, acc1); acc1b = fmaf(x1.y, a1, acc1b); acc1 = fmaf(x1.z, a2, acc1); acc1b = fmaf(x1.w, a3, acc1b);
+        if (MODE == 0) {
+          acc2 = fmaf(x2.x, a0, acc2); acc2b = fmaf(x2.y, a1, acc2b); acc2 = fmaf(x2.z, a2, acc2); acc2b = fmaf(x2.w, a3, acc2b);
+        } else {
+          acc2 = fmaf(x2.x, B[o * P + c], acc2); acc2b = fmaf(x2.y, B[(o + 1) * P + c], acc2b);
+          acc2 = fmaf(x2.z, B[(o + 2) * P + c], acc2); acc2b = fmaf(x2.w, B[(o + 3) * P + c], acc2b);
+        }
+      }
+      for (; o < n; ++o) { acc1 = fmaf(w1[o], A[o * P + c], acc1); acc2 = fmaf(w2[o], MODE == 0 ? A[o * P + c] : B[o * P + c], acc2); }
+      acc1 += acc1b; acc2 += acc2b;
+      if (MODE == 0) dqkvs[node * ldg + head * C + c] = scale * (acc1 - dsum * acc2);
+      else {
+        dqkvs[node * ldg + HC + head * C + c] = scale * acc1;       // dk_j = scale sum_i ds_ij q_i
+        dqkvs[node * ldg + 2 * HC + head * C + c] = acc2;           // dv_j = sum_i alpha_ij dO_i
+      }
+    }
+    if (MODE == 0 && lane == 0) delta[node * H + head] = dsum;
+    __syncwarp();
+  }
+}
+
+size_t attn_bwd_graph_smem(int n, int C, int bm_words) {
+  const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
+  return sizeof(float) * ((size_t)2 * n * (C + 4) + (size_t)TW * (2 * C + 2 * n4) + 3 * (size_t)n) + sizeof(uint32_t) * (size_t)n * bm_words;
+}
+
 __global__ void copy_skip_grad_kernel(const float* __restrict__ dO, int ldo, float* __restrict__ dqkvs, int ldg, int n, int HC) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * HC) return;
@@ -362,6 +485,35 @@ cudaError_t launch_attn_backward(const float* qkvs, const float* dO, const CsrGr
   else if (R <= 13) DA_LAUNCH(13);
   else return cudaErrorInvalidValue;
 #undef DA_LAUNCH
+  const size_t total = (size_t)n * HC;
+  copy_skip_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dO, HC, dqkvs, ld, n, HC);
+  return cudaGetLastError();
+}
+
+bool attn_backward_dense_fits(int n_max, int C, int bm_words_max) {
+  if (C % 4) return false;
+  return attn_bwd_graph_smem(n_max, C, bm_words_max) <= (size_t)227 * 1024;
+}
+
+cudaError_t launch_attn_backward_dense(const float* qkvs, const float* dO, const void* graphs_dev, int n_graphs, int n_max,
+                                       int bm_words_max, const uint32_t* bitmap, const float* stats, int n, int H, int C,
+                                       float* dqkvs, float* delta, cudaStream_t s) {
+  if (n_graphs <= 0) return cudaSuccess;
+  const size_t smem = attn_bwd_graph_smem(n_max, C, bm_words_max);
+  if (smem > (size_t)227 * 1024) return cudaErrorInvalidValue;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_graph_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_graph_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  const int HC = H * C, ld = 4 * HC;
+  const float scale = 1.0f / sqrtf((float)C);
+  const GraphDesc* gd = reinterpret_cast<const GraphDesc*>(graphs_dev);
+  dim3 grid((unsigned)n_graphs, (unsigned)H);
+  attn_bwd_graph_kernel<0><<<grid, TW * 32, smem, s>>>(qkvs, ld, dO, HC, gd, bitmap, stats, delta, H, C, scale, dqkvs, ld);
+  attn_bwd_graph_kernel<1><<<grid, TW * 32, smem, s>>>(qkvs, ld, dO, HC, gd, bitmap, stats, delta, H, C, scale, dqkvs, ld);
   const size_t total = (size_t)n * HC;
   copy_skip_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dO, HC, dqkvs, ld, n, HC);
   return cudaGetLastError();
