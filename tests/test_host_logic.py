@@ -157,3 +157,58 @@ def test_shard_bounds_and_shard_batch():
     bad = torch.tensor([[0], [13]])
     with pytest.raises(ValueError):
         sharding.shard_batch(torch.cat([ei, bad], 1), batch, [x], 2, 1)
+
+
+def test_adafactor_descriptor_layout_matches_header():
+    """``da_adafactor_param`` is filled as a numpy record (training.FusedAdafactor): 6 pointers + 2 int32 + 2 float."""
+    import numpy as np
+
+    from diffassemble_b200.training import FusedAdafactor
+
+    opt = FusedAdafactor([torch.nn.Parameter(torch.zeros(3, 4))])
+    assert opt._DESC.itemsize == 64
+    assert [opt._DESC.fields[k][1] for k in ("p", "g", "sq_row", "sq_col", "sq", "rms", "rows", "cols", "beta2t", "rel_step")] == \
+        [0, 8, 16, 24, 32, 40, 48, 52, 56, 60]
+    header = (ROOT / "include" / "diffassemble_b200.h").read_text()
+    body = header[header.index("typedef struct da_adafactor_param {"):header.index("} da_adafactor_param;")]
+    order = re.findall(r"\b(p|g|sq_row|sq_col|sq|rms_out|rows, cols|beta2t, rel_step);", body)
+    assert order == ["p", "g", "sq_row", "sq_col", "sq", "rms_out", "rows, cols", "beta2t, rel_step"]
+    assert np.dtype(opt._DESC).alignment <= 8
+
+
+def test_fused_adafactor_falls_back_to_stock_path_on_cpu_parameters():
+    """Parameters the kernel does not cover (here: CPU tensors) take transformers' own code inside the same step,
+    so the optimizer is a drop-in even for modules that keep some state on the host."""
+    from transformers.optimization import Adafactor
+
+    from diffassemble_b200.training import FusedAdafactor
+
+    g = torch.Generator().manual_seed(0)
+    base = [torch.randn(6, 5, generator=g), torch.randn(7, generator=g)]
+    a = [torch.nn.Parameter(t.clone()) for t in base]
+    b = [torch.nn.Parameter(t.clone()) for t in base]
+    oa, ob = Adafactor(a), FusedAdafactor(b)
+    for _ in range(3):
+        for pa, pb in zip(a, b):
+            gr = torch.randn(pa.shape, generator=g)
+            pa.grad, pb.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for pa, pb in zip(a, b):
+        assert torch.equal(pa, pb)
+        assert pb.grad is not None   # gradients are left in place
+
+
+def test_pointnet_mirror_has_reference_state_dict_and_no_cpu_path():
+    enc = dab.PointNet(128)
+    ref = oracle.PointNetRef(128)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        enc.eval()(torch.zeros(1, 4, 3))
+    with pytest.raises(NotImplementedError):
+        enc.train()(torch.zeros(1, 4, 3))
+
+
+def test_prefetch_requires_feature_matrix():
+    m = dab.GNN_Diffusion(steps=10, rotation=True)
+    with pytest.raises(ValueError, match="pre-computed node features"):
+        m.prefetch(torch.zeros(4, 3, 32, 32), oracle.dense_edge_index(4), torch.zeros(4, dtype=torch.long))
