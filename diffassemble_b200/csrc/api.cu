@@ -299,7 +299,10 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
                            (hv.n_targets > 0 || lt.n_targets > 0);
     if (side_rows) {
       if (!h->side) {
-        DA_CK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking), "side stream");
+        // highest priority: its few CTAs take the next free slots instead of queueing behind the dense grid's 2048
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        DA_CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_hi), "side stream");
         DA_CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "side stream");
         DA_CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "side stream");
       }
