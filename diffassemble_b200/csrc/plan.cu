@@ -201,7 +201,8 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     if (ce != cudaSuccess) goto fail;
   }
   DA_TRY(cudaStreamSynchronize(s));
-  if (plan->n_tiles > 0 && plan->residual.E > 0 && !getenv("DA_NO_PROMOTE")) {
+  // (the pass walks the residual on the host: skipped when that is not "small", i.e. a mostly sparse batch)
+  if (plan->n_tiles > 0 && plan->residual.E > 0 && plan->residual.E <= (int64_t)8 << 20 && !getenv("DA_NO_PROMOTE")) {
     // ---- promotion pass (host): residual in-edges of dense-tile rows with multiplicity one move into the bitmap
     // on extra columns (see DensePlan); the residual CSR is rewritten without them
     const int64_t Er = plan->residual.E;
