@@ -70,6 +70,21 @@ def bytes_per_node(D=1152, Dv=1088, C=4, hid=256):
     return 4 * (Dv + C + C + 3 * D + 4 * shc + 2 * 3 * hid)
 
 
+def step_work(M, E_tot, ms_per_step, pk, passes):
+    sec = ms_per_step * 1e-3
+    f_gemm, f_attn = M * flops_per_node(), E_tot * flops_per_edge()
+    byt = bytes_per_node() * M + 16 * E_tot
+    w = {"gflop_per_step": (f_gemm + f_attn) / 1e9, "compulsory_gb_per_step": byt / 1e9,
+         "achieved_tflops_total": (f_gemm + f_attn) / sec / 1e12,
+         "achieved_tflops_gemm": f_gemm / sec / 1e12, "achieved_tflops_attention": f_attn / sec / 1e12,
+         "achieved_hbm_gbs_compulsory": byt / sec / 1e9}
+    w["frac_tensor_peak"] = w["achieved_tflops_total"] / pk["tensor_sustained"]
+    w["frac_tensor_peak_at_%d_passes" % passes] = w["achieved_tflops_total"] * passes / pk["tensor_sustained"]
+    w["frac_hbm_peak"] = w["achieved_hbm_gbs_compulsory"] / pk["hbm"]
+    w["step_roofline_frac"] = max(w["frac_tensor_peak"], w["frac_hbm_peak"])
+    return w
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -383,9 +398,9 @@ def run_b200(args):
         "clocks": clk.summary(),
         "e2e": e2e,
         "roofline": roof,
-        "work": {"gflop_per_step": (M * flops_per_node() + E_tot * flops_per_edge()) / 1e9,
-                 "compulsory_gb_per_step": (bytes_per_node() * M + 16 * E_tot) / 1e9,
-                 "achieved_tflops_total": (M * flops_per_node() + E_tot * flops_per_edge()) / (ms_per_step * 1e-3) / 1e12},
+        # the three whole-step rates and their fractions of the respective peaks (algorithmic
+        # work of the reference formulation / measured step time); the largest is the step's roofline fraction
+        "work": step_work(M, E_tot, ms_per_step, pk, passes),
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(w, steps=args.cpu_steps)
