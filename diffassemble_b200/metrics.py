@@ -42,3 +42,51 @@ def greedy_cost_assignment_batched(pos1: torch.Tensor, pos2: torch.Tensor, graph
 def greedy_cost_assignment(pos1: torch.Tensor, pos2: torch.Tensor) -> torch.Tensor:
     n = pos1.shape[0]
     return greedy_cost_assignment_batched(pos1, pos2, torch.tensor([0, n], dtype=torch.int32))
+
+
+def real_grid(n_rows: int, n_cols: int, device) -> torch.Tensor:
+    """The target cell centres of an ``n_rows x n_cols`` puzzle exactly as ``spatial_diffusion.py:791-794`` builds them
+    (``linspace`` per axis, ``meshgrid(x, y, indexing="xy")``, rows flattened first)."""
+    y = torch.linspace(-1, 1, n_rows, device=device)
+    x = torch.linspace(-1, 1, n_cols, device=device)
+    xy = torch.stack(torch.meshgrid(x, y, indexing="xy"), -1)
+    return xy.reshape(-1, 2)
+
+
+@torch.no_grad()
+def puzzle_accuracy(img: torch.Tensor, x_gt: torch.Tensor, batch: torch.Tensor, patches_dim, rotation: bool):
+    """Validation metric of ``spatial_diffusion.py:783-856`` / ``:921-950`` for a WHOLE batch.
+
+    The reference loops over the puzzles on the host and runs two ``greedy_cost_assignment`` calls per puzzle (each an
+    O(n) host-synchronising loop); here the predicted and the ground-truth assignments of every puzzle are ONE
+    ``da_greedy_cost_assignment`` launch each.  Returns ``(correct [B] bool, piece_accuracy [N] bool)``:
+    a piece counts when it lands on the same grid cell as in the ground truth (and, with ``rotation``, when the cosine
+    between predicted and true rotation vectors exceeds cos(pi/4)); a puzzle is correct when all its pieces are."""
+    dev = img.device
+    B = int(batch.max()) + 1
+    counts = torch.bincount(batch, minlength=B)
+    ptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(counts, 0)
+    dims = patches_dim.tolist() if torch.is_tensor(patches_dim) else [list(d) for d in patches_dim]
+    grid = torch.cat([real_grid(int(r), int(c), dev) for r, c in dims])
+    if grid.shape[0] != img.shape[0]:
+        raise ValueError("patches_dim does not match the number of pieces per puzzle")
+    gp = ptr.to(torch.int32)
+    ass_gt = greedy_cost_assignment_batched(x_gt[:, :2], grid, gp)
+    ass_pr = greedy_cost_assignment_batched(img[:, :2], grid, gp)
+    puzzle_of = batch.to(torch.int64)
+    base = ptr[:-1][puzzle_of]                       # the kernel's indices are local to each puzzle, rows in greedy order
+
+    def cell_of_piece(ass):                          # == ass[sort(ass[:, 0])][:, 1] per puzzle (:796-801)
+        cell = torch.empty(img.shape[0], dtype=torch.int64, device=dev)
+        cell[base + ass[:, 0]] = ass[:, 1]
+        return cell
+
+    piece_ok = cell_of_piece(ass_gt) == cell_of_piece(ass_pr)
+    if rotation:
+        import math
+
+        rot_ok = torch.cosine_similarity(img[:, 2:], x_gt[:, 2:]) > math.cos(math.pi / 4)
+        piece_ok = piece_ok & rot_ok
+    wrong = torch.zeros(B, dtype=torch.int64, device=dev).index_add_(0, puzzle_of, (~piece_ok).to(torch.int64))
+    return wrong == 0, piece_ok

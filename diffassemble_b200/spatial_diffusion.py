@@ -467,10 +467,37 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
         return self.prediction_step(batch, batch_idx)
 
     def validation_step(self, batch, batch_idx):
-        """Sampling half of ``spatial_diffusion.py:775-790``; the assignment metric that
-        follows (greedy_cost_assignment, :179-216) is scope row N2."""
+        """``spatial_diffusion.py:775-904`` without the image dumps: sample, then the assignment metric (scope row N2)
+        for the whole batch in two kernel launches; running sums are kept in ``self.val_stats`` under the reference's
+        metric names (``overall_acc``, ``overall__piece_acc``, ``(r, c)_acc`` ...) and logged."""
+        from .metrics import puzzle_accuracy
+
         imgs, _ = self.p_sample_loop(batch.x.shape, batch.patches, batch.edge_index, batch=batch.batch)
-        return imgs[-1]
+        img = imgs[-1]
+        dims = getattr(batch, "patches_dim", None)
+        if dims is not None:
+            correct, piece_ok = puzzle_accuracy(img, batch.x, batch.batch, dims, self.rotation)
+            stats = self.__dict__.setdefault("val_stats", {})
+            dims_l = dims.tolist() if torch.is_tensor(dims) else [list(d) for d in dims]
+            correct_h, piece_h = correct.cpu(), piece_ok.cpu()
+            sizes = torch.bincount(batch.batch.cpu()).tolist()
+            off = 0
+            for i, (d, n) in enumerate(zip(dims_l, sizes)):
+                for key, val, cnt in ((f"{tuple(d)}_acc", float(correct_h[i]), 1), ("overall_acc", float(correct_h[i]), 1),
+                                      (f"{tuple(d)}__piece_acc", float(piece_h[off:off + n].sum()), n),
+                                      ("overall__piece_acc", float(piece_h[off:off + n].sum()), n)):
+                    acc = stats.setdefault(key, [0.0, 0])
+                    acc[0] += val; acc[1] += cnt
+                off += n
+            self.log_dict({k: v[0] / max(v[1], 1) for k, v in stats.items()})
+        return img
+
+    def validation_epoch_end(self, outputs=None) -> None:
+        stats = self.__dict__.get("val_stats", {})
+        self.log_dict({k: v[0] / max(v[1], 1) for k, v in stats.items()})
+
+    def test_epoch_end(self, outputs=None) -> None:
+        return self.validation_epoch_end(outputs)
 
     def test_step(self, batch, batch_idx):
         return self.validation_step(batch, batch_idx)

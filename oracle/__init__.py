@@ -46,5 +46,5 @@ from .topology import (  # noqa: F401
     generate_random_expander,
     batch_graphs,
 )
-from .assignment import greedy_cost_assignment_ref  # noqa: F401,E402
+from .assignment import greedy_cost_assignment_ref, puzzle_accuracy_ref  # noqa: F401,E402
 from .pointnet import PointNetRef  # noqa: F401,E402

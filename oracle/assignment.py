@@ -31,3 +31,32 @@ def greedy_cost_assignment_ref(pos1: torch.Tensor, pos2: torch.Tensor, separatel
         mask[i, :] = 0
         mask[:, j] = 0
     return assignments[:counter]
+
+
+def puzzle_accuracy_ref(img, x_gt, batch, patches_dim, rotation):
+    """The per-puzzle metric loop of ``spatial_diffusion.py:783-856`` (test infrastructure): returns
+    ``(correct [B] bool, piece_accuracy [N] bool)``."""
+    import math
+
+    correct, piece = [], []
+    for i in range(int(batch.max()) + 1):
+        idx = torch.where(batch == i)[0]
+        gt_pos, pos = x_gt[idx, :2], img[idx, :2]
+        n_patches = patches_dim[i].tolist() if torch.is_tensor(patches_dim) else list(patches_dim[i])
+        y = torch.linspace(-1, 1, n_patches[0])
+        x = torch.linspace(-1, 1, n_patches[1])
+        xy = torch.stack(torch.meshgrid(x, y, indexing="xy"), -1)
+        real_grid = xy.reshape(-1, 2)                      # einops "x y c -> (x y) c"
+        gt_ass = greedy_cost_assignment_ref(gt_pos, real_grid)
+        gt_ass = gt_ass[torch.sort(gt_ass[:, 0])[1]]
+        pred_ass = greedy_cost_assignment_ref(pos, real_grid)
+        pred = pred_ass[torch.sort(pred_ass[:, 0])[1]][:, 1]
+        ok = gt_ass[:, 1] == pred
+        c = bool(ok.all())
+        if rotation:
+            rot_ok = torch.cosine_similarity(img[idx, 2:], x_gt[idx, 2:]) > math.cos(math.pi / 4)
+            c = c and bool(rot_ok.all())
+            ok = rot_ok * ok
+        correct.append(c)
+        piece.append(ok)
+    return torch.tensor(correct), torch.cat(piece)

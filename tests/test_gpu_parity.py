@@ -610,3 +610,31 @@ def test_training_gradients_with_dense_tile_forward(mode):
     assert checked >= 30
     graph = mod._train_graph[1]
     assert graph._lib is not None   # the TrainGraph was built with the batch vector (dense plan attached)
+
+
+def test_batched_validation_metric_matches_reference_loop():
+    """The validation metric (spatial_diffusion.py:783-856): two batched assignment launches against the reference's
+    per-puzzle loop, on solved, nearly solved and scrambled puzzles of different shapes, with rotations."""
+    from diffassemble_b200.metrics import puzzle_accuracy, real_grid
+
+    g = torch.Generator().manual_seed(5)
+    dims = [(6, 6), (4, 5), (12, 12), (3, 7)]
+    xs, imgs, batch = [], [], []
+    for i, (r, c) in enumerate(dims):
+        n = r * c
+        grid = real_grid(r, c, "cpu")
+        ang = torch.rand(n, generator=g) * 6.283
+        gt = torch.cat([grid[torch.randperm(n, generator=g)], torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)
+        pred = gt.clone()
+        pred[:, :2] += (0.05, 0.02, 0.6, 0.3)[i] / max(r, c) * torch.randn(n, 2, generator=g)   # puzzle 2: many swaps
+        if i == 1:
+            pred[3, 2:] = -pred[3, 2:]          # one piece rotated by pi: rotation check fails for it only
+        xs.append(gt); imgs.append(pred); batch.append(torch.full((n,), i))
+    x_gt, img, batch = torch.cat(xs), torch.cat(imgs), torch.cat(batch)
+    pd = torch.tensor(dims)
+    for rotation in (True, False):
+        want_c, want_p = oracle.puzzle_accuracy_ref(img, x_gt, batch, pd, rotation)
+        got_c, got_p = puzzle_accuracy(img.to(DEV), x_gt.to(DEV), batch.to(DEV), pd, rotation)
+        assert torch.equal(got_c.cpu(), want_c), rotation
+        assert torch.equal(got_p.cpu(), want_p), rotation
+    assert bool(want_c[0]) and not bool(want_c[2])   # the solved puzzle is correct, the scrambled one is not
