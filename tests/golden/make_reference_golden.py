@@ -215,14 +215,14 @@ def _identity_features(x):
 
 
 def case_2d(sd2, name, sizes, architecture, virt_nodes, sampling, mean_type, ratio, kind="dense", degree="60%",
-            T=300, rotation=True, loop_T=None, cfg=(0.0, 0.0), seed=0):
+            T=300, rotation=True, loop_T=None, cfg=(0.0, 0.0), seed=0, scheduler="LINEAR"):
     from common import reseed_parameters, synth_graph_batch
 
     torch.manual_seed(seed)
     ref = sd2.GNN_Diffusion(steps=T, sampling=sampling, rotation=rotation, architecture=architecture,
                             virt_nodes=virt_nodes, model_mean_type=sd2.ModelMeanType[mean_type],
                             inference_ratio=ratio, noise_weight=1.0, classifier_free_prob=cfg[0],
-                            classifier_free_w=cfg[1]).eval()
+                            classifier_free_w=cfg[1], scheduler=sd2.ModelScheduler[scheduler]).eval()
     ref.visual_features = _identity_features
     reseed_parameters(ref, seed)
     C = 4 if rotation else 2
@@ -233,7 +233,8 @@ def case_2d(sd2, name, sizes, architecture, virt_nodes, sampling, mean_type, rat
     x = torch.randn(M, C, generator=g)
     t = torch.full((M,), T - 1, dtype=torch.long)
     d = dict(kind="2d", sizes=sizes, architecture=architecture, virt_nodes=virt_nodes, sampling=sampling,
-             mean_type=mean_type, ratio=ratio, T=T, rotation=rotation, cfg=cfg, seed=seed, edge_index=ei, batch=batch,
+             mean_type=mean_type, ratio=ratio, T=T, rotation=rotation, cfg=cfg, seed=seed, scheduler=scheduler,
+             edge_index=ei, batch=batch,
              feats=feats, x=x, t=t, weight_checksum=weight_checksum(ref))
     with torch.no_grad():
         out, atts = ref.forward_with_feats(x, t, None, ei, feats, batch, return_attentions=True)
@@ -421,6 +422,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":
         case_pointnet()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "schedulers":
+        case_2d(sd2, "dense_cosine_ddim", [20, 12], "transformer", 0, "DDIM", "START_X", 10, scheduler="COSINE", seed=4)
+        case_2d(sd2, "dense_cosdisc_ddpm", [16], "transformer", 0, "DDPM", "EPSILON", 1, T=100, scheduler="COSINE_DISCRETE", seed=5)
+        sys.exit(0)
     case_pointnet()
     case_assignment(sd2)
     case_training(sd2, "dense", [36, 25], "transformer", 0, "EPSILON")
@@ -440,6 +445,9 @@ if __name__ == "__main__":
     case_2d(sd2, "exph_v0_eps_ddim", [48, 50], "exophormer", 0, "DDIM", "EPSILON", 10, kind="expander", degree="40%")
     # no-rotation variant (2 channels) and classifier-free guidance
     case_2d(sd2, "dense_norot_cfg_ddim", [25, 16], "transformer", 0, "DDIM", "START_X", 10, rotation=False, cfg=(0.1, 0.5))
+    # the other two beta schedules through the samplers (cosine: DDIM x0; discrete cosine: DDPM eps)
+    case_2d(sd2, "dense_cosine_ddim", [20, 12], "transformer", 0, "DDIM", "START_X", 10, scheduler="COSINE", seed=4)
+    case_2d(sd2, "dense_cosdisc_ddpm", [16], "transformer", 0, "DDPM", "EPSILON", 1, T=100, scheduler="COSINE_DISCRETE", seed=5)
     # c4-like: ragged 3-D fragments, SE(3) head + SO(3) DDIM
     case_3d(sd3, "se3_ragged", [2, 5, 20, 11, 7])
     case_topology()

@@ -25,7 +25,8 @@ def product_2d(d, gemm, attn, steps=None):
     mod = dab.GNN_Diffusion(
         steps=steps or d["T"], sampling=d["sampling"], rotation=d["rotation"], architecture=d["architecture"],
         virt_nodes=d["virt_nodes"], model_mean_type=dab.ModelMeanType[d["mean_type"]], inference_ratio=d["ratio"],
-        noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1], gemm_mode=gemm, attn_mode=attn)
+        noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1],
+        scheduler=dab.ModelScheduler[d.get("scheduler", "LINEAR")], gemm_mode=gemm, attn_mode=attn)
     reseed_parameters(mod, d["seed"])
     return mod.to(DEV)
 

@@ -18,7 +18,7 @@ from common import quat_rel_err, rel_err, reseed_parameters
 
 G = Path(__file__).resolve().parent / "golden"
 CASES_2D = ["c1_dense36_ddpm", "c2_dense144_ddpm", "dense_ragged_ddim", "exph_2x64_v4_ddim", "exph_ragged_v8_ddim",
-            "exph_v0_eps_ddim", "dense_norot_cfg_ddim"]
+            "exph_v0_eps_ddim", "dense_norot_cfg_ddim", "dense_cosine_ddim", "dense_cosdisc_ddpm"]
 EXACT = 2e-6  # same torch, same op order: only the reduction order of a few sums may differ
 
 
@@ -30,7 +30,8 @@ def oracle_2d(d, steps=None):
     ref = oracle.GNNDiffusionRef(
         steps=steps or d["T"], sampling=d["sampling"], rotation=d["rotation"], architecture=d["architecture"],
         virt_nodes=d["virt_nodes"], model_mean_type=oracle.ModelMeanType[d["mean_type"]], inference_ratio=d["ratio"],
-        noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1]).eval()
+        noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1],
+        scheduler=oracle.ModelScheduler[d.get("scheduler", "LINEAR")]).eval()
     return reseed_parameters(ref, d["seed"])
 
 
