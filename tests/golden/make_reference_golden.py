@@ -269,12 +269,12 @@ def case_2d(sd2, name, sizes, architecture, virt_nodes, sampling, mean_type, rat
     print(f"ref_{name}: M={M} E={ei.shape[1]} out={tuple(out.shape)} |out|max={out.abs().max():.4f}")
 
 
-def case_3d(sd3, name, sizes, T=300, ratio=10, seed=0):
+def case_3d(sd3, name, sizes, T=300, ratio=10, seed=0, architecture="transformer"):
     from common import reseed_parameters, synth_graph_batch
 
     torch.manual_seed(seed)
     ref = sd3.GNN_Diffusion(steps=T, sampling="DDIM", backbone="pointnet", inference_ratio=ratio,
-                            model_mean_type=sd3.ModelMeanType.START_X, noise_weight=1.0).eval()
+                            model_mean_type=sd3.ModelMeanType.START_X, noise_weight=1.0, architecture=architecture).eval()
     ref.pcd_features = _identity_features
     reseed_parameters(ref, seed)
     ei, batch = synth_graph_batch(sizes, kind="dense")
@@ -283,7 +283,7 @@ def case_3d(sd3, name, sizes, T=300, ratio=10, seed=0):
     feats = torch.randn(M, 128, generator=g)
     q = torch.nn.functional.normalize(torch.randn(M, 4, generator=g), dim=-1)
     x = torch.cat([q, torch.randn(M, 3, generator=g)], 1)
-    d = dict(kind="3d", sizes=sizes, T=T, ratio=ratio, seed=seed, edge_index=ei, batch=batch, feats=feats, x=x,
+    d = dict(kind="3d", sizes=sizes, T=T, ratio=ratio, seed=seed, architecture=architecture, edge_index=ei, batch=batch, feats=feats, x=x,
              weight_checksum=weight_checksum(ref))
     with torch.no_grad():
         steps = [T - ratio, (T // 2 // ratio) * ratio, 0]
@@ -422,6 +422,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":
         case_pointnet()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "se3_exph":
+        case_3d(sd3, "se3_exph_v8", [12, 20, 5], seed=6, architecture="exophormer")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "schedulers":
         case_2d(sd2, "dense_cosine_ddim", [20, 12], "transformer", 0, "DDIM", "START_X", 10, scheduler="COSINE", seed=4)
         case_2d(sd2, "dense_cosdisc_ddpm", [16], "transformer", 0, "DDPM", "EPSILON", 1, T=100, scheduler="COSINE_DISCRETE", seed=5)
@@ -450,4 +453,6 @@ if __name__ == "__main__":
     case_2d(sd2, "dense_cosdisc_ddpm", [16], "transformer", 0, "DDPM", "EPSILON", 1, T=100, scheduler="COSINE_DISCRETE", seed=5)
     # c4-like: ragged 3-D fragments, SE(3) head + SO(3) DDIM
     case_3d(sd3, "se3_ragged", [2, 5, 20, 11, 7])
+    # 3-D with the exophormer backbone (Eff_GAT_3d default virt_nodes = 8, efficient_gat_3d.py:65)
+    case_3d(sd3, "se3_exph_v8", [12, 20, 5], seed=6, architecture="exophormer")
     case_topology()

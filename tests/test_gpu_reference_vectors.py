@@ -68,10 +68,12 @@ def test_cuda_matches_reference_sampling_loop(name, gemm, attn):
 
 
 @pytest.mark.parametrize("gemm,attn", [("fp32", "csr"), ("bf16x3", "auto")])
-def test_cuda_matches_reference_3d(gemm, attn):
-    d = torch.load(G / "ref_se3_ragged.pt")
+@pytest.mark.parametrize("name", ["se3_ragged", "se3_exph_v8"])
+def test_cuda_matches_reference_3d(name, gemm, attn):
+    d = torch.load(G / f"ref_{name}.pt")
     mod = dab.GNN_Diffusion_3d(steps=d["T"], sampling="DDIM", backbone="pointnet", inference_ratio=d["ratio"],
-                               model_mean_type=dab.ModelMeanType.START_X, noise_weight=1.0, gemm_mode=gemm, attn_mode=attn)
+                               model_mean_type=dab.ModelMeanType.START_X, noise_weight=1.0,
+                               architecture=d.get("architecture", "transformer"), gemm_mode=gemm, attn_mode=attn)
     reseed_parameters(mod, d["seed"])
     mod = mod.to(DEV)
     x, ei, feats, batch = (d[k].to(DEV) for k in ("x", "edge_index", "feats", "batch"))

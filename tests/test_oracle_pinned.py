@@ -66,10 +66,12 @@ def test_oracle_matches_reference_loop(name):
         assert rel_err(got, want) < EXACT * (k + 1), k
 
 
-def test_oracle_matches_reference_3d():
-    d = torch.load(G / "ref_se3_ragged.pt")
+@pytest.mark.parametrize("name", ["se3_ragged", "se3_exph_v8"])
+def test_oracle_matches_reference_3d(name):
+    d = torch.load(G / f"ref_{name}.pt")
     ref = oracle.GNNDiffusion3dRef(steps=d["T"], backbone="pointnet", inference_ratio=d["ratio"],
-                                   model_mean_type=oracle.ModelMeanType.START_X, noise_weight=1.0).eval()
+                                   model_mean_type=oracle.ModelMeanType.START_X, noise_weight=1.0,
+                                   architecture=d.get("architecture", "transformer")).eval()
     reseed_parameters(ref, d["seed"])
     with torch.no_grad():
         for ti, want_f, want_s in zip(d["step_ts"], d["fwd_out"], d["step_out"]):
