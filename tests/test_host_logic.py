@@ -212,3 +212,24 @@ def test_prefetch_requires_feature_matrix():
     m = dab.GNN_Diffusion(steps=10, rotation=True)
     with pytest.raises(ValueError, match="pre-computed node features"):
         m.prefetch(torch.zeros(4, 3, 32, 32), oracle.dense_edge_index(4), torch.zeros(4, dtype=torch.long))
+
+
+def test_mirror_schedule_buffers_match_reference_modules():
+    """a1: every registered length-T buffer of the mirror modules (2-D and 3-D, three schedulers, three T) equals the
+    buffer of the REFERENCE module (tests/golden/ref_schedules.pt, written by executing the reference)."""
+    from pathlib import Path
+
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "ref_schedules.pt")
+    checked = 0
+    for key, bufs in d.items():
+        tag, sch, T = key.split("/")
+        if tag == "2d":
+            m = dab.GNN_Diffusion(steps=int(T), scheduler=dab.ModelScheduler[sch], rotation=True)
+        else:
+            m = dab.GNN_Diffusion_3d(steps=int(T), scheduler=dab.ModelScheduler[sch], backbone="pointnet", sampling="DDIM")
+        mine = dict(m.named_buffers())
+        for name, want in bufs.items():
+            assert name in mine, (key, name)
+            assert torch.allclose(mine[name], want, rtol=1e-6, atol=0), (key, name)
+            checked += 1
+    assert checked >= 100
