@@ -233,3 +233,20 @@ def test_mirror_schedule_buffers_match_reference_modules():
             assert torch.allclose(mine[name], want, rtol=1e-6, atol=0), (key, name)
             checked += 1
     assert checked >= 100
+
+
+@pytest.mark.parametrize("name,V", [("exph_2x64_v4_ddim", 4), ("exph_ragged_v8_ddim", 8), ("exph_v0_eps_ddim", 0)])
+def test_mirror_virtual_wiring_equals_reference_run(name, V):
+    """a10: ``Exophormer_GNN.extend_graph`` (host, once per batch) reproduces, edge for edge and in order, the edge list
+    the REFERENCE's ``Exophormer_GNN.forward`` handed to its last TransformerConv (returned with the attention weights
+    and stored in the fixture by tests/golden/make_reference_golden.py)."""
+    from pathlib import Path
+
+    d = torch.load(Path(__file__).resolve().parent / "golden" / f"ref_{name}.pt")
+    gnn = dab.Exophormer_GNN(1152, hidden_dim=256, heads=8, output_size=1152, n_layers=4, virt_nodes=V)
+    ext, num_total, virt_ids = gnn.extend_graph(d["edge_index"], d["batch"])
+    assert torch.equal(ext, d["alpha_edge_index"])
+    n_graphs = int(d["batch"].max()) + 1
+    assert num_total == len(d["batch"]) + V * n_graphs
+    if V > 0:
+        assert torch.equal(virt_ids.long(), torch.arange(V).repeat(n_graphs))
