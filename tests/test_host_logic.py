@@ -250,3 +250,24 @@ def test_mirror_virtual_wiring_equals_reference_run(name, V):
     assert num_total == len(d["batch"]) + V * n_graphs
     if V > 0:
         assert torch.equal(virt_ids.long(), torch.arange(V).repeat(n_graphs))
+
+
+def test_mirror_topology_equals_reference_generator_output():
+    """a14: the host mirror of ``generate_random_expander`` against edge lists the REFERENCE function produced
+    (tests/golden/ref_topology.pt): the single-attempt output exactly; the 5-attempt output (whose winner the reference
+    itself picks by ARPACK noise) as a member of the candidate set."""
+    from pathlib import Path
+
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "ref_topology.pt")
+    for key, want in d.items():
+        kind, n, deg, seed = key.split("/")
+        n, seed = int(n), int(seed)
+        deg = deg if deg.endswith("%") else int(deg)
+        if kind == "expander1":
+            got = topology.expander_edge_index(n, deg, rng=np.random.default_rng(seed))   # [2, E]
+            assert torch.equal(got.t(), want), key
+        else:
+            dnum = topology.resolve_degree(n, deg)
+            rng = np.random.default_rng(seed)
+            cands = [torch.as_tensor(np.stack(topology.random_regular_edges(n, dnum, rng), 1)) for _ in range(5)]
+            assert any(torch.equal(c, want) for c in cands), key
