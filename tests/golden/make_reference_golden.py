@@ -394,6 +394,21 @@ def randomize_batchnorm(module, seed=0):
     return module
 
 
+def case_state_dict_keys(sd2, sd3):
+    """state_dict layout (key -> shape) of the reference modules: what a checkpoint written by the reference contains."""
+    d = {}
+    for arch, V in (("transformer", 0), ("exophormer", 4), ("exophormer", 8)):
+        m = sd2.GNN_Diffusion(steps=30, rotation=True, architecture=arch, virt_nodes=V)
+        d[f"2d/{arch}/{V}"] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m = sd2.GNN_Diffusion(steps=30, rotation=False, architecture="transformer")
+    d["2d/norot"] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    for arch in ("transformer", "exophormer"):
+        m = sd3.GNN_Diffusion(steps=30, sampling="DDIM", backbone="pointnet", architecture=arch)
+        d[f"3d/{arch}"] = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    torch.save(d, HERE / "ref_state_dict_keys.pt")
+    print("ref_state_dict_keys:", {k: len(v) for k, v in d.items()})
+
+
 def case_pointnet():
     """``PointNet`` fragment encoder (backbones/pointnet.py:8-43, N4) in eval mode, executed from the reference file."""
     from common import reseed_parameters
@@ -422,6 +437,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":
         case_pointnet()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "keys":
+        case_state_dict_keys(sd2, sd3)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "se3_exph":
         case_3d(sd3, "se3_exph_v8", [12, 20, 5], seed=6, architecture="exophormer")
         sys.exit(0)
@@ -430,6 +448,7 @@ if __name__ == "__main__":
         case_2d(sd2, "dense_cosdisc_ddpm", [16], "transformer", 0, "DDPM", "EPSILON", 1, T=100, scheduler="COSINE_DISCRETE", seed=5)
         sys.exit(0)
     case_pointnet()
+    case_state_dict_keys(sd2, sd3)
     case_assignment(sd2)
     case_training(sd2, "dense", [36, 25], "transformer", 0, "EPSILON")
     case_training(sd2, "exph_v4", [36, 64], "exophormer", 4, "START_X", kind="expander", seed=1)

@@ -271,3 +271,24 @@ def test_mirror_topology_equals_reference_generator_output():
             rng = np.random.default_rng(seed)
             cands = [torch.as_tensor(np.stack(topology.random_regular_edges(n, dnum, rng), 1)) for _ in range(5)]
             assert any(torch.equal(c, want) for c in cands), key
+
+
+def test_mirror_state_dict_layout_equals_reference_checkpoint_layout():
+    """b: a checkpoint written by the reference loads into the mirror: every key of the reference's ``state_dict``
+    (tests/golden/ref_state_dict_keys.pt, from the reference modules themselves) exists in the mirror with the same
+    shape -- for the 3-D module including the PointNet encoder and the ``identity`` buffer -- and the mirror adds
+    nothing of its own.  (The 2-D visual encoder is an ``nn.Identity`` in the fixture: timm is absent.)"""
+    from pathlib import Path
+
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "ref_state_dict_keys.pt")
+    for key, want in d.items():
+        parts = key.split("/")
+        if parts[0] == "2d":
+            if parts[1] == "norot":
+                m = dab.GNN_Diffusion(steps=30, rotation=False, architecture="transformer")
+            else:
+                m = dab.GNN_Diffusion(steps=30, rotation=True, architecture=parts[1], virt_nodes=int(parts[2]))
+        else:
+            m = dab.GNN_Diffusion_3d(steps=30, sampling="DDIM", backbone="pointnet", architecture=parts[1])
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert mine == want, (key, sorted(set(mine) ^ set(want))[:8])
