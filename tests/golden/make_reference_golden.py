@@ -409,6 +409,39 @@ def case_state_dict_keys(sd2, sd3):
     print("ref_state_dict_keys:", {k: len(v) for k, v in d.items()})
 
 
+def case_signatures(sd2, sd3):
+    """Constructor and public-method signatures of the reference classes on the path (names + defaults)."""
+    import inspect
+
+    from model.backbones.efficient_gat import Eff_GAT
+    from model.backbones.efficient_gat_3d import Eff_GAT_3d
+    from model.backbones.exophormer_gnn import Exophormer_GNN
+    from model.backbones.pointnet import PointNet
+    from model.backbones.Transformer_GNN import Transformer_GNN
+
+    def sig(fn):
+        out = []
+        for name, p in inspect.signature(fn).parameters.items():
+            if name in ("self", "args", "kwargs"):
+                continue
+            dflt = None if p.default is inspect._empty else (p.default.name if hasattr(p.default, "name") and hasattr(p.default, "value") else repr(p.default))
+            out.append((name, p.default is not inspect._empty, dflt))
+        return out
+
+    d = {"GNN_Diffusion.__init__": sig(sd2.GNN_Diffusion.__init__), "GNN_Diffusion_3d.__init__": sig(sd3.GNN_Diffusion.__init__),
+         "Eff_GAT.__init__": sig(Eff_GAT.__init__), "Eff_GAT_3d.__init__": sig(Eff_GAT_3d.__init__),
+         "Transformer_GNN.__init__": sig(Transformer_GNN.__init__), "Exophormer_GNN.__init__": sig(Exophormer_GNN.__init__),
+         "PointNet.__init__": sig(PointNet.__init__),
+         "GNN_Diffusion.forward_with_feats": sig(sd2.GNN_Diffusion.forward_with_feats),
+         "GNN_Diffusion.p_sample_loop": sig(sd2.GNN_Diffusion.p_sample_loop),
+         "GNN_Diffusion.p_losses": sig(sd2.GNN_Diffusion.p_losses),
+         "GNN_Diffusion_3d.forward_with_feats": sig(sd3.GNN_Diffusion.forward_with_feats),
+         "Eff_GAT.forward_with_feats": sig(Eff_GAT.forward_with_feats),
+         "Eff_GAT_3d.forward_with_feats": sig(Eff_GAT_3d.forward_with_feats)}
+    torch.save(d, HERE / "ref_signatures.pt")
+    print("ref_signatures:", {k: len(v) for k, v in d.items()})
+
+
 def case_pointnet():
     """``PointNet`` fragment encoder (backbones/pointnet.py:8-43, N4) in eval mode, executed from the reference file."""
     from common import reseed_parameters
@@ -437,6 +470,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pointnet":
         case_pointnet()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "signatures":
+        case_signatures(sd2, sd3)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "keys":
         case_state_dict_keys(sd2, sd3)
         sys.exit(0)
@@ -449,6 +485,7 @@ if __name__ == "__main__":
         sys.exit(0)
     case_pointnet()
     case_state_dict_keys(sd2, sd3)
+    case_signatures(sd2, sd3)
     case_assignment(sd2)
     case_training(sd2, "dense", [36, 25], "transformer", 0, "EPSILON")
     case_training(sd2, "exph_v4", [36, 64], "exophormer", 4, "START_X", kind="expander", seed=1)

@@ -292,3 +292,33 @@ def test_mirror_state_dict_layout_equals_reference_checkpoint_layout():
             m = dab.GNN_Diffusion_3d(steps=30, sampling="DDIM", backbone="pointnet", architecture=parts[1])
         mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
         assert mine == want, (key, sorted(set(mine) ^ set(want))[:8])
+
+
+def test_mirror_signatures_cover_reference_signatures():
+    """b: every parameter of the reference's constructors / public methods on the path (tests/golden/ref_signatures.pt,
+    read from the reference classes by ``inspect``) exists in the mirror with the same default; the mirror only adds
+    keyword arguments of its own (``gemm_mode``, ``attn_mode``, ``noise=``, ``generator=``)."""
+    import inspect
+    from pathlib import Path
+
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "ref_signatures.pt")
+    mine = {"GNN_Diffusion.__init__": dab.GNN_Diffusion.__init__, "GNN_Diffusion_3d.__init__": dab.GNN_Diffusion_3d.__init__,
+            "Eff_GAT.__init__": dab.Eff_GAT.__init__, "Eff_GAT_3d.__init__": dab.Eff_GAT_3d.__init__,
+            "Transformer_GNN.__init__": dab.Transformer_GNN.__init__, "Exophormer_GNN.__init__": dab.Exophormer_GNN.__init__,
+            "PointNet.__init__": dab.PointNet.__init__, "GNN_Diffusion.forward_with_feats": dab.GNN_Diffusion.forward_with_feats,
+            "GNN_Diffusion.p_sample_loop": dab.GNN_Diffusion.p_sample_loop, "GNN_Diffusion.p_losses": dab.GNN_Diffusion.p_losses,
+            "GNN_Diffusion_3d.forward_with_feats": dab.GNN_Diffusion_3d.forward_with_feats,
+            "Eff_GAT.forward_with_feats": dab.Eff_GAT.forward_with_feats,
+            "Eff_GAT_3d.forward_with_feats": dab.Eff_GAT_3d.forward_with_feats}
+    assert set(d) == set(mine)
+    for key, want in d.items():
+        params = inspect.signature(mine[key]).parameters
+        order = [n for n in params if n not in ("self", "args", "kwargs")]
+        ref_order = [name for name, _, _ in want]
+        assert order[: len(ref_order)] == ref_order, (key, order, ref_order)      # positional calls keep working
+        for name, has_default, dflt in want:
+            p = params[name]
+            if has_default:
+                assert p.default is not inspect._empty, (key, name)
+                got = p.default.name if hasattr(p.default, "name") and hasattr(p.default, "value") else repr(p.default)
+                assert got == dflt, (key, name, got, dflt)
