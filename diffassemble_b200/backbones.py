@@ -125,6 +125,10 @@ class _EngineMixin:
         self._weights_key = None
         self._graph_key = None
         self._feats_key = None
+        # strong references to the tensors the graph / feature keys were taken from: while a key is cached its
+        # tensors cannot be freed, so the caching allocator cannot hand their address (with _version 0 again) to
+        # the NEXT batch's same-shaped tensors and make a different topology look like the cached one
+        self._graph_refs = None
         # double buffering (prefetch): a second engine that a side stream fills with the NEXT batch
         self._spare: Optional[DenoiserEngine] = None
         self._spare_weights_key = None
@@ -165,6 +169,7 @@ class _EngineMixin:
     def invalidate(self):
         """Force weights / graph / features to be re-sent on the next call."""
         self._weights_key = self._graph_key = self._feats_key = None
+        self._graph_refs = None
         self._spare_weights_key = None
         self._prefetched = None
 
@@ -175,6 +180,7 @@ class _EngineMixin:
             eng.set_graph(ext, batch, num_real=len(batch), num_total=num_total, virt_ids=virt_ids)
             self._ext_edge_index = ext  # what TransformerConv sees: the reference returns THIS with alpha
             self._graph_key = gkey
+            self._graph_refs = (edge_index, batch)
             self._feats_key = None
         fkey = self._tensor_key(feats) if feats is not None else "zero"
         if fkey != self._feats_key:
@@ -227,7 +233,7 @@ class _EngineMixin:
         for t in (ei, b, f, ext):
             t.record_stream(main)   # allocated on the side stream, consumed on the compute stream
         self._prefetched = dict(gkey=(self._tensor_key(ei), self._tensor_key(b)), fkey=self._tensor_key(f), ready=ready,
-                                ext=ext, wkey=wkey)
+                                ext=ext, wkey=wkey, refs=(ei, b, f))
         return ei, f, b
 
     def _take_prefetched(self, edge_index: Tensor, feats: Optional[Tensor], batch: Tensor) -> bool:
@@ -247,6 +253,7 @@ class _EngineMixin:
         self._weights_key, self._spare_weights_key = pf["wkey"], self._weights_key
         self._spare_last_use = done
         self._graph_key, self._feats_key = pf["gkey"], pf["fkey"]
+        self._graph_refs = pf["refs"][:2]
         self._ext_edge_index = pf["ext"]
         self._prefetched = None
         return True

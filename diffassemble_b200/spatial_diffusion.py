@@ -309,7 +309,8 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             cached = getattr(self, "_train_graph", None)
             graph = cached[1] if cached is not None and cached[0] == key else None
             prediction, graph = denoiser_forward_train(self.model, x_noisy, t, edge_index, patch_feats, batch, graph)
-            self._train_graph = (key, graph)
+            # (edge_index, batch) are kept alive next to the key: see _EngineMixin._graph_refs
+            self._train_graph = (key, graph, (edge_index, batch))
         else:
             prediction = self.forward_with_feats(x_noisy, t, cond, edge_index, patch_feats=patch_feats, batch=batch)
         target = {ModelMeanType.START_X: x_start, ModelMeanType.EPSILON: noise}[self.model_mean_type]
@@ -468,8 +469,11 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
 
     def validation_step(self, batch, batch_idx):
         """``spatial_diffusion.py:775-904`` without the image dumps: sample, then the assignment metric (scope row N2)
-        for the whole batch in two kernel launches; running sums are kept in ``self.val_stats`` under the reference's
-        metric names (``overall_acc``, ``overall__piece_acc``, ``(r, c)_acc`` ...) and logged."""
+        for the whole batch in two kernel launches.  The sums behind the reference's torchmetrics objects
+        (``MeanMetric`` for ``overall_acc``, ``overall__piece_acc``, ``(r, c)_acc``, ``(r, c)__piece_acc``; ``SumMetric``
+        for ``*_nImages``, ``spatial_diffusion.py:359-369,893-906``) are accumulated in ``self.val_stats``, which is
+        cleared at the start of every validation / test epoch (as Lightning resets torchmetrics) and reduced over
+        the ranks and logged once per epoch in ``validation_epoch_end``."""
         from .metrics import puzzle_accuracy
 
         imgs, _ = self.p_sample_loop(batch.x.shape, batch.patches, batch.edge_index, batch=batch.batch)
@@ -485,16 +489,45 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             for i, (d, n) in enumerate(zip(dims_l, sizes)):
                 for key, val, cnt in ((f"{tuple(d)}_acc", float(correct_h[i]), 1), ("overall_acc", float(correct_h[i]), 1),
                                       (f"{tuple(d)}__piece_acc", float(piece_h[off:off + n].sum()), n),
-                                      ("overall__piece_acc", float(piece_h[off:off + n].sum()), n)):
+                                      ("overall__piece_acc", float(piece_h[off:off + n].sum()), n),
+                                      (f"{tuple(d)}_nImages", 1.0, 0), ("overall_nImages", 1.0, 0)):
                     acc = stats.setdefault(key, [0.0, 0])
                     acc[0] += val; acc[1] += cnt
                 off += n
-            self.log_dict({k: v[0] / max(v[1], 1) for k, v in stats.items()})
         return img
 
-    def validation_epoch_end(self, outputs=None) -> None:
+    def _reset_val_stats(self):
+        self.__dict__["val_stats"] = {}
+
+    def on_validation_epoch_start(self) -> None:
+        self._reset_val_stats()
+
+    def on_test_epoch_start(self) -> None:
+        self._reset_val_stats()
+
+    def epoch_metrics(self):
+        """The epoch's metric values from ``val_stats``: means = sum / count, ``*_nImages`` = sum; sums and counts are
+        all-reduced over the process group first (torchmetrics' ``dist_reduce_fx="sum"``)."""
         stats = self.__dict__.get("val_stats", {})
-        self.log_dict({k: v[0] / max(v[1], 1) for k, v in stats.items()})
+        import torch.distributed as dist
+
+        keys = sorted(stats)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # ranks may have seen different puzzle sizes: agree on the key set first
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, keys)
+            keys = sorted(set(k for ks in gathered for k in ks))
+            dev = self.betas.device if dist.get_backend() == "nccl" else torch.device("cpu")
+            buf = torch.tensor([[stats.get(k, [0.0, 0])[0], float(stats.get(k, [0.0, 0])[1])] for k in keys], dtype=torch.float64,
+                               device=dev).reshape(-1, 2)
+            dist.all_reduce(buf)
+            tot = {k: (buf[i, 0].item(), buf[i, 1].item()) for i, k in enumerate(keys)}
+        else:
+            tot = {k: (stats[k][0], float(stats[k][1])) for k in keys}
+        return {k: (s if k.endswith("_nImages") else s / max(c, 1.0)) for k, (s, c) in tot.items()}
+
+    def validation_epoch_end(self, outputs=None) -> None:
+        self.log_dict(self.epoch_metrics())
 
     def test_epoch_end(self, outputs=None) -> None:
         return self.validation_epoch_end(outputs)

@@ -8,7 +8,7 @@ handles the small element-wise glue (GELU, concatenation, embedding lookup, Hube
 
 The optimizer is the reference's own choice, ``transformers.optimization.Adafactor()`` with default arguments
 (``spatial_diffusion.py:701-705``), stepping the ``nn.Parameter`` storage that the inference engine also reads
-(its packed copies are refreshed automatically because the parameters' version counters change).
+(its packed copies are refreshed because the fused step bumps the parameters' version counters explicitly).
 """
 import ctypes as C
 import math
@@ -270,6 +270,10 @@ def FusedAdafactor(params, **kwargs):
                 if stt != _cabi.DA_OK:
                     raise _cabi.DiffAssembleError(stt, "da_adafactor_step failed")
                 table.record_stream(torch.cuda.current_stream(dev))
+                # the kernel wrote the parameters through raw pointers: bump their version counters so that every
+                # cache keyed on (data_ptr, _version) -- the inference engine's packed weight copies, the prefetch
+                # engine, captured loop graphs -- sees the update (an in-place torch op would have done this itself)
+                torch.autograd.graph.increment_version(fused)
             # everything else: the stock implementation, with the fused parameters' gradients hidden from it
             for p, grad, _ in stash:
                 p.grad = None
