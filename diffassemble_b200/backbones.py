@@ -195,7 +195,8 @@ class _EngineMixin:
         """Stage the NEXT batch while the current one computes (double buffering).
 
         The host -> device copies of ``edge_index`` / ``feats`` / ``batch`` (pinned host tensors copy
-        asynchronously), the virtual-node wiring, ``da_set_graph`` (edge classification, bitmaps, residual CSR)
+        asynchronously; ``edge_index`` may also be a deferred topology such as ``topology.ExpanderBatchSpec``, whose
+        edge list is then written on the device and ``batch`` is ignored), the virtual-node wiring, ``da_set_graph`` (edge classification, bitmaps, residual CSR)
         and ``da_set_features`` (the step-invariant hoist GEMM) all run on a side stream into a second engine
         handle; none of it touches the stream or the handle the running sampling loop uses.  Returns the
         device tensors ``(edge_index, feats, batch)``: pass exactly these to ``p_sample_loop`` /
@@ -222,8 +223,12 @@ class _EngineMixin:
                 st.wait_stream(main)                  # parameters may have been written on the compute stream
                 eng.load_weights(self._denoiser_state())
                 self._spare_weights_key = wkey
-            ei = edge_index.to(dev, non_blocking=True)
-            b = batch.to(dev, non_blocking=True)
+            if hasattr(edge_index, "build"):
+                # deferred topology (topology.ExpanderBatchSpec / DenseBatchSpec): written on the device, on this stream
+                ei, b = edge_index.build(dev)
+            else:
+                ei = edge_index.to(dev, non_blocking=True)
+                b = batch.to(dev, non_blocking=True)
             f = feats.to(dev, non_blocking=True)
             ext, num_total, virt_ids = self.gnn_backbone.extend_graph(ei, b)
             eng.set_graph(ext, b, num_real=len(b), num_total=num_total, virt_ids=virt_ids)

@@ -21,9 +21,26 @@ def _worker(rank, world, port, q):
     for r in range(world):
         g0, g1 = sharding.shard_bounds(len(sizes), world, r)
         counts.append(sum(sizes[g0:g1]))
-    poses = x_r * 2.0  # stand-in for the per-rank sampling loop (no collective inside it)
+    poses = x_r * 2.0  # plumbing only: the gather must restore the global node order
     full = sharding.gather_poses(poses, counts)
-    q.put((rank, torch.equal(full, x * 2.0)))
+    ok = torch.equal(full, x * 2.0)
+    # the per-rank sampling loop itself (no collective inside it): every rank samples ITS graphs with the CPU oracle
+    # (there is no CUDA device here; tests/test_gpu_multirank.py runs the same check through the CUDA path over NCCL)
+    # and the gathered trajectory end must equal the unsharded run on the whole batch (V = 0: graphs are independent)
+    torch.manual_seed(0)
+    ref = oracle.GNNDiffusionRef(steps=20, sampling="DDIM", rotation=True, architecture="exophormer", virt_nodes=0,
+                                 model_mean_type=oracle.ModelMeanType.START_X, inference_ratio=5).eval()
+    g = torch.Generator().manual_seed(3)
+    feats, xT = torch.randn(sum(sizes), 1088, generator=g), torch.randn(sum(sizes), 4, generator=g)
+    ei_r, batch_r, (f_r, xs), _ = sharding.shard_batch(ei, batch, [feats, xT], world, rank)
+    xu = xT
+    with torch.no_grad():
+        for i in (15, 10, 5, 0):
+            xs, _ = ref.p_sample(xs, torch.full((len(batch_r),), i), i, edge_index=ei_r, patch_feats=f_r, batch=batch_r)
+            xu, _ = ref.p_sample(xu, torch.full((len(batch),), i), i, edge_index=ei, patch_feats=feats, batch=batch)
+    full = sharding.gather_poses(xs, counts)
+    ok = ok and torch.allclose(full, xu, rtol=1e-5, atol=1e-6)
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
