@@ -233,7 +233,7 @@ def run_sample2d(args, w):
 
     mod = make_module(w, args.gemm, args.attn, device)
     ddpm = w["sampler"] == "ddpm"
-    scaling = args.scaling if w["B"] >= 8 else "weak"
+    scaling = args.scaling if w["B"] >= 2 else "weak"
     spec, feats_h, x_h, g0, Bl = host_batch(w, world, rank, scaling)
     B_global = w["B"] if scaling == "strong" else w["B"] * world
     n = w["n"]
@@ -821,11 +821,15 @@ def main():
     ap.add_argument("--e2e-loops", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="override the workload's global batch (development: e.g. 4 = the per-GPU share of the 8-GPU strong-scaling run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.global_batch > 0:
+        w["B"] = args.global_batch
     {"sample2d": run_sample2d, "sample3d": run_sample3d, "train": run_train}[w["kind"]](args, w)
 
 

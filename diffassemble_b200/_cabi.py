@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "da_launch_count", "da_graph_stats", "da_set_profiling", "da_get_profile", "da_profile_tag_name",
     "da_op_linear", "da_op_graph_attention", "da_op_graph_attention_dense", "da_greedy_cost_assignment", "da_expander_edge_index", "da_graph_create", "da_graph_destroy",
     "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws", "da_op_segment_max", "da_adafactor_step", "da_graph_set_batch",
-    "da_op_linear_workspace_bytes",
+    "da_op_linear_workspace_bytes", "da_graph_plan_info",
 ]
 
 
@@ -92,6 +92,7 @@ def load_library():
     lib.da_launch_count.argtypes = [vp]
     lib.da_launch_count.restype = i64
     lib.da_graph_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    lib.da_graph_plan_info.argtypes = [vp, C.POINTER(i64), i32]
     lib.da_set_profiling.argtypes = [vp, i32]
     lib.da_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), i32, i32]
     lib.da_profile_tag_name.argtypes = [i32]

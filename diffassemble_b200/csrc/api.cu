@@ -70,6 +70,7 @@ struct da_handle {
   bool no_fuse = getenv("DA_NO_FUSE") != nullptr && getenv("DA_NO_FUSE")[0] == '1';
   bool no_side = getenv("DA_NO_SIDE") != nullptr && getenv("DA_NO_SIDE")[0] == '1';
   bool no_vrows = getenv("DA_NO_VROWS") != nullptr && getenv("DA_NO_VROWS")[0] == '1';
+  bool no_head_fuse = getenv("DA_NO_HEAD_FUSE") != nullptr && getenv("DA_NO_HEAD_FUSE")[0] == '1';
   // side stream: the CSR kernels of rows outside every dense tile (virtual nodes) run next to the dense kernel
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -78,6 +79,7 @@ struct da_handle {
   // activations / workspace
   DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
   // split-bf16 operand planes for the tensor-core path
+  DevBuf feats_perm;   // exact-fp32 mode: features gathered into the planner's internal node order
   DevBuf feats_sp_hi, feats_sp_lo, h_hi, h_lo, comb_hi, comb_lo, xa_hi, xa_lo, xb_hi, xb_lo, r_hi, r_lo;
   int64_t launches = 0;
   bool profiling = false;
@@ -91,7 +93,7 @@ struct da_handle {
     return (int)DA_ERR_CUDA;
   }
   size_t workspace_bytes() const {
-    const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats, &qimg, &kimg, &vimg,
+    const DevBuf* all[] = {&P, &hbuf, &combined, &qkvs, &xa, &xb, &r, &u, &model_out, &scores, &stats, &qimg, &kimg, &vimg, &feats_perm,
                            &qimg_l, &kimg_l, &vimg_l, &dacc, &dstats,
                            &feats_sp_hi, &feats_sp_lo, &h_hi, &h_lo, &comb_hi, &comb_lo, &xa_hi, &xa_lo,
                            &xb_hi, &xb_lo, &r_hi, &r_lo};
@@ -177,6 +179,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     a.time_emb = h->time_emb.as<float>(); a.w1pt_T = h->w1pt_T.as<float>();
     a.M = Mr; a.C_in = c.in_channels; a.Hm = Hm; a.T = c.steps;
     a.act = (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_GELU;
+    a.row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;   // internal node order of the planner (x / t are the caller's)
     if (umma) { a.out.hi = h->h_hi.as<__nv_bfloat16>(); a.out.lo = h->h_lo.as<__nv_bfloat16>(); a.out.ld_split = Hm; }
     else { a.out.f32 = h->hbuf.as<float>(); a.out.ldc = Hm; }
     Scoped sc(h, s, TAG_PROLOGUE);
@@ -311,7 +314,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     if (dense) {
       AttnDenseArgs da_{};
       da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;
-      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap;
+      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap; da_.blk_list = h->plan.blk_list;
       da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
       da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
       da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
@@ -346,9 +349,6 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
   }
   // 4. head: u = GELU(r @ Wa^T + ba) ; then final linear(s) + pose map + sampler update
   {
-    LinearOut o; o.f32 = h->u.as<float>(); o.ldc = h->Nh;
-    DA_CK(run_linear(h, h->head1, h->r.as<float>(), D, h->r_hi.as<__nv_bfloat16>(), h->r_lo.as<__nv_bfloat16>(), D, Mr,
-                     ACT_GELU, o, TAG_HEAD_GEMM, s), "head gemm");
     HeadFinalArgs a{};
     a.u = h->u.as<float>(); a.Nh = h->Nh;
     a.w_b = h->headb_w.as<float>(); a.b_b = h->headb_b.as<float>();
@@ -357,8 +357,17 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     a.step_mode = step_mode;
     if (coef) a.coef = *coef;
     a.x_in = x_in; a.noise = noise; a.out = out;
-    Scoped sc(h, s, TAG_HEAD_FINAL);
-    DA_CK(launch_head_final(a, s), "head final");
+    a.row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;
+    // 2-D head on the tensor-core path: final_mlp[2] + the sampler update ride in the GEMM epilogue (one launch)
+    const bool fused_head = umma && c.head_kind == DA_HEAD_2D && h->Nh == 32 && !h->no_head_fuse;
+    LinearOut o;
+    if (fused_head) o.head = &a; else { o.f32 = h->u.as<float>(); o.ldc = h->Nh; }
+    DA_CK(run_linear(h, h->head1, h->r.as<float>(), D, h->r_hi.as<__nv_bfloat16>(), h->r_lo.as<__nv_bfloat16>(), D, Mr,
+                     ACT_GELU, o, TAG_HEAD_GEMM, s), "head gemm");
+    if (!fused_head) {
+      Scoped sc(h, s, TAG_HEAD_FINAL);
+      DA_CK(launch_head_final(a, s), "head final");
+    }
   }
 #undef DA_CK
   return DA_OK;
@@ -435,7 +444,8 @@ void da_destroy(da_handle* h) {
                    &h->headb_b, &h->headr_w, &h->headr_b, &h->virt_emb, &h->P, &h->hbuf, &h->combined, &h->qkvs,
                    &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
                    &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
-                   &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l, &h->dacc, &h->dstats};
+                   &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l, &h->dacc, &h->dstats,
+                   &h->feats_perm};
   for (auto* b : all) b->release();
   free_csr(&h->csr);
   free_plan(&h->plan);
@@ -594,7 +604,7 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
   h->use_plan = (c.attn_mode == DA_ATTN_AUTO) && batch != nullptr && (c_hid % 8 == 0) && (c_last % 8 == 0) && cpad_max <= 144;
   free_csr(&h->csr, s);
   free_plan(&h->plan, s);
-  if (h->use_plan) ce = build_dense_plan(edge_src, edge_dst, E, batch, num_real, num_total, &h->plan, s, &why);
+  if (h->use_plan) ce = build_dense_plan(edge_src, edge_dst, E, batch, num_real, num_total, &h->plan, s, &why, /*allow_reorder=*/true);
   else ce = build_csr(edge_src, edge_dst, E, num_total, &h->csr, s, &why);
   if (ce != cudaSuccess) {
     if (ce == cudaErrorInvalidValue && why[0]) return h->fail(DA_ERR_INVALID, why);
@@ -661,13 +671,21 @@ int da_set_features(da_handle* h, const float* feats, void* stream) {
   h->feats_zero = false;
   const int Mr = h->num_real, Dv = h->cfg.feat_dim, Hm = h->cfg.mlp_hidden;
   cudaError_t ce;
+  // the planner may have renumbered the nodes inside each graph: the hoisted product P is kept in internal order
+  const int32_t* row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;
   if (use_umma(h)) {
     const size_t b2 = sizeof(__nv_bfloat16);
     ce = h->feats_sp_hi.ensure((size_t)Mr * Dv * b2); if (ce != cudaSuccess) return h->cuda_fail(ce, "alloc");
     ce = h->feats_sp_lo.ensure((size_t)Mr * Dv * b2); if (ce != cudaSuccess) return h->cuda_fail(ce, "alloc");
     Scoped sc(h, s, TAG_OTHER);
-    ce = launch_split_bf16(feats, Dv, h->feats_sp_hi.as<__nv_bfloat16>(), h->feats_sp_lo.as<__nv_bfloat16>(), Dv, Mr, Dv, s);
+    ce = launch_split_bf16(feats, Dv, h->feats_sp_hi.as<__nv_bfloat16>(), h->feats_sp_lo.as<__nv_bfloat16>(), Dv, Mr, Dv, s, row_ext);
     if (ce != cudaSuccess) return h->cuda_fail(ce, "split features");
+  } else if (row_ext) {
+    ce = h->feats_perm.ensure((size_t)Mr * Dv * sizeof(float)); if (ce != cudaSuccess) return h->cuda_fail(ce, "alloc");
+    Scoped sc(h, s, TAG_OTHER);
+    ce = launch_gather_rows(feats, Dv, h->feats_perm.as<float>(), Dv, Mr, Dv, row_ext, s);
+    if (ce != cudaSuccess) return h->cuda_fail(ce, "gather features");
+    feats = h->feats_perm.as<float>();
   }
   LinearOut o; o.f32 = h->P.as<float>(); o.ldc = Hm;
   ce = run_linear(h, h->hoist, feats, Dv, h->feats_sp_hi.as<__nv_bfloat16>(), h->feats_sp_lo.as<__nv_bfloat16>(), Dv, Mr,
@@ -725,6 +743,21 @@ int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_ed
   if (n_dense_edges) *n_dense_edges = h->use_plan ? h->plan.n_dense_edges : 0;
   if (n_csr_edges) *n_csr_edges = h->use_plan ? h->plan.residual.E : h->csr.E;
   if (n_dense_graphs) *n_dense_graphs = h->use_plan ? h->plan.n_dense_graphs : 0;
+  return DA_OK;
+}
+
+int da_graph_plan_info(const da_handle* h, int64_t* out, int32_t n) {
+  if (!h || !h->graph_set || !out || n < 8) return DA_ERR_INVALID;
+  const DensePlan& p = h->plan;
+  const bool on = h->use_plan;
+  out[0] = on ? p.n_tiles : 0;
+  out[1] = on ? p.n_blocks_total : 0;      // (tile, 64-source block) pairs of the dense tiles
+  out[2] = on ? p.n_blocks_listed : 0;     // ... that hold at least one edge and are visited
+  out[3] = on ? p.n_blocks_full : 0;       // ... of which every bit is set
+  out[4] = on ? p.n_reordered_graphs : 0;  // graphs renumbered by the ring walk
+  out[5] = on ? p.n_extra : 0;             // promoted extra sources
+  out[6] = on ? p.n_fused : 0;             // rows finalised inside the dense kernel
+  out[7] = on ? p.n_csr_rows : 0;          // rows served by the CSR kernels
   return DA_OK;
 }
 
@@ -953,6 +986,7 @@ int da_op_graph_attention_fwd(const da_graph* gc, const float* qkvs, int32_t H, 
     if (ce == cudaSuccess) {
       AttnDenseArgs da_{pa.qimg, pa.kimg, pa.vimg, g->plan.tiles, g->plan.n_tiles, g->plan.bitmap, H, C, Cpad, g->acc.as<float>(),
                         stats, nullptr};
+      da_.blk_list = g->plan.blk_list;
       ce = launch_attn_dense(da_, s);
     }
     if (ce == cudaSuccess) {
@@ -1034,6 +1068,7 @@ int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, cons
       if (ce == cudaSuccess) ce = launch_gather_extra(pa, plan.x_src, plan.x_slot, plan.n_extra, s);
       if (ce == cudaSuccess) {
         AttnDenseArgs da_{qi, ki, vi, plan.tiles, plan.n_tiles, plan.bitmap, H, C, Cpad, acc, st, nullptr};
+        da_.blk_list = plan.blk_list;
         if (fuse) {
           da_.row_fused = plan.row_fused; da_.qkvs = qkvs; da_.ld = 4 * H * C; da_.n_rows = n;
           da_.rowptr = plan.residual.rowptr; da_.col = plan.residual.col; da_.weight = plan.residual.weight;

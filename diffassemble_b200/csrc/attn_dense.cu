@@ -273,7 +273,21 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / a.H, head = blockIdx.x % a.H;
   const TileInfo ti = a.tiles[tile];
-  const int nblk = (ti.gn + TS - 1) / TS;
+  // the source blocks this tile visits: the planner's list of blocks that hold at least one edge of the tile (in the
+  // planner's internal node order the adjacency of an Exphander graph is a band, so ~1/4 of the blocks drop out at 60 %
+  // density and ~2/3 at 20 %).  Every role walks the same list; ring stages / TMEM buffers are indexed by the POSITION j.
+  const int nblk = ti.n_list;
+  const uint16_t* __restrict__ blist = a.blk_list + ti.list_off;
+  // development aid: per-CTA (start, end, SM id) records behind the 128-entry trace of CTA 0 when dbg[127] says there is room
+  const bool dbg_rec = a.dbg != nullptr && threadIdx.x == 0 && a.dbg[127] > (long long)blockIdx.x;
+  if (dbg_rec) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    a.dbg[128 + 8 * blockIdx.x + 0] = (long long)gt; a.dbg[128 + 8 * blockIdx.x + 2] = smid;
+    a.dbg[128 + 8 * blockIdx.x + 3] = clock64();
+  }
+  const bool dbg_sm = a.dbg != nullptr && threadIdx.x == 64 && a.dbg[127] > (long long)blockIdx.x;   // first softmax thread
 
   if (threadIdx.x == 0) {
     mbar_init(&sh->q_full, 4);   // the four softmax warps have parked Q in TMEM
@@ -293,12 +307,13 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  if (dbg_sm) a.dbg[128 + 8 * blockIdx.x + 4] = clock64();   // setup (barriers, TMEM allocation) done
   const uint32_t tmem_s = tmem_base;             // 2 x TS columns: S_j (fp32), later P_j (bf16 hi | lo)
   const uint32_t tmem_o = tmem_base + 2 * TS;    // Cpad columns
   const uint32_t tmem_q = tmem_o + Cpad;         // Cpad columns: Q as packed bf16 pairs, hi plane then lo plane
 
   if (warp == 0) {  // ===== bulk-copy producer (warp-uniform): K and V blocks run ST ahead =====
-    auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + j) * a.H + head) * kv_block_elems(Cpad); };
+    auto blk_off = [&](int j) { return ((size_t)(ti.gblock0 + (int)(__ldg(blist + j) >> 1)) * a.H + head) * kv_block_elems(Cpad); };
     auto load_k = [&](int j) {
       if (elect_one()) {
         const int st = j % KST;
@@ -418,6 +433,7 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->q_full);
+      if (dbg_sm) a.dbg[128 + 8 * blockIdx.x + 5] = clock64();   // Q parked
     }
     const int node = ti.node0 + r;
     const int HC = a.H * a.C;
@@ -449,11 +465,11 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
     int res_beg = 0, n_e = 0;
     if (fused) { res_beg = a.rowptr[node]; n_e = a.rowptr[node + 1] - res_beg; }
     float m = -INFINITY, l = 0.f;  // m: reference point in raw-score units (>= true max - tau_raw)
-    uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row) : make_uint2(0u, 0u);
+    uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist) >> 1) * 2) : make_uint2(0u, 0u);
     for (int j = 0; j < nblk; ++j) {
       const int b = j & 1;
       const uint2 bits = bits_next;
-      if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (j + 1) * 2);
+      if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist + j + 1) >> 1) * 2);
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 0] = clock64();   // start waiting for S_j
       mbar_wait(&sh->s_full[b], (j >> 1) & 1);
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 1] = clock64();   // S_j ready
@@ -545,6 +561,7 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
       if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64 && j < 15) a.dbg[1 * 64 + j * 4 + 2] = clock64();   // P_j published
     }
     // epilogue
+    if (dbg_sm) a.dbg[128 + 8 * blockIdx.x + 6] = clock64();   // softmax loop done
     if (a.dbg && blockIdx.x == 0 && threadIdx.x == 64) a.dbg[120] = clock64();   // last P published
     mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
@@ -786,6 +803,12 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+  }
+  if (dbg_rec) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    a.dbg[128 + 8 * blockIdx.x + 1] = (long long)gt;
+    a.dbg[128 + 8 * blockIdx.x + 7] = clock64();
   }
 }
 

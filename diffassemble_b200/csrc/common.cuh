@@ -64,6 +64,9 @@ struct LinearOut {
   // optional per-128-row-tile flags (bit 0: some row's fp32 Q is read later, bit 1: some row's fp32 K / V is):
   // tiles whose Q / K / V only feed the tensor-core attention skip those fp32 stores (HBM-write-bound GEMMs).
   const uint8_t* f32_tile_flags = nullptr;
+  // optional (N == 32 tiles only): the 2-D head's last linear + sampler update fused behind the activation
+  // (efficient_gat.py:144 final_mlp[2], spatial_diffusion.py:485-627): see HeadFinalArgs; nothing else is stored then
+  const struct HeadFinalArgs* head = nullptr;
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
@@ -71,8 +74,12 @@ cudaError_t launch_linear_simt(const float* a, int lda, const float* w, int ldw,
                                const LinearOut& out, int M, int N, int K, int act, cudaStream_t s);
 
 // fp32 -> split bf16 planes (hi = bf16(x), lo = bf16(x - hi)); rows x cols with row strides.
+// row_map (optional, device int32 [rows]): output row r is read from input row row_map[r]
 cudaError_t launch_split_bf16(const float* x, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld,
-                              int rows, int cols, cudaStream_t s);
+                              int rows, int cols, cudaStream_t s, const int32_t* row_map = nullptr);
+// y[r, :] = x[row_map[r], :]
+cudaError_t launch_gather_rows(const float* x, int ldx, float* y, int ldy, int rows, int cols, const int32_t* row_map,
+                               cudaStream_t s);
 
 // CSR-by-target multigraph attention (TransformerConv message/aggregate stage).
 struct AttnCsrArgs {
@@ -130,6 +137,9 @@ struct PrologueArgs {
   const float* w1pt_T;   // [64, Hm]  transposed W1[:, Dv:Dv+64]
   int M, C_in, Hm, T, act;
   LinearOut out;         // [M, Hm]
+  // optional: the engine's internal node order (DensePlan::ext_of_int): internal row r reads x / t of the caller's row
+  // row_ext[r]; P and the outputs are in internal order
+  const int32_t* row_ext = nullptr;
 };
 cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s);
 
@@ -149,8 +159,46 @@ struct HeadFinalArgs {
   const float* x_in;     // [M, C] current sample (step modes)
   const float* noise;    // [M, C] or null
   float* out;            // [M, C_out] model output (STEP_NONE) or x_prev
+  const int32_t* row_ext = nullptr;   // optional: internal row r reads / writes the caller's row row_ext[r] of x_in, noise, out
 };
 cudaError_t launch_head_final(const HeadFinalArgs& a, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// Sampler updates (one value per thread), evaluated op by op in the reference's order with
+// explicit round-to-nearest intrinsics so no FMA contraction changes the result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ddpm_update(float x, float out, float noise, const da_step_coef& c) {
+  // spatial_diffusion.py:495-510
+  float mean = __fmul_rn(c.sqrt_recip_alpha, __fsub_rn(x, __fdiv_rn(__fmul_rn(c.beta_t, out), c.sqrt_one_minus_acp)));
+  if (c.t_index == 0) return mean;
+  return __fadd_rn(mean, __fmul_rn(sqrtf(c.posterior_variance), noise));
+}
+
+__device__ __forceinline__ float ddim_x0(float x, float out, const da_step_coef& c) {
+  // spatial_diffusion.py:603-606
+  if (c.pred == DA_PRED_START_X) return out;
+  float beta = __fsub_rn(1.f, c.acp);
+  return __fdiv_rn(__fsub_rn(x, __fmul_rn(sqrtf(beta), out)), sqrtf(c.acp));
+}
+
+__device__ __forceinline__ float ddim_update(float x, float out, float noise, const da_step_coef& c) {
+  // spatial_diffusion.py:548-627 with _get_variance :528-546 and _predict_eps_from_xstart :629-632
+  float x0 = ddim_x0(x, out, c);
+  float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.sqrt_recip_acp, x), x0), c.sqrt_recipm1_acp);
+  float beta = __fsub_rn(1.f, c.acp), beta_prev = __fsub_rn(1.f, c.acp_prev);
+  float variance = __fmul_rn(__fdiv_rn(beta_prev, beta), __fsub_rn(1.f, __fdiv_rn(c.acp, c.acp_prev)));
+  float std_eta = __fmul_rn(c.eta, sqrtf(variance));
+  float dir = __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.f, c.acp_prev), __fmul_rn(std_eta, std_eta))), eps);
+  float prev = __fadd_rn(__fmul_rn(sqrtf(c.acp_prev), x0), dir);
+  if (c.eta > 0.f) prev = __fadd_rn(prev, __fmul_rn(std_eta, noise));
+  return prev;
+}
+
+__device__ __forceinline__ float step_update(int mode, float x, float out, float noise, const da_step_coef& c) {
+  if (mode == STEP_DDPM) return ddpm_update(x, out, noise, c);
+  if (mode == STEP_DDIM) return ddim_update(x, out, noise, c);
+  return out;
+}
 cudaError_t launch_sampler_update(const float* x_in, const float* model_out, float* x_out, int M, int C,
                                   int head_kind, int step_mode, const da_step_coef& coef,
                                   const float* noise, cudaStream_t s);
@@ -247,6 +295,11 @@ struct TileInfo {
   int32_t bm_words;  // uint32 words per bitmap row of this graph (multiple of 2)
   int32_t row0;      // local index (within the graph) of the tile's first row
   int64_t bm_off;    // word offset of the graph's bitmap
+  // the 64-source blocks this tile has to visit, in order (DensePlan::blk_list + list_off): blocks whose bitmap words
+  // are all zero for every row of the tile are skipped.  Entry = (block index within the graph << 1) | full, where
+  // full = every (valid row, column) bit of the block is set (no masking needed).
+  int32_t n_list;
+  int32_t list_off;
 };
 
 struct DensePlan {
@@ -283,11 +336,24 @@ struct DensePlan {
   // per 128-row tile of the node index space: bit 0 = a row has residual in-edges (its fp32 Q is read),
   // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
   uint8_t* f32_tile_flags[2] = {nullptr, nullptr};
+  // Internal node order.  The engine is free to number the nodes of a graph as it likes as long as it reads its inputs
+  // and writes its outputs in the caller's order.  For sparse-ish dense-tile graphs the planner walks the graph greedily
+  // along maximal neighbourhood overlap, which recovers the ring order of the reference's Exphander graphs (a random
+  // permutation joined to its d/2 cyclic shifts, puzzle_dataset.py:133-152): in that order the adjacency is a band, a
+  // 128-row tile only touches ~(128 + d) / 64 of the graph's source blocks, and the rest is skipped.
+  // ext_of_int[r] = caller's node id of internal row r (null = identity).  Every node id inside the plan (bitmap rows /
+  // columns, residual CSR, slots, row lists) is INTERNAL.
+  int32_t* ext_of_int = nullptr;
+  int n_reordered_graphs = 0;
+  uint16_t* blk_list = nullptr;    // [n_tiles * max_blocks] (see TileInfo)
+  int max_blocks = 0;
+  int64_t n_blocks_total = 0, n_blocks_listed = 0, n_blocks_full = 0;
 };
 void free_plan(DensePlan* p, cudaStream_t s = nullptr);   // stream-ordered (cudaFreeAsync on s)
-// Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.
+// Classifies the edges, fills the bitmap and builds the residual CSR.  Synchronous.  allow_reorder: the caller reads the
+// plan's ext_of_int and feeds / drains the kernels in internal order (the fused engine); false keeps the caller's order.
 cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
-                             int num_total, DensePlan* plan, cudaStream_t s, const char** err);
+                             int num_total, DensePlan* plan, cudaStream_t s, const char** err, bool allow_reorder = false);
 
 // fp32 [Q | K | V | skip] rows -> split-bf16 operand images of the dense tiles
 struct PackArgs {
@@ -319,6 +385,7 @@ struct AttnDenseArgs {
   const float* resid = nullptr; int ld_resid = 0;   // optional second addend (trunk residual), staged like skip when it fits
   int act = 0;
   LinearOut out;
+  const uint16_t* blk_list = nullptr;   // DensePlan::blk_list (required)
 };
 constexpr int DA_FUSE_MAX_RESIDUAL = 2;
 // true when the fused epilogue's staging area (128 skip rows of C floats) fits the kernel's K ring

@@ -137,16 +137,27 @@ linear_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict
   }
 }
 
+// row_map (optional): output row r is taken from input row row_map[r] (the planner's internal node order)
 __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int ld, int rows, int cols) {
+                                  __nv_bfloat16* __restrict__ lo, int ld, int rows, int cols,
+                                  const int32_t* __restrict__ row_map) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)rows * cols;
   if (idx >= total) return;
   int r = (int)(idx / cols), c = (int)(idx % cols);
-  float v = x[(size_t)r * ldx + c];
+  const int rs = row_map ? row_map[r] : r;
+  float v = x[(size_t)rs * ldx + c];
   __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[(size_t)r * ld + c] = h;
   lo[(size_t)r * ld + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int rows, int cols,
+                                   const int32_t* __restrict__ row_map) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * cols) return;
+  int r = (int)(idx / cols), c = (int)(idx % cols);
+  y[(size_t)r * ldy + c] = x[(size_t)row_map[r] * ldx + c];
 }
 
 }  // namespace
@@ -172,10 +183,18 @@ cudaError_t launch_linear_simt(const float* a, int lda, const float* w, int ldw,
 }
 
 cudaError_t launch_split_bf16(const float* x, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld,
-                              int rows, int cols, cudaStream_t s) {
+                              int rows, int cols, cudaStream_t s, const int32_t* row_map) {
   size_t total = (size_t)rows * cols;
   if (total == 0) return cudaSuccess;
-  split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, ldx, hi, lo, ld, rows, cols);
+  split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, ldx, hi, lo, ld, rows, cols, row_map);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* x, int ldx, float* y, int ldy, int rows, int cols, const int32_t* row_map,
+                               cudaStream_t s) {
+  size_t total = (size_t)rows * cols;
+  if (total == 0) return cudaSuccess;
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, ldx, y, ldy, rows, cols, row_map);
   return cudaGetLastError();
 }
 

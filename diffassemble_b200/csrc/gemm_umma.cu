@@ -138,12 +138,21 @@ struct EpiParams {
   int iH, iC, iCpad, irows;
   const uint8_t* f32_tile_flags;
 };
+// Mode-specific arguments travel as a separate kernel parameter: growing EpiParams itself changes ptxas' register
+// allocation of the plain epilogue (168 -> 142 registers) and costs the store-bound GEMMs 30-50 %.
+struct EpiNone { const void* unused; };
+template <int MODE> struct EpiExtraT { using type = EpiNone; };
+template <> struct EpiExtraT<2> { using type = HeadFinalArgs; };
 
-template <int BN>
+// MODE 0: plain epilogue; 2: fused 2-D head (BN == 32).  Compile-time so that the plain, store-bound epilogue keeps its
+// code shape.  (Measured and dropped: MODE 1, the per-layer gather of the promoted extra sources folded into this
+// epilogue -- the extra code moved ptxas to a 144-register allocation of the whole epilogue and cost the QKVS GEMMs
+// 15-50 %, far more than the four 7 us gather launches it saved.)
+template <int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                    const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
-                   EpiParams p) {
+                   EpiParams p, const typename EpiExtraT<MODE>::type ex) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -254,6 +263,30 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
+        if constexpr (BN == 32 && MODE == 2) {
+          // fused 2-D head: this thread holds the whole 32-wide row: activation, final_mlp[2], sampler update, store
+          const HeadFinalArgs& hd = ex;
+          const int row = row_base + lane;
+          if (row < p.M) {
+            float u[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) u[k] = apply_act_rt(__uint_as_float(r[k]) + (p.bias ? __ldg(p.bias + n0 + k) : 0.f), p.act);
+            const int ext = hd.row_ext ? __ldg(hd.row_ext + row) : row;
+            for (int c = 0; c < hd.C_out; ++c) {
+              float sacc = __ldg(hd.b_b + c);
+#pragma unroll
+              for (int k = 0; k < 32; ++k) sacc = fmaf(__ldg(hd.w_b + c * 32 + k), u[k], sacc);
+              float x = 0.f, nz = 0.f;
+              const int eidx = ext * hd.C_out + c;
+              if (hd.step_mode != STEP_NONE) {
+                x = hd.x_in[eidx];
+                if (hd.noise) nz = hd.noise[eidx];
+              }
+              hd.out[eidx] = step_update(hd.step_mode, x, sacc, nz, hd.coef);
+            }
+          }
+          continue;
+        }
         // thread == row: park the 32 columns of this row in the staging tile
         float4* srow = reinterpret_cast<float4*>(stage + lane * EPI_PITCH);
 #pragma unroll
@@ -446,9 +479,9 @@ int num_sms() {
   return n;
 }
 
-template <int BN>
+template <int BN, int MODE>
 cudaError_t launch_bn(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int lda, const __nv_bfloat16* w_hi,
-                      const __nv_bfloat16* w_lo, int ldw, const EpiParams& p, cudaStream_t s) {
+                      const __nv_bfloat16* w_lo, int ldw, const EpiParams& p, const typename EpiExtraT<MODE>::type& ex, cudaStream_t s) {
   using C = Cfg<BN>;
   CUtensorMap mah, mal, mwh, mwl;
   if (!get_tensor_map(a_hi, p.M, p.K, lda, BM, &mah) || !get_tensor_map(a_lo, p.M, p.K, lda, BM, &mal) ||
@@ -456,13 +489,13 @@ cudaError_t launch_bn(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int 
     return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(linear_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(linear_umma_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  linear_umma_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(mah, mal, mwh, mwl, p);
+  linear_umma_kernel<BN, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(mah, mal, mwh, mwl, p, ex);
   return cudaGetLastError();
 }
 
@@ -477,14 +510,19 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
   EpiParams p{bias, out.f32, out.ldc, out.hi, out.lo, out.ld_split, M, N, K, act,
               out.img_node_slot, out.qimg, out.kimg, out.vimg, out.img_H, out.img_C, out.img_Cpad, out.img_rows,
               out.img_node_slot ? out.f32_tile_flags : nullptr};
+  const EpiNone none{nullptr};
+  if (out.head != nullptr) {
+    if (N != 32 || out.head->Nh != 32 || out.head->head_kind != DA_HEAD_2D) return cudaErrorInvalidValue;
+    return launch_bn<32, 2>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, *out.head, s);
+  }
   if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
   // short-K GEMMs (K <= 256) are bound by the L2 -> SM operand traffic (a 128 x 128 tile loads 256 KB of split-bf16
   // operands for 2.7 us of MMAs): 256-wide tiles re-use the A block twice as often
   static const bool wide = !(getenv("DA_GEMM_BN256") && getenv("DA_GEMM_BN256")[0] == '0');
-  if (wide && N % 256 == 0 && K <= 256 && M >= 4096) return launch_bn<256>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
-  if (N % 128 == 0) return launch_bn<128>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
-  if (N % 64 == 0) return launch_bn<64>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
-  return launch_bn<32>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, s);
+  if (wide && N % 256 == 0 && K <= 256 && M >= 4096) return launch_bn<256, 0>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, none, s);
+  if (N % 128 == 0) return launch_bn<128, 0>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, none, s);
+  if (N % 64 == 0) return launch_bn<64, 0>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, none, s);
+  return launch_bn<32, 0>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, none, s);
 }
 
 }  // namespace da

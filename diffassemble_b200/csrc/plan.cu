@@ -38,12 +38,13 @@ __global__ void count_ingraph_edges_kernel(const int64_t* __restrict__ src, cons
   if (g >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&cnt[g], (unsigned long long)__popc(peers));
 }
 
-// flag[e] = 1 -> residual edge (goes to the CSR), 0 -> recorded in the bitmap
+// flag[e] = 1 -> residual edge (goes to the CSR), 0 -> recorded in the bitmap.  int_of_ext (optional): the internal
+// number of each real node (a permutation inside every graph); bitmap rows / columns are internal.
 __global__ void classify_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
                                       const int64_t* __restrict__ batch, int num_real,
                                       const int32_t* __restrict__ g_node0, const int64_t* __restrict__ g_bm_off,
                                       const int32_t* __restrict__ g_bm_words, uint32_t* __restrict__ bitmap,
-                                      uint8_t* __restrict__ flag) {
+                                      uint8_t* __restrict__ flag, const int32_t* __restrict__ int_of_ext) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   int64_t s = src[e], d = dst[e];
@@ -51,6 +52,7 @@ __global__ void classify_edges_kernel(const int64_t* __restrict__ src, const int
   if (s >= 0 && d >= 0 && s < num_real && d < num_real) {
     int64_t g = batch[d];
     if (batch[s] == g && g_bm_off[g] >= 0) {
+      if (int_of_ext) { s = int_of_ext[s]; d = int_of_ext[d]; }
       const int i = (int)(d - g_node0[g]), j = (int)(s - g_node0[g]);
       uint32_t* w = bitmap + g_bm_off[g] + (int64_t)i * g_bm_words[g] + (j >> 5);
       const uint32_t bit = 1u << (j & 31);
@@ -58,7 +60,117 @@ __global__ void classify_edges_kernel(const int64_t* __restrict__ src, const int
       residual = (old & bit) ? 1 : 0;  // a duplicate of an edge already in the bitmap stays in the CSR
     }
   }
-  flag[e] = residual;
+  if (flag) flag[e] = residual;
+}
+
+// Greedy walk along maximal neighbourhood overlap, one CTA per dense-tile graph: from the current node go to the unvisited
+// neighbour that shares the most neighbours with it (bitmap row AND + popcount); when there is none, to the lowest
+// unvisited node.  On the reference's Exphander graphs (ring position p joined to p +- 1 .. p +- d/2) the overlap with
+// position p + k is d - 1 - k, strictly decreasing, so the walk follows the ring and the relabelled adjacency is a band.
+// Any other graph just gets some permutation, which is harmless.  Writes ext_of_int / int_of_ext for the graph's nodes.
+__global__ void __launch_bounds__(256)
+ring_order_kernel(const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ g_node0, const int32_t* __restrict__ g_n,
+                  const int64_t* __restrict__ g_bm_off, const int32_t* __restrict__ g_bm_words, const uint8_t* __restrict__ g_reorder,
+                  int32_t* __restrict__ ext_of_int, int32_t* __restrict__ int_of_ext) {
+  const int g = blockIdx.x;
+  if (!g_reorder[g]) return;
+  extern __shared__ uint32_t ro_sm[];
+  const int n = g_n[g], words = g_bm_words[g], node0 = g_node0[g];
+  const uint32_t* bm = bitmap + g_bm_off[g];
+  uint32_t* visited = ro_sm;            // [words]
+  uint32_t* cur_row = ro_sm + words;    // [words]
+  __shared__ unsigned long long warp_best[8];
+  __shared__ int cur_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int w = tid; w < words; w += 256) visited[w] = 0u;
+  if (tid == 0) cur_s = 0;
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const int cur = cur_s;
+    if (tid == 0) {
+      visited[cur >> 5] |= 1u << (cur & 31);
+      ext_of_int[node0 + k] = node0 + cur;
+      int_of_ext[node0 + cur] = node0 + k;
+    }
+    for (int w = tid; w < words; w += 256) cur_row[w] = bm[(size_t)cur * words + w];
+    __syncthreads();
+    if (k == n - 1) break;
+    unsigned long long best = 0ull;
+    for (int v = tid; v < n; v += 256) {
+      if (!((cur_row[v >> 5] >> (v & 31)) & 1u) || ((visited[v >> 5] >> (v & 31)) & 1u)) continue;
+      const uint32_t* rv = bm + (size_t)v * words;
+      int score = 0;
+      for (int w = 0; w < words; ++w) score += __popc(cur_row[w] & rv[w]);
+      const unsigned long long key = ((unsigned long long)(score + 1) << 32) | (unsigned long long)(0x7fffffff - v);
+      best = key > best ? key : best;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) warp_best[wid] = best;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long b = 0ull;
+      for (int i = 0; i < 8; ++i) b = warp_best[i] > b ? warp_best[i] : b;
+      int nxt = -1;
+      if (b != 0ull) nxt = 0x7fffffff - (int)(b & 0xffffffffull);
+      else {   // dead end: lowest unvisited node
+        for (int w = 0; w < words && nxt < 0; ++w) {
+          const uint32_t free_bits = ~visited[w];
+          if (free_bits) { const int v = w * 32 + __ffs(free_bits) - 1; if (v < n) nxt = v; }
+        }
+      }
+      cur_s = nxt;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ a, int32_t* __restrict__ b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = i; b[i] = i; }
+}
+
+__global__ void relabel_kernel(int64_t* __restrict__ ids, int64_t n, const int32_t* __restrict__ int_of_ext, int num_real) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int64_t v = ids[i]; if (v >= 0 && v < num_real) ids[i] = int_of_ext[v]; }
+}
+
+// Per 128-row tile: which 64-source blocks of the graph hold at least one bit on a valid row (listed, in order), and
+// which of those hold ALL bits (valid rows x the block's 64 columns).  One CTA of 128 threads per tile.
+__global__ void __launch_bounds__(128)
+tile_blocks_kernel(TileInfo* __restrict__ tiles, const uint32_t* __restrict__ bitmap, uint16_t* __restrict__ blk_list, int max_blocks,
+                   unsigned long long* __restrict__ counters) {
+  const int t = blockIdx.x, r = threadIdx.x;
+  TileInfo ti = tiles[t];
+  const int nblk = (ti.gn + 63) / 64;
+  const bool valid = r < ti.rows;
+  const uint32_t* row = bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
+  __shared__ int n_list_s;
+  if (r == 0) n_list_s = 0;
+  __syncthreads();
+  int n_full = 0;
+  for (int b = 0; b < nblk; ++b) {
+    uint32_t w0 = 0u, w1 = 0u;
+    if (valid) { w0 = row[2 * b]; w1 = row[2 * b + 1]; }
+    const int any = __syncthreads_or(valid && (w0 | w1) != 0u);
+    const int all = __syncthreads_and(!valid || (w0 & w1) == 0xffffffffu);
+    if (any && r == 0) {
+      blk_list[(size_t)t * max_blocks + n_list_s] = (uint16_t)((b << 1) | (all ? 1 : 0));
+      n_list_s++;
+      n_full += all ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (r == 0) {
+    if (n_list_s == 0) { blk_list[(size_t)t * max_blocks] = 0; n_list_s = 1; }   // the kernel always visits one block
+    tiles[t].n_list = n_list_s;
+    tiles[t].list_off = t * max_blocks;
+    atomicAdd(&counters[0], (unsigned long long)nblk);
+    atomicAdd(&counters[1], (unsigned long long)n_list_s);
+    atomicAdd(&counters[2], (unsigned long long)n_full);
+  }
 }
 
 __global__ void set_bits_kernel(const int64_t* __restrict__ word, const uint32_t* __restrict__ bit, int n,
@@ -78,6 +190,7 @@ __global__ void check_sorted_kernel(const int64_t* __restrict__ batch, int n, in
 void free_plan(DensePlan* p, cudaStream_t s) {
   if (!p) return;
   tmp_free(p->tiles, s); tmp_free(p->node_slot, s); tmp_free(p->bitmap, s); tmp_free(p->light, s); tmp_free(p->heavy, s); tmp_free(p->row_fused, s); tmp_free(p->light_nf, s); tmp_free(p->csr_rows, s); tmp_free(p->x_src, s); tmp_free(p->x_slot, s); tmp_free(p->f32_tile_flags[0], s); tmp_free(p->f32_tile_flags[1], s);
+  tmp_free(p->ext_of_int, s); tmp_free(p->blk_list, s);
   free_csr(&p->residual, s);
   *p = DensePlan();
 }
@@ -85,7 +198,7 @@ void free_plan(DensePlan* p, cudaStream_t s) {
 size_t dense_image_elems(int n_tiles, int H, int Cpad) { return (size_t)n_tiles * 128 * H * Cpad * 2; }
 
 cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, const int64_t* batch, int num_real,
-                             int num_total, DensePlan* plan, cudaStream_t s, const char** err) {
+                             int num_total, DensePlan* plan, cudaStream_t s, const char** err, bool allow_reorder) {
   *err = "";
   free_plan(plan, s);
   cudaError_t ce = cudaSuccess;
@@ -107,6 +220,11 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   int B = 0;
   size_t words = 0;
   int block64 = 0;
+  int32_t* d_int_of_ext = nullptr; int32_t* d_g_n = nullptr; uint8_t* d_g_reorder = nullptr;
+  unsigned long long* d_counters = nullptr;
+  std::vector<uint8_t> g_reorder;
+  int n_reorder = 0, words_max = 0;
+  static const bool no_reorder_env = getenv("DA_NO_REORDER") != nullptr && getenv("DA_NO_REORDER")[0] == '1';
 
   DA_TRY(tmp_alloc(&d_bad, sizeof(int32_t), s));
   DA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), s));
@@ -121,6 +239,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     B = (int)hbatch[num_real - 1] + 1;
   }
   g_node0.assign(B, 0); g_n.assign(B, 0); g_bm_words.assign(B, 0); g_bm_off.assign(B, -1); g_tile0.assign(B, -1);
+  g_reorder.assign(B, 0);
   for (int i = 0; i < num_real && B > 0; ++i) g_n[hbatch[i]]++;
   for (int g = 1; g < B; ++g) g_node0[g] = g_node0[g - 1] + g_n[g - 1];
   if (B > 0 && E > 0) {
@@ -139,6 +258,13 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     const long long n = g_n[g];
     if (n < MIN_DENSE_NODES || (long long)hcnt[g] * DENSITY_DIV < n * n) continue;
     const int ntile = (int)((n + 127) / 128);
+    // worth reordering: more than two source blocks and at most half dense.  (A band of relative width w leaves
+    // 1 - w - 128 / n of a tile's blocks empty; above ~50 % nothing is left to skip -- and the reference's odd-degree
+    // Exphander graphs add a perfect matching p <-> p + n/2 that lands in the middle of what would be empty.)
+    static const bool force_reorder = getenv("DA_FORCE_REORDER") != nullptr && getenv("DA_FORCE_REORDER")[0] == '1';
+    if (allow_reorder && !no_reorder_env && n > 128 && ((long long)hcnt[g] * 2 <= n * n || (force_reorder && (long long)hcnt[g] * 10 < n * n * 9))) {
+      g_reorder[g] = 1; ++n_reorder;
+    }
     g_bm_words[g] = ntile * 4;   // one bit per image row of the graph (its nodes + the padding rows extra sources may use)
     g_bm_off[g] = (int64_t)words;
     g_tile0[g] = (int)tiles.size();
@@ -175,10 +301,30 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     DA_TRY(cudaMemcpyAsync(d_g_bm_words, g_bm_words.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
     DA_TRY(cudaMemcpyAsync(d_g_bm_off, g_bm_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
   }
+  if (plan->n_tiles > 0 && E > 0 && n_reorder > 0) {
+    // ---- internal node order: bitmap in the caller's order -> greedy ring walk per graph -> bitmap rebuilt in internal order
+    for (int g = 0; g < B; ++g) if (g_reorder[g] && g_bm_words[g] > words_max) words_max = g_bm_words[g];
+    DA_TRY(tmp_alloc(&plan->ext_of_int, sizeof(int32_t) * (size_t)num_total, s));
+    DA_TRY(tmp_alloc(&d_int_of_ext, sizeof(int32_t) * (size_t)num_total, s));
+    DA_TRY(tmp_alloc(&d_g_n, sizeof(int32_t) * B, s));
+    DA_TRY(tmp_alloc(&d_g_reorder, (size_t)B, s));
+    DA_TRY(cudaMemcpyAsync(d_g_n, g_n.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    DA_TRY(cudaMemcpyAsync(d_g_reorder, g_reorder.data(), (size_t)B, cudaMemcpyHostToDevice, s));
+    iota_kernel<<<(num_total + 255) / 256, 256, 0, s>>>(plan->ext_of_int, d_int_of_ext, num_total);
+    DA_TRY(cudaGetLastError());
+    classify_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, d_g_node0, d_g_bm_off,
+                                                                     d_g_bm_words, plan->bitmap, nullptr, nullptr);
+    DA_TRY(cudaGetLastError());
+    ring_order_kernel<<<B, 256, sizeof(uint32_t) * 2 * (size_t)words_max, s>>>(plan->bitmap, d_g_node0, d_g_n, d_g_bm_off, d_g_bm_words,
+                                                                             d_g_reorder, plan->ext_of_int, d_int_of_ext);
+    DA_TRY(cudaGetLastError());
+    DA_TRY(cudaMemsetAsync(plan->bitmap, 0, sizeof(uint32_t) * words, s));
+    plan->n_reordered_graphs = n_reorder;
+  }
   if (plan->n_tiles > 0 && E > 0) {
     DA_TRY(tmp_alloc(&flag, (size_t)E, s));
     classify_edges_kernel<<<(unsigned)((E + 255) / 256), 256, 0, s>>>(src, dst, E, batch, num_real, d_g_node0, d_g_bm_off,
-                                                                     d_g_bm_words, plan->bitmap, flag);
+                                                                     d_g_bm_words, plan->bitmap, flag, d_int_of_ext);
     DA_TRY(cudaGetLastError());
     DA_TRY(tmp_alloc(&res_src, sizeof(int64_t) * (size_t)E, s));
     DA_TRY(tmp_alloc(&res_dst, sizeof(int64_t) * (size_t)E, s));
@@ -192,6 +338,11 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     DA_TRY(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     DA_TRY(cudaStreamSynchronize(s));
     n_res = nsel;
+    if (d_int_of_ext && n_res > 0) {   // the residual CSR is in internal numbering too
+      relabel_kernel<<<(unsigned)((n_res + 255) / 256), 256, 0, s>>>(res_src, n_res, d_int_of_ext, num_real);
+      relabel_kernel<<<(unsigned)((n_res + 255) / 256), 256, 0, s>>>(res_dst, n_res, d_int_of_ext, num_real);
+      DA_TRY(cudaGetLastError());
+    }
     plan->n_dense_edges = E - n_res;
     ce = build_csr_compressed(res_src, res_dst, n_res, num_total, &plan->residual, s, err);
     if (ce != cudaSuccess) goto fail;
@@ -272,8 +423,21 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     }
     extra_sources = xs;
   }
-  if (plan->n_tiles > 0)
+  if (plan->n_tiles > 0) {
+    int max_blocks = 1;
+    for (TileInfo& t : tiles) { t.n_list = 0; t.list_off = 0; max_blocks = std::max(max_blocks, (t.gn + 63) / 64); }
     DA_TRY(copy_sync(plan->tiles, tiles.data(), sizeof(TileInfo) * tiles.size(), cudaMemcpyHostToDevice, s));
+    // per-tile lists of the source blocks that hold at least one edge (the final bitmap: in-graph + promoted bits)
+    plan->max_blocks = max_blocks;
+    unsigned long long hc[3] = {0, 0, 0};
+    DA_TRY(tmp_alloc(&plan->blk_list, sizeof(uint16_t) * tiles.size() * (size_t)max_blocks, s));
+    DA_TRY(tmp_alloc(&d_counters, sizeof(hc), s));
+    DA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(hc), s));
+    tile_blocks_kernel<<<plan->n_tiles, 128, 0, s>>>(plan->tiles, plan->bitmap, plan->blk_list, max_blocks, d_counters);
+    DA_TRY(cudaGetLastError());
+    DA_TRY(copy_sync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, s));
+    plan->n_blocks_total = (int64_t)hc[0]; plan->n_blocks_listed = (int64_t)hc[1]; plan->n_blocks_full = (int64_t)hc[2];
+  }
   {  // degree classes of the residual CSR (node order kept, real nodes before virtual rows)
     std::vector<int32_t> rp((size_t)num_total + 1), light, heavy, light_nf;
     std::vector<uint8_t> fused((size_t)num_total, 0);
@@ -342,10 +506,12 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
   }
   tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
   tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
+  tmp_free(d_int_of_ext, s); tmp_free(d_g_n, s); tmp_free(d_g_reorder, s); tmp_free(d_counters, s);
   return cudaSuccess;
 fail:
   tmp_free(dcnt, s); tmp_free(d_g_node0, s); tmp_free(d_g_bm_words, s); tmp_free(d_bad, s); tmp_free(d_g_bm_off, s);
   tmp_free(res_src, s); tmp_free(res_dst, s); tmp_free(d_nsel, s); tmp_free(flag, s); tmp_free(tmp, s);
+  tmp_free(d_int_of_ext, s); tmp_free(d_g_n, s); tmp_free(d_g_reorder, s); tmp_free(d_counters, s);
   free_plan(plan, s);
   return ce;
 #undef DA_TRY

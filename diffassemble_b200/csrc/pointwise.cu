@@ -30,10 +30,11 @@ prologue_kernel(PrologueArgs a) {
     *reinterpret_cast<float4*>(pro_sm + i) = __ldg(reinterpret_cast<const float4*>(a.w1pt_T + i));
   for (int idx = tid; idx < PRO_NB * 8; idx += PRO_NT) {
     const int nb = idx / 8, c = idx % 8, node = node0 + nb;
-    xs[nb][c] = (node < a.M && c < a.C_in) ? a.x[(size_t)node * a.C_in + c] : 0.f;
+    const int ext = (a.row_ext && node < a.M) ? a.row_ext[node] : node;   // the caller's row of this internal node
+    xs[nb][c] = (node < a.M && c < a.C_in) ? a.x[(size_t)ext * a.C_in + c] : 0.f;
     if (c == 0) {
       int tt = a.t_uniform;
-      if (a.t && node < a.M) tt = (int)a.t[node];
+      if (a.t && node < a.M) tt = (int)a.t[ext];
       ts[nb] = min(max(tt, 0), a.T - 1);
     }
   }
@@ -99,43 +100,6 @@ prologue_kernel(PrologueArgs a) {
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Sampler updates (one value per thread), evaluated op by op in the reference's order with
-// explicit round-to-nearest intrinsics so no FMA contraction changes the result.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ddpm_update(float x, float out, float noise, const da_step_coef& c) {
-  // spatial_diffusion.py:495-510
-  float mean = __fmul_rn(c.sqrt_recip_alpha, __fsub_rn(x, __fdiv_rn(__fmul_rn(c.beta_t, out), c.sqrt_one_minus_acp)));
-  if (c.t_index == 0) return mean;
-  return __fadd_rn(mean, __fmul_rn(sqrtf(c.posterior_variance), noise));
-}
-
-__device__ __forceinline__ float ddim_x0(float x, float out, const da_step_coef& c) {
-  // spatial_diffusion.py:603-606
-  if (c.pred == DA_PRED_START_X) return out;
-  float beta = __fsub_rn(1.f, c.acp);
-  return __fdiv_rn(__fsub_rn(x, __fmul_rn(sqrtf(beta), out)), sqrtf(c.acp));
-}
-
-__device__ __forceinline__ float ddim_update(float x, float out, float noise, const da_step_coef& c) {
-  // spatial_diffusion.py:548-627 with _get_variance :528-546 and _predict_eps_from_xstart :629-632
-  float x0 = ddim_x0(x, out, c);
-  float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c.sqrt_recip_acp, x), x0), c.sqrt_recipm1_acp);
-  float beta = __fsub_rn(1.f, c.acp), beta_prev = __fsub_rn(1.f, c.acp_prev);
-  float variance = __fmul_rn(__fdiv_rn(beta_prev, beta), __fsub_rn(1.f, __fdiv_rn(c.acp, c.acp_prev)));
-  float std_eta = __fmul_rn(c.eta, sqrtf(variance));
-  float dir = __fmul_rn(sqrtf(__fsub_rn(__fsub_rn(1.f, c.acp_prev), __fmul_rn(std_eta, std_eta))), eps);
-  float prev = __fadd_rn(__fmul_rn(sqrtf(c.acp_prev), x0), dir);
-  if (c.eta > 0.f) prev = __fadd_rn(prev, __fmul_rn(std_eta, noise));
-  return prev;
-}
-
-__device__ __forceinline__ float step_update(int mode, float x, float out, float noise, const da_step_coef& c) {
-  if (mode == STEP_DDPM) return ddpm_update(x, out, noise, c);
-  if (mode == STEP_DDIM) return ddim_update(x, out, noise, c);
-  return out;
-}
-
 // 2D head: out = W_b @ u + b_b (final_mlp[2], efficient_gat.py:91), fused with the sampler update.
 __global__ void head_final_2d_kernel(HeadFinalArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,11 +109,12 @@ __global__ void head_final_2d_kernel(HeadFinalArgs a) {
   float s = a.b_b[c];
   for (int k = 0; k < a.Nh; ++k) s = fmaf(a.w_b[c * a.Nh + k], u[k], s);
   float x = 0.f, nz = 0.f;
+  const int eidx = a.row_ext ? a.row_ext[node] * a.C_out + c : idx;   // state / noise / output are in the caller's order
   if (a.step_mode != STEP_NONE) {
-    x = a.x_in[idx];
-    if (a.noise) nz = a.noise[idx];
+    x = a.x_in[eidx];
+    if (a.noise) nz = a.noise[eidx];
   }
-  a.out[idx] = step_update(a.step_mode, x, s, nz, a.coef);
+  a.out[eidx] = step_update(a.step_mode, x, s, nz, a.coef);
 }
 
 // SE(3) head: one warp per node.  t = mlp_t[2](u[:256]); r = mlp_r[2](u[256:]);
@@ -176,7 +141,8 @@ __global__ void head_final_se3_kernel(HeadFinalArgs a) {
   float q[4];
   se3::axis_angle_to_unit_quat(o[3], o[4], o[5], q);
   float model_out[7] = {q[0], q[1], q[2], q[3], o[0], o[1], o[2]};
-  float* dst = a.out + (size_t)node * 7;
+  const int ext = a.row_ext ? a.row_ext[node] : node;
+  float* dst = a.out + (size_t)ext * 7;
   if (a.step_mode == STEP_NONE) {
 #pragma unroll
     for (int i = 0; i < 7; ++i) dst[i] = model_out[i];
@@ -184,7 +150,7 @@ __global__ void head_final_se3_kernel(HeadFinalArgs a) {
   }
   float x[7];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) x[i] = a.x_in[(size_t)node * 7 + i];
+  for (int i = 0; i < 7; ++i) x[i] = a.x_in[(size_t)ext * 7 + i];
   float y[7];
   se3::ddim_update_se3(x, model_out, a.coef, y);
 #pragma unroll

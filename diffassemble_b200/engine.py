@@ -165,6 +165,13 @@ class DenoiserEngine:
         self._check(self._lib.da_graph_stats(self._h, C.byref(nd), C.byref(nc), C.byref(ng)))
         return {"dense_edges": nd.value, "csr_edges": nc.value, "dense_graphs": ng.value}
 
+    def plan_info(self):
+        """What the dense-tile planner made of the bound graph (``da_graph_plan_info``)."""
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.da_graph_plan_info(self._h, out, 8))
+        keys = ("tiles", "blocks_total", "blocks_visited", "blocks_full", "reordered_graphs", "extra_sources", "fused_rows", "csr_rows")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def set_profiling(self, enable: bool):
         self._check(self._lib.da_set_profiling(self._h, 1 if enable else 0))
 
