@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "da_launch_count", "da_graph_stats", "da_set_profiling", "da_get_profile", "da_profile_tag_name",
     "da_op_linear", "da_op_graph_attention", "da_op_graph_attention_dense", "da_greedy_cost_assignment", "da_expander_edge_index", "da_graph_create", "da_graph_destroy",
     "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws", "da_op_segment_max", "da_adafactor_step", "da_graph_set_batch",
-    "da_op_linear_workspace_bytes", "da_graph_plan_info",
+    "da_op_linear_workspace_bytes", "da_graph_plan_info", "da_ddpm_step_t", "da_ddim_step_t", "da_forward_attn",
 ]
 
 
@@ -50,6 +50,14 @@ class da_step_coef(C.Structure):
         ("beta_t", C.c_float), ("sqrt_one_minus_acp", C.c_float), ("sqrt_recip_alpha", C.c_float),
         ("posterior_variance", C.c_float), ("acp", C.c_float), ("acp_prev", C.c_float),
         ("sqrt_recip_acp", C.c_float), ("sqrt_recipm1_acp", C.c_float), ("eta", C.c_float), ("cfg_w", C.c_float),
+    ]
+
+
+class da_schedule(C.Structure):
+    _fields_ = [
+        ("betas", C.c_void_p), ("alphas_cumprod", C.c_void_p), ("sqrt_one_minus_alphas_cumprod", C.c_void_p),
+        ("sqrt_recip_alphas", C.c_void_p), ("posterior_variance", C.c_void_p), ("sqrt_recip_alphas_cumprod", C.c_void_p),
+        ("sqrt_recipm1_alphas_cumprod", C.c_void_p), ("steps", C.c_int32), ("inference_ratio", C.c_int32),
     ]
 
 
@@ -84,8 +92,11 @@ def load_library():
     lib.da_set_graph.argtypes = [vp, vp, vp, i64, vp, i32, i32, vp, vp]
     lib.da_set_features.argtypes = [vp, vp, vp]
     lib.da_forward.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.da_forward_attn.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.da_ddpm_step.argtypes = [vp, vp, vp, C.POINTER(da_step_coef), vp, vp]
     lib.da_ddim_step.argtypes = [vp, vp, vp, C.POINTER(da_step_coef), vp, vp]
+    lib.da_ddpm_step_t.argtypes = [vp, vp, vp, vp, i32, C.POINTER(da_schedule), vp, vp]
+    lib.da_ddim_step_t.argtypes = [vp, vp, vp, vp, i32, C.c_float, C.POINTER(da_schedule), vp, vp]
     lib.da_ddim_update.argtypes = [vp, vp, vp, vp, C.POINTER(da_step_coef), vp, vp]
     lib.da_workspace_bytes.argtypes = [vp]
     lib.da_workspace_bytes.restype = C.c_size_t

@@ -324,11 +324,39 @@ class Eff_GAT(nn.Module, _EngineMixin):
 
     def forward_with_feats(self, xy_pos: Tensor, time: Tensor, patch_rgb: Tensor, edge_index: Tensor,
                            patch_feats: Tensor, batch, return_attention=False):
-        eng = self.engine_for(edge_index, patch_feats, batch)
         if return_attention:
-            out, alpha = eng.forward(xy_pos, time, return_alpha=True)
-            return out, [(self._ext_edge_index, alpha)]  # exophormer_gnn.py:203-208: edge list incl. virtual wiring
+            return self._forward_with_attentions(xy_pos, time, edge_index, patch_feats, batch)
+        eng = self.engine_for(edge_index, patch_feats, batch)
         return eng.forward(xy_pos, time), None
+
+    def _forward_with_attentions(self, xy_pos, time, edge_index, patch_feats, batch):
+        """``return_attention=True``: one ``(edge_index, alpha[E, H])`` tuple PER LAYER, as ``Transformer_GNN.forward``
+        returns them (``Transformer_GNN.py:29-46``); ``Exophormer_GNN.forward`` only keeps the LAST layer's tuple, with
+        the extended edge list that holds the virtual wiring (``exophormer_gnn.py:203-208``).  Attention weights per edge only exist on the CSR path, so this call
+        runs on a second engine in ``attn_mode="csr"`` whatever the module's mode is (the tensor-core tiles never
+        materialise per-edge weights); layer l's weights are obtained by truncating the stack after layer l -- the
+        reference's viz / app code calls this once per sample, not per step."""
+        eng = getattr(self, "_alpha_engine", None)
+        dev = torch.device("cuda", edge_index.device.index if edge_index.device.index is not None else torch.cuda.current_device())
+        if eng is None or eng.device != dev:
+            saved = self.attn_mode
+            self.attn_mode = "csr"
+            try:
+                eng = self._make_engine(dev)
+            finally:
+                self.attn_mode = saved
+            self._alpha_engine, self._alpha_wkey = eng, None
+        wkey = self._weights_state_key()
+        if wkey != self._alpha_wkey:
+            eng.load_weights(self._denoiser_state())
+            self._alpha_wkey = wkey
+        ext, num_total, virt_ids = self.gnn_backbone.extend_graph(edge_index, batch)
+        eng.set_graph(ext, batch, num_real=len(batch), num_total=num_total, virt_ids=virt_ids)
+        eng.set_features(patch_feats)
+        out, alphas = eng.forward(xy_pos, time, return_alpha=True, all_layers=True)
+        if self.gnn_backbone.arch == _cabi.DA_ARCH_EXOPHORMER:   # Exophormer_GNN.forward only keeps the last layer's (:203-208)
+            return out, [(ext, alphas[-1])]
+        return out, [(ext, a) for a in alphas]
 
     def visual_features(self, patch_rgb):
         if self.visual_backbone is None:

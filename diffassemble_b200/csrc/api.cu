@@ -79,6 +79,7 @@ struct da_handle {
   // activations / workspace
   DevBuf P, hbuf, combined, qkvs, xa, xb, r, u, model_out, scores, stats;
   // split-bf16 operand planes for the tensor-core path
+  DevBuf tmin;         // per-node-t sampler steps: min over the nodes of t (device scalar)
   DevBuf feats_perm;   // exact-fp32 mode: features gathered into the planner's internal node order
   DevBuf feats_sp_hi, feats_sp_lo, h_hi, h_lo, comb_hi, comb_lo, xa_hi, xa_lo, xb_hi, xb_lo, r_hi, r_lo;
   int64_t launches = 0;
@@ -156,7 +157,9 @@ cudaError_t upload(DevBuf& dst, const float* src, size_t n) {
 struct WView { const float* data; int64_t rows, cols; };
 
 int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_uniform, float* out, float* alpha_last,
-                 int step_mode, const da_step_coef* coef, const float* x_in, const float* noise, cudaStream_t s) {
+                 int step_mode, const da_step_coef* coef, const float* x_in, const float* noise, cudaStream_t s,
+                 const da_schedule* sched = nullptr, float* alpha_all = nullptr) {
+  if (alpha_all && !alpha_last) alpha_last = alpha_all + (size_t)(h->L - 1) * (size_t)h->csr.E * h->cfg.heads;   // [L, E, H]
   if (!h->weights_loaded) return h->fail(DA_ERR_MISSING, "weights not loaded (da_load_weights)");
   if (!h->graph_set) return h->fail(DA_ERR_INVALID, "graph not set (da_set_graph)");
   if (!h->feats_set) return h->fail(DA_ERR_INVALID, "features not set (da_set_features)");
@@ -247,11 +250,6 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       a.resid = h->combined.as<float>(); a.ld_resid = D;  // trunk residual feats + combined (efficient_gat.py:145)
       if (umma) { a.out.hi = h->r_hi.as<__nv_bfloat16>(); a.out.lo = h->r_lo.as<__nv_bfloat16>(); a.out.ld_split = D; }
       else { a.out.f32 = h->r.as<float>(); a.out.ldc = D; }
-      if (alpha_last) {
-        DA_CK(h->scores.ensure((size_t)(h->csr.E > 0 ? h->csr.E : 1) * c.heads * sizeof(float)), "alloc scores");
-        DA_CK(h->stats.ensure((size_t)Mt * c.heads * 2 * sizeof(float)), "alloc stats");
-        a.scores = h->scores.as<float>(); a.stats = h->stats.as<float>();
-      }
     } else {
       a.n_targets = Mt;
       DevBuf& yb = (l & 1) ? h->xb : h->xa;
@@ -260,6 +258,12 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       if (umma) { a.out.hi = yh.as<__nv_bfloat16>(); a.out.lo = yl.as<__nv_bfloat16>(); a.out.ld_split = HC; }
       else { a.out.f32 = yb.as<float>(); a.out.ldc = HC; }
       xin = yb.as<float>(); xin_hi = yh.as<__nv_bfloat16>(); xin_lo = yl.as<__nv_bfloat16>(); ld_in = HC;
+    }
+    float* alpha_l = last ? alpha_last : (alpha_all ? alpha_all + (size_t)l * (size_t)h->csr.E * c.heads : nullptr);
+    if (alpha_l) {   // attention weights of this layer in the caller's edge order (CSR mode only, checked above)
+      DA_CK(h->scores.ensure((size_t)(h->csr.E > 0 ? h->csr.E : 1) * c.heads * sizeof(float)), "alloc scores");
+      DA_CK(h->stats.ensure((size_t)Mt * c.heads * 2 * sizeof(float)), "alloc stats");
+      a.scores = h->scores.as<float>(); a.stats = h->stats.as<float>();
     }
     const bool rows_path = h->use_plan && attn_csr_rows_supported(c.heads, C) && !a.scores;
     AttnCsrArgs hv = a, lt = a;
@@ -341,10 +345,10 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
       DA_CK(launch_attn_csr(a, s), "graph attention");
     }
-    if (last && alpha_last) {
+    if (alpha_l) {
       Scoped sc(h, s, TAG_OTHER);
       DA_CK(launch_alpha_normalize(h->scores.as<float>(), h->stats.as<float>(), h->csr.rowptr, h->csr.eid, Mt,
-                                   c.heads, alpha_last, s), "alpha normalize");
+                                   c.heads, alpha_l, s), "alpha normalize");
     }
   }
   // 4. head: u = GELU(r @ Wa^T + ba) ; then final linear(s) + pose map + sampler update
@@ -358,6 +362,12 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     if (coef) a.coef = *coef;
     a.x_in = x_in; a.noise = noise; a.out = out;
     a.row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;
+    if (sched != nullptr && t_arr != nullptr && step_mode != STEP_NONE) {   // per-node schedule coefficients
+      DA_CK(h->tmin.ensure(sizeof(int32_t)), "alloc");
+      h->launches++;
+      DA_CK(launch_min_t(t_arr, Mr, h->tmin.as<int32_t>(), s), "min t");
+      a.tabs.sched = *sched; a.tabs.t = t_arr; a.tabs.tmin = h->tmin.as<int32_t>();
+    }
     // 2-D head on the tensor-core path: final_mlp[2] + the sampler update ride in the GEMM epilogue (one launch)
     const bool fused_head = umma && c.head_kind == DA_HEAD_2D && h->Nh == 32 && !h->no_head_fuse;
     LinearOut o;
@@ -445,7 +455,7 @@ void da_destroy(da_handle* h) {
                    &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
                    &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
                    &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l, &h->dacc, &h->dstats,
-                   &h->feats_perm};
+                   &h->feats_perm, &h->tmin};
   for (auto* b : all) b->release();
   free_csr(&h->csr);
   free_plan(&h->plan);
@@ -702,6 +712,14 @@ int da_forward(da_handle* h, const float* x, const int64_t* t, float* out, float
   return forward_impl(h, x, t, 0, out, alpha_last, STEP_NONE, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+int da_forward_attn(da_handle* h, const float* x, const int64_t* t, float* out, float* alpha_all, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x || !t || !out || !alpha_all) return h->fail(DA_ERR_INVALID, "null x / t / out / alpha");
+  if (h->cfg.attn_mode != DA_ATTN_CSR) return h->fail(DA_ERR_UNSUPPORTED, "attention weights are only produced with attn_mode = DA_ATTN_CSR");
+  cudaSetDevice(h->cfg.device);
+  return forward_impl(h, x, t, 0, out, nullptr, STEP_NONE, nullptr, nullptr, nullptr, (cudaStream_t)stream, nullptr, alpha_all);
+}
+
 int da_ddpm_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c, const float* noise, void* stream) {
   if (!h) return DA_ERR_INVALID;
   if (!x_in || !x_out || !c) return h->fail(DA_ERR_INVALID, "null argument");
@@ -718,6 +736,41 @@ int da_ddim_step(da_handle* h, const float* x_in, float* x_out, const da_step_co
   if (c->eta > 0.f && h->cfg.head_kind == DA_HEAD_SE3) return h->fail(DA_ERR_UNSUPPORTED, "SE3 sampler is eta = 0 only");
   cudaSetDevice(h->cfg.device);
   return forward_impl(h, x_in, nullptr, c->t, x_out, nullptr, STEP_DDIM, c, x_in, noise, (cudaStream_t)stream);
+}
+
+static int check_sched(da_handle* h, const da_schedule* sc) {
+  if (!sc || !sc->betas || !sc->alphas_cumprod || !sc->sqrt_one_minus_alphas_cumprod || !sc->sqrt_recip_alphas || !sc->posterior_variance ||
+      !sc->sqrt_recip_alphas_cumprod || !sc->sqrt_recipm1_alphas_cumprod)
+    return h->fail(DA_ERR_INVALID, "null schedule table");
+  if (sc->steps != h->cfg.steps || sc->inference_ratio <= 0) return h->fail(DA_ERR_INVALID, "schedule length / inference_ratio mismatch");
+  return DA_OK;
+}
+
+int da_ddpm_step_t(da_handle* h, const float* x_in, float* x_out, const int64_t* t, int32_t t_index, const da_schedule* sched,
+                   const float* noise, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x_in || !x_out || !t) return h->fail(DA_ERR_INVALID, "null argument");
+  if (int rc = check_sched(h, sched)) return rc;
+  if (h->cfg.head_kind != DA_HEAD_2D) return h->fail(DA_ERR_UNSUPPORTED, "DDPM step is defined for the 2D head only (the 3D module binds DDIM only)");
+  if (t_index != 0 && !noise) return h->fail(DA_ERR_INVALID, "DDPM step with t_index > 0 needs noise");
+  cudaSetDevice(h->cfg.device);
+  da_step_coef c{};
+  c.t_index = t_index; c.pred = DA_PRED_EPSILON; c.eta = 1.f;
+  return forward_impl(h, x_in, t, 0, x_out, nullptr, STEP_DDPM, &c, x_in, noise, (cudaStream_t)stream, sched);
+}
+
+int da_ddim_step_t(da_handle* h, const float* x_in, float* x_out, const int64_t* t, int32_t pred, float eta, const da_schedule* sched,
+                   const float* noise, void* stream) {
+  if (!h) return DA_ERR_INVALID;
+  if (!x_in || !x_out || !t) return h->fail(DA_ERR_INVALID, "null argument");
+  if (int rc = check_sched(h, sched)) return rc;
+  if (eta > 0.f && !noise) return h->fail(DA_ERR_INVALID, "DDIM step with eta > 0 needs noise");
+  if (eta > 0.f && h->cfg.head_kind == DA_HEAD_SE3) return h->fail(DA_ERR_UNSUPPORTED, "SE3 sampler is eta = 0 only");
+  if (pred != DA_PRED_START_X && pred != DA_PRED_EPSILON) return h->fail(DA_ERR_INVALID, "unknown pred");
+  cudaSetDevice(h->cfg.device);
+  da_step_coef c{};
+  c.pred = pred; c.eta = eta;
+  return forward_impl(h, x_in, t, 0, x_out, nullptr, STEP_DDIM, &c, x_in, noise, (cudaStream_t)stream, sched);
 }
 
 int da_ddim_update(da_handle* h, const float* x_in, const float* model_out, float* x_out, const da_step_coef* c,

@@ -146,6 +146,30 @@ cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s);
 // sampler update modes for the head epilogue
 enum StepMode : int { STEP_NONE = 0, STEP_DDPM = 1, STEP_DDIM = 2 };
 
+// per-node timesteps: schedule tables on the device + the batch-wide minimum of t (for "(prev_timestep >= 0).all()")
+struct StepTables {
+  da_schedule sched;
+  const int64_t* t = nullptr;    // [M] per node, the caller's order (null = uniform t: coefficients come in da_step_coef)
+  const int32_t* tmin = nullptr; // device scalar: min over the nodes of t
+};
+__device__ __forceinline__ da_step_coef node_coef(const da_step_coef& base, const StepTables& tb, int ext) {
+  da_step_coef c = base;
+  int t = (int)tb.t[ext];
+  t = t < 0 ? 0 : (t >= tb.sched.steps ? tb.sched.steps - 1 : t);
+  c.t = t;
+  c.beta_t = tb.sched.betas[t];
+  c.sqrt_one_minus_acp = tb.sched.sqrt_one_minus_alphas_cumprod[t];
+  c.sqrt_recip_alpha = tb.sched.sqrt_recip_alphas[t];
+  c.posterior_variance = tb.sched.posterior_variance[t];
+  c.acp = tb.sched.alphas_cumprod[t];
+  c.sqrt_recip_acp = tb.sched.sqrt_recip_alphas_cumprod[t];
+  c.sqrt_recipm1_acp = tb.sched.sqrt_recipm1_alphas_cumprod[t];
+  const bool all_prev = *tb.tmin >= tb.sched.inference_ratio;   // (prev_timestep >= 0).all()
+  c.has_prev = all_prev ? 1 : 0;
+  c.acp_prev = all_prev ? tb.sched.alphas_cumprod[t - tb.sched.inference_ratio] : 1.f;
+  return c;
+}
+
 struct HeadFinalArgs {
   const float* u;        // [M, Nh] hidden of the head after GELU
   int Nh;
@@ -160,7 +184,9 @@ struct HeadFinalArgs {
   const float* noise;    // [M, C] or null
   float* out;            // [M, C_out] model output (STEP_NONE) or x_prev
   const int32_t* row_ext = nullptr;   // optional: internal row r reads / writes the caller's row row_ext[r] of x_in, noise, out
+  StepTables tabs;                    // tabs.t != null: per-node schedule coefficients (gathered on the device)
 };
+cudaError_t launch_min_t(const int64_t* t, int n, int32_t* out, cudaStream_t s);
 cudaError_t launch_head_final(const HeadFinalArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------

@@ -272,6 +272,8 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
 #pragma unroll
             for (int k = 0; k < 32; ++k) u[k] = apply_act_rt(__uint_as_float(r[k]) + (p.bias ? __ldg(p.bias + n0 + k) : 0.f), p.act);
             const int ext = hd.row_ext ? __ldg(hd.row_ext + row) : row;
+            da_step_coef cf_ = hd.coef;
+            if (hd.tabs.t != nullptr && hd.step_mode != STEP_NONE) cf_ = node_coef(hd.coef, hd.tabs, ext);
             for (int c = 0; c < hd.C_out; ++c) {
               float sacc = __ldg(hd.b_b + c);
 #pragma unroll
@@ -282,7 +284,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                 x = hd.x_in[eidx];
                 if (hd.noise) nz = hd.noise[eidx];
               }
-              hd.out[eidx] = step_update(hd.step_mode, x, sacc, nz, hd.coef);
+              hd.out[eidx] = step_update(hd.step_mode, x, sacc, nz, cf_);
             }
           }
           continue;

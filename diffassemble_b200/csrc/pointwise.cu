@@ -114,7 +114,12 @@ __global__ void head_final_2d_kernel(HeadFinalArgs a) {
     x = a.x_in[eidx];
     if (a.noise) nz = a.noise[eidx];
   }
-  a.out[eidx] = step_update(a.step_mode, x, s, nz, a.coef);
+  if (a.tabs.t != nullptr && a.step_mode != STEP_NONE) {
+    const da_step_coef cn = node_coef(a.coef, a.tabs, a.row_ext ? a.row_ext[node] : node);
+    a.out[eidx] = step_update(a.step_mode, x, s, nz, cn);
+  } else {
+    a.out[eidx] = step_update(a.step_mode, x, s, nz, a.coef);
+  }
 }
 
 // SE(3) head: one warp per node.  t = mlp_t[2](u[:256]); r = mlp_r[2](u[256:]);
@@ -152,7 +157,8 @@ __global__ void head_final_se3_kernel(HeadFinalArgs a) {
 #pragma unroll
   for (int i = 0; i < 7; ++i) x[i] = a.x_in[(size_t)ext * 7 + i];
   float y[7];
-  se3::ddim_update_se3(x, model_out, a.coef, y);
+  if (a.tabs.t != nullptr) se3::ddim_update_se3(x, model_out, node_coef(a.coef, a.tabs, ext), y);
+  else se3::ddim_update_se3(x, model_out, a.coef, y);
 #pragma unroll
   for (int i = 0; i < 7; ++i) dst[i] = y[i];
 }
@@ -177,6 +183,13 @@ __global__ void sampler_update_se3_kernel(const float* __restrict__ x_in, const 
   for (int i = 0; i < 7; ++i) x_out[(size_t)node * 7 + i] = y[i];
 }
 
+__global__ void min_t_kernel(const int64_t* __restrict__ t, int n, int32_t* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = i < n ? (int)t[i] : 0x7fffffff;
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(out, v);
+}
+
 __global__ void fill_rows_kernel(float* __restrict__ dst, int ld, const float* __restrict__ table,
                                  const int32_t* __restrict__ ids, int rows, int cols) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,6 +211,13 @@ cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
     smem_set = smem;
   }
   prologue_kernel<<<(a.M + PRO_NB - 1) / PRO_NB, PRO_NT, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_min_t(const int64_t* t, int n, int32_t* out, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(out, 0x7f, sizeof(int32_t), s);
+  if (e != cudaSuccess || n <= 0) return e;
+  min_t_kernel<<<(n + 255) / 256, 256, 0, s>>>(t, n, out);
   return cudaGetLastError();
 }
 

@@ -120,11 +120,15 @@ class DenoiserEngine:
         self._check(self._lib.da_set_features(self._h, _ptr(feats), _stream(self.device)))
 
     # -- compute -----------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, t: torch.Tensor, return_alpha: bool = False):
+    def forward(self, x: torch.Tensor, t: torch.Tensor, return_alpha: bool = False, all_layers: bool = False):
         _require_cuda(x, "x")
         x = x.to(dtype=torch.float32).contiguous()
         t = t.to(device=self.device, dtype=torch.int64).contiguous()
         out = torch.empty((self.num_real, self.out_channels), dtype=torch.float32, device=self.device)
+        if return_alpha and all_layers:   # one [E, H] tensor per layer (da_forward_attn)
+            alphas = torch.empty((self.cfg.n_layers, self.num_edges, self.heads), dtype=torch.float32, device=self.device)
+            self._check(self._lib.da_forward_attn(self._h, _ptr(x), _ptr(t), _ptr(out), _ptr(alphas), _stream(self.device)))
+            return out, list(alphas.unbind(0))
         alpha = None
         if return_alpha:
             alpha = torch.empty((self.num_edges, self.heads), dtype=torch.float32, device=self.device)
@@ -146,6 +150,31 @@ class DenoiserEngine:
 
     def ddim_step(self, x, coef, noise=None, out=None):
         return self._step(self._lib.da_ddim_step, x, coef, noise, out)
+
+    def _step_t(self, x, t, noise, out):
+        _require_cuda(x, "x")
+        x = x.to(dtype=torch.float32).contiguous()
+        t = t.to(device=self.device, dtype=torch.int64).contiguous()
+        if t.shape[0] != self.num_real:
+            raise ValueError(f"t has {t.shape[0]} entries, expected one per node ({self.num_real})")
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
+        return x, t, noise, (torch.empty_like(x) if out is None else out)
+
+    def ddpm_step_t(self, x, t, t_index: int, sched, noise=None, out=None):
+        """``da_ddpm_step_t``: per-node timesteps, schedule coefficients gathered on the device (no host look at t)."""
+        x, t, noise, out = self._step_t(x, t, noise, out)
+        self._keep["sched"] = sched
+        self._check(self._lib.da_ddpm_step_t(self._h, _ptr(x), _ptr(out), _ptr(t), int(t_index), C.byref(sched.struct), _ptr(noise),
+                                             _stream(self.device)))
+        return out
+
+    def ddim_step_t(self, x, t, pred: int, eta: float, sched, noise=None, out=None):
+        x, t, noise, out = self._step_t(x, t, noise, out)
+        self._keep["sched"] = sched
+        self._check(self._lib.da_ddim_step_t(self._h, _ptr(x), _ptr(out), _ptr(t), int(pred), float(eta), C.byref(sched.struct), _ptr(noise),
+                                             _stream(self.device)))
+        return out
 
     def ddim_update(self, x, model_out, coef, noise=None):
         out = torch.empty_like(x)

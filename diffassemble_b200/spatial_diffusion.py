@@ -128,6 +128,28 @@ class DiffusionScheduleMixin:
         c.cfg_w = float(getattr(self, "classifier_free_w", 0.0))
         return c
 
+    def _device_schedule(self):
+        """The registered schedule buffers as a ``da_schedule`` (device pointers) for the per-node-t sampler steps."""
+        from ._cabi import da_schedule
+
+        names = ("betas", "alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_recip_alphas", "posterior_variance",
+                 "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod")
+        key = tuple((getattr(self, n).data_ptr(), getattr(self, n)._version) for n in names) + (int(self.inference_ratio),)
+        cur = self.__dict__.get("_dev_sched")
+        if cur is None or cur.key != key:
+            class _Sched:   # keeps the fp32 contiguous tensors alive next to the struct that points at them
+                pass
+
+            cur = _Sched()
+            cur.key = key
+            cur.tensors = [getattr(self, n).detach().to(torch.float32).contiguous() for n in names]
+            for t in cur.tensors:
+                if not t.is_cuda:
+                    raise RuntimeError("the schedule buffers are on the CPU: move the module to cuda (no CPU path)")
+            cur.struct = da_schedule(*[t.data_ptr() for t in cur.tensors], int(self.steps), int(self.inference_ratio))
+            self.__dict__["_dev_sched"] = cur
+        return cur
+
     def _pred_code(self) -> int:
         if self.model_mean_type == ModelMeanType.START_X:
             return _cabi.DA_PRED_START_X
@@ -323,31 +345,29 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
         raise NotImplementedError()
 
     # -- reverse diffusion -------------------------------------------------------------------
-    def _uniform_t(self, t: Tensor, t_index: int) -> bool:
-        return bool((t == int(t_index)).all())
-
     @torch.no_grad()
     def p_sample_ddpm(self, x, t, t_index, cond, edge_index, patch_feats, batch, noise=None):
-        """``spatial_diffusion.py:485-510``: fused denoiser + posterior-mean update."""
+        """``spatial_diffusion.py:485-510``: fused denoiser + posterior-mean update.  ``t`` is the reference's per-node
+        tensor: the schedule coefficients are gathered per node ON THE DEVICE (``extract``, :173-176), so nothing here
+        looks at ``t`` on the host (no synchronisation); ``t_index`` only decides whether noise is added, as in the
+        reference."""
         if self.model_mean_type != ModelMeanType.EPSILON:
             raise NotImplementedError("p_sample_ddpm treats the model output as epsilon (spatial_diffusion.py:495-502)")
-        if not self._uniform_t(t, t_index):
-            raise NotImplementedError("the fused DDPM step needs t == t_index for every node (spatial_diffusion.py:665)")
         eng = self.model.engine_for(edge_index, patch_feats, batch)
         if int(t_index) != 0 and noise is None:
             noise = torch.randn_like(x)
-        coef = self._step_coef(int(t_index), _cabi.DA_PRED_EPSILON)
-        return eng.ddpm_step(x, coef, noise if int(t_index) != 0 else None), None
+        return eng.ddpm_step_t(x, t, int(t_index), self._device_schedule(), noise if int(t_index) != 0 else None), None
 
     @torch.no_grad()
     def p_sample_ddim(self, x, t, t_index, cond, edge_index, patch_feats, batch, noise=None):
-        """``spatial_diffusion.py:548-627`` (incl. classifier-free guidance :568-589)."""
-        if not self._uniform_t(t, t_index):
-            raise NotImplementedError("the fused DDIM step needs t == t_index for every node (spatial_diffusion.py:665)")
-        coef = self._step_coef(int(t_index), self._pred_code())
+        """``spatial_diffusion.py:548-627`` (incl. classifier-free guidance :568-589); per-node ``t`` as above, and the
+        reference's ``(prev_timestep >= 0).all()`` (:560, :535) is evaluated on the device."""
         if self.eta > 0 and noise is None:
             noise = torch.randn(x.shape, dtype=x.dtype, device=x.device)
         if self.classifier_free_prob > 0.0:
+            # the blended model output goes through the update alone, with the scalar coefficients of t_index (the
+            # reference's loop always passes t == t_index; a non-uniform t is not defined for the guidance branch here)
+            coef = self._step_coef(int(t_index), self._pred_code())
             eng = self.model.engine_for(edge_index, patch_feats, batch)
             out_cond = eng.forward(x, t)
             eng = self.model.engine_for(edge_index, None, batch)  # patch_feats = zeros (:578-586)
@@ -355,7 +375,7 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             model_output = (1 + self.classifier_free_w) * out_cond - self.classifier_free_w * out_uncond
             return eng.ddim_update(x, model_output, coef, noise if self.eta > 0 else None), None
         eng = self.model.engine_for(edge_index, patch_feats, batch)
-        return eng.ddim_step(x, coef, noise if self.eta > 0 else None), None
+        return eng.ddim_step_t(x, t, self._pred_code(), float(self.eta), self._device_schedule(), noise if self.eta > 0 else None), None
 
     @torch.no_grad()
     def _p_sample(self, x, t, t_index, cond, edge_index, sampling_func, patch_feats, batch, noise=None):

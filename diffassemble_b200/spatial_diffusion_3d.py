@@ -105,10 +105,9 @@ class GNN_Diffusion_3d(_Base, DiffusionScheduleMixin):
 
     @torch.no_grad()
     def p_sample_ddim(self, x, t, t_index, edge_index, pcd_feats, batch):  # :595-663
-        if not bool((t == int(t_index)).all()):
-            raise NotImplementedError("the fused DDIM step needs t == t_index for every node")
+        # per-node t: coefficients gathered on the device, no host look at t (see GNN_Diffusion.p_sample_ddim)
         eng = self.model.engine_for(edge_index, pcd_feats, batch)
-        return eng.ddim_step(x, self._step_coef(int(t_index), self._pred_code())), None
+        return eng.ddim_step_t(x, t, self._pred_code(), 0.0, self._device_schedule()), None
 
     @torch.no_grad()
     def _p_sample(self, x, t, t_index, edge_index, sampling_func, pcd_feats, batch):

@@ -134,6 +134,11 @@ int da_set_features(da_handle* h, const float* feats, void* stream);
 int da_forward(da_handle* h, const float* x, const int64_t* t, float* out, float* alpha_last,
                void* stream);
 
+/* Same forward, returning the attention weights of EVERY layer as the reference's Transformer_GNN / Exophormer_GNN do
+ * (one (edge_index, alpha) tuple per layer, Transformer_GNN.py:29-46): alpha_all is fp32 [n_layers, E, H] in the caller's
+ * edge order.  DA_ATTN_CSR only (the tensor-core tiles never materialise per-edge weights). */
+int da_forward_attn(da_handle* h, const float* x, const int64_t* t, float* out, float* alpha_all, void* stream);
+
 /* Scalar schedule coefficients of one sampler step, computed by the caller in fp32
  * exactly as the reference does from its registered buffers
  * (spatial_diffusion.py:289-321). */
@@ -166,6 +171,28 @@ int da_ddpm_step(da_handle* h, const float* x_in, float* x_out, const da_step_co
  * update of spatial_diffusion_3d_test_double_diffusion.py:595-685. */
 int da_ddim_step(da_handle* h, const float* x_in, float* x_out, const da_step_coef* c,
                  const float* noise, void* stream);
+
+/* Per-node timesteps (the reference gathers every schedule coefficient per node, `extract`, spatial_diffusion.py:173-176;
+ * p_sample is called with a [nodes] tensor t).  The registered schedule buffers of the module are passed as device pointers
+ * and gathered on the device, so a caller of p_sample never has to inspect t on the host. */
+typedef struct da_schedule {
+  const float* betas;                          /* all fp32 device arrays of length `steps` */
+  const float* alphas_cumprod;
+  const float* sqrt_one_minus_alphas_cumprod;
+  const float* sqrt_recip_alphas;
+  const float* posterior_variance;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  int32_t steps;
+  int32_t inference_ratio;                     /* DDIM: prev_timestep = t - inference_ratio (spatial_diffusion.py:557) */
+} da_schedule;
+/* da_ddpm_step / da_ddim_step with t int64 [num_real] on the device.  t_index is the reference's Python int (DDPM adds no
+ * noise when it is 0); DDIM's "(prev_timestep >= 0).all()" is evaluated on the device over all nodes, as the reference
+ * evaluates it over the whole batch (spatial_diffusion.py:535,560). */
+int da_ddpm_step_t(da_handle* h, const float* x_in, float* x_out, const int64_t* t, int32_t t_index,
+                   const da_schedule* sched, const float* noise, void* stream);
+int da_ddim_step_t(da_handle* h, const float* x_in, float* x_out, const int64_t* t, int32_t pred, float eta,
+                   const da_schedule* sched, const float* noise, void* stream);
 
 /* Sampler update alone on a given model output (used for classifier-free guidance,
  * where two forwards are blended first, spatial_diffusion.py:568-589). */
