@@ -322,3 +322,17 @@ def test_mirror_signatures_cover_reference_signatures():
                 assert p.default is not inspect._empty, (key, name)
                 got = p.default.name if hasattr(p.default, "name") and hasattr(p.default, "value") else repr(p.default)
                 assert got == dflt, (key, name, got, dflt)
+
+
+def test_dense_attention_kernel_keeps_two_ctas_per_sm(lib_built):
+    """The 32-channel dense attention kernel is paced by its softmax warps and needs TWO resident CTAs per SM:
+    2 x 192 threads x R registers <= 65536 -> R <= 168 (after rounding to the allocation granule).  ptxas' allocation of
+    this kernel moves between 165 and 196 registers with unrelated edits (measured: 171 registers = one CTA per SM =
+    0.26 ms instead of 0.19 ms per launch), so the build log is checked here, on the CPU, every round."""
+    import re
+    from pathlib import Path
+
+    log = (Path(lib_built).parent.parent / "build" / "attn_dense.log").read_text()
+    m = re.search(r"attn_dense_kernelILi32ELi4E.*?Used (\d+) registers", log, re.S)
+    assert m, "attn_dense_kernel<32, 4> not found in the ptxas log"
+    assert int(m.group(1)) <= 168, f"attn_dense_kernel<32, 4> uses {m.group(1)} registers: only one CTA per SM would fit"
