@@ -13,9 +13,11 @@ namespace {
 //   here: h = act(P + W1[:, Dv:Dv+64] @ [pos(32), temb(32)]) with P = feats @ W1[:, :Dv]^T + b1
 //   hoisted out of the step loop by da_set_features (it does not depend on x or t).
 // ---------------------------------------------------------------------------------------------
-constexpr int PRO_NB = 64;     // nodes per CTA
 constexpr int PRO_NT = 256;
 
+// PRO_NB: nodes per CTA.  64 amortises the 32 KB weight stage best; 16 keeps all SMs busy when the whole batch is only a
+// few thousand nodes (the per-GPU share of a strong-scaled batch), where this kernel is pure latency.
+template <int PRO_NB>
 __global__ void __launch_bounds__(PRO_NT)
 prologue_kernel(PrologueArgs a) {
   extern __shared__ __align__(16) float pro_sm[];   // w1pt_T [64][Hm] staged once per CTA
@@ -206,11 +208,21 @@ cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
   const size_t smem = (size_t)64 * a.Hm * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {   // static (23 KB) + dynamic shared memory exceeds the 48 KB default
-    cudaError_t e = cudaFuncSetAttribute(prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(prologue_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  prologue_kernel<<<(a.M + PRO_NB - 1) / PRO_NB, PRO_NT, smem, s>>>(a);
+  if (a.M <= 148 * 48) {
+    static size_t smem_set16 = 0;
+    if (smem > smem_set16) {
+      cudaError_t e = cudaFuncSetAttribute(prologue_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      smem_set16 = smem;
+    }
+    prologue_kernel<16><<<(a.M + 15) / 16, PRO_NT, smem, s>>>(a);
+  } else {
+    prologue_kernel<64><<<(a.M + 63) / 64, PRO_NT, smem, s>>>(a);
+  }
   return cudaGetLastError();
 }
 
