@@ -26,7 +26,7 @@ def product_2d(d, gemm, attn, steps=None):
         steps=steps or d["T"], sampling=d["sampling"], rotation=d["rotation"], architecture=d["architecture"],
         virt_nodes=d["virt_nodes"], model_mean_type=dab.ModelMeanType[d["mean_type"]], inference_ratio=d["ratio"],
         noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1],
-        scheduler=dab.ModelScheduler[d.get("scheduler", "LINEAR")], gemm_mode=gemm, attn_mode=attn)
+        scheduler=dab.ModelScheduler[d["scheduler"]], gemm_mode=gemm, attn_mode=attn)
     reseed_parameters(mod, d["seed"])
     return mod.to(DEV)
 
@@ -73,7 +73,7 @@ def test_cuda_matches_reference_3d(name, gemm, attn):
     d = torch.load(G / f"ref_{name}.pt")
     mod = dab.GNN_Diffusion_3d(steps=d["T"], sampling="DDIM", backbone="pointnet", inference_ratio=d["ratio"],
                                model_mean_type=dab.ModelMeanType.START_X, noise_weight=1.0,
-                               architecture=d.get("architecture", "transformer"), gemm_mode=gemm, attn_mode=attn)
+                               architecture=d["architecture"], gemm_mode=gemm, attn_mode=attn)
     reseed_parameters(mod, d["seed"])
     mod = mod.to(DEV)
     x, ei, feats, batch = (d[k].to(DEV) for k in ("x", "edge_index", "feats", "batch"))

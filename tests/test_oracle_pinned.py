@@ -31,7 +31,7 @@ def oracle_2d(d, steps=None):
         steps=steps or d["T"], sampling=d["sampling"], rotation=d["rotation"], architecture=d["architecture"],
         virt_nodes=d["virt_nodes"], model_mean_type=oracle.ModelMeanType[d["mean_type"]], inference_ratio=d["ratio"],
         noise_weight=1.0, classifier_free_prob=d["cfg"][0], classifier_free_w=d["cfg"][1],
-        scheduler=oracle.ModelScheduler[d.get("scheduler", "LINEAR")]).eval()
+        scheduler=oracle.ModelScheduler[d["scheduler"]]).eval()
     return reseed_parameters(ref, d["seed"])
 
 
@@ -71,7 +71,7 @@ def test_oracle_matches_reference_3d(name):
     d = torch.load(G / f"ref_{name}.pt")
     ref = oracle.GNNDiffusion3dRef(steps=d["T"], backbone="pointnet", inference_ratio=d["ratio"],
                                    model_mean_type=oracle.ModelMeanType.START_X, noise_weight=1.0,
-                                   architecture=d.get("architecture", "transformer")).eval()
+                                   architecture=d["architecture"]).eval()
     reseed_parameters(ref, d["seed"])
     with torch.no_grad():
         for ti, want_f, want_s in zip(d["step_ts"], d["fwd_out"], d["step_out"]):
