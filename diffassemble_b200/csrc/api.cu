@@ -1091,6 +1091,35 @@ int da_op_segment_max(const float* x, int32_t ld, const int32_t* seg_ptr, int32_
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+// ---- scope row N4: convolution pieces of the EfficientNet-B0 patch encoder (NHWC fp32) --------------------------------
+int da_op_conv2d_nhwc(const float* x, const float* w, const float* bias, float* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                      int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act, void* stream) {
+  if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 || pad < 0) return DA_ERR_INVALID;
+  cudaError_t ce = launch_conv2d_nhwc(x, w, bias, y, N, H, W, Cin, Cout, k, stride, pad, act, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_dwconv2d_nhwc(const float* x, const float* w, const float* bias, float* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t k, int32_t stride, int32_t pad, int32_t act, void* stream) {
+  if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || C <= 0 || k <= 0 || stride <= 0 || pad < 0) return DA_ERR_INVALID;
+  if (C % 4) return DA_ERR_UNSUPPORTED;
+  cudaError_t ce = launch_dwconv2d_nhwc(x, w, bias, y, N, H, W, C, k, stride, pad, act, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_spatial_mean(const float* x, float* y, int32_t ldy, int32_t N, int32_t HW, int32_t C, void* stream) {
+  if (!x || !y || N <= 0 || HW <= 0 || C <= 0 || ldy < C) return DA_ERR_INVALID;
+  cudaError_t ce = launch_spatial_mean(x, y, ldy, N, HW, C, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_channel_scale(float* x, const float* gate, int32_t ldg, int32_t N, int32_t HW, int32_t C, void* stream) {
+  if (!x || !gate || N <= 0 || HW <= 0 || C <= 0 || ldg < C) return DA_ERR_INVALID;
+  if (C % 4 || ldg % 4) return DA_ERR_UNSUPPORTED;
+  cudaError_t ce = launch_channel_scale(x, gate, ldg, N, HW, C, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

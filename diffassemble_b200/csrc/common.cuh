@@ -9,25 +9,31 @@
 
 namespace da {
 
-enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_RELU = 3 };
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_SIGMOID = 5 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() / F.gelu default = exact erf form (efficient_gat.py:89,95,100; Transformer_GNN.py:36)
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float lrelu02(float x) { return x > 0.f ? x : 0.2f * x; }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }   // x * sigmoid(x) (EfficientNet, scope row N4)
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   if (ACT == ACT_GELU) return gelu_erf(x);
   if (ACT == ACT_LRELU) return lrelu02(x);
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == ACT_SILU) return silu_f(x);
+  if (ACT == ACT_SIGMOID) return sigmoid_f(x);
   return x;
 }
 __device__ __forceinline__ float apply_act_rt(float x, int act) {
   if (act == ACT_GELU) return gelu_erf(x);
   if (act == ACT_LRELU) return lrelu02(x);
   if (act == ACT_RELU) return fmaxf(x, 0.f);
+  if (act == ACT_SILU) return silu_f(x);
+  if (act == ACT_SIGMOID) return sigmoid_f(x);
   return x;
 }
 
@@ -291,6 +297,14 @@ cudaError_t launch_attn_backward_dense(const float* qkvs, const float* dO, const
 cudaError_t launch_adafactor(const da_adafactor_param* params_dev, int n, float eps1, float eps2, float clip, float weight_decay,
                              cudaStream_t s);
 cudaError_t launch_linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int N, int K, cudaStream_t s);
+
+// NHWC fp32 convolution pieces of the EfficientNet-B0 patch encoder (scope row N4, conv.cu); bias + activation fused
+cudaError_t launch_conv2d_nhwc(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
+                               int k, int stride, int pad, int act, cudaStream_t s);      // w [Cout][k][k][Cin]
+cudaError_t launch_dwconv2d_nhwc(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int C, int k,
+                                 int stride, int pad, int act, cudaStream_t s);           // w [k][k][C]
+cudaError_t launch_spatial_mean(const float* x, float* y, int ldy, int N, int HW, int C, cudaStream_t s);   // y[n, c] = mean over HW
+cudaError_t launch_channel_scale(float* x, const float* gate, int ldg, int N, int HW, int C, cudaStream_t s);   // x[n, :, c] *= gate[n, c]
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);

@@ -176,6 +176,8 @@ cudaError_t launch_linear_simt(const float* a, int lda, const float* w, int ldw,
     case ACT_GELU: DA_LAUNCH(ACT_GELU); break;
     case ACT_LRELU: DA_LAUNCH(ACT_LRELU); break;
     case ACT_RELU: DA_LAUNCH(ACT_RELU); break;
+    case ACT_SILU: DA_LAUNCH(ACT_SILU); break;
+    case ACT_SIGMOID: DA_LAUNCH(ACT_SIGMOID); break;
     default: return cudaErrorInvalidValue;
   }
 #undef DA_LAUNCH

@@ -218,7 +218,7 @@ int da_get_profile(da_handle* h, double* ms_out, int64_t* launches_out, int32_t 
 const char* da_profile_tag_name(int32_t i);
 
 /* Stand-alone operator entry points (unit-level parity tests and micro-benchmarks).
- * y[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]); act: 0 none, 1 GELU(erf), 2 LeakyReLU(0.2), 3 ReLU.
+ * y[M,N] = act(a[M,K] @ w[N,K]^T + bias[N]); act: 0 none, 1 GELU(erf), 2 LeakyReLU(0.2), 3 ReLU, 4 SiLU, 5 sigmoid.
  * mode = DA_GEMM_*; all pointers device fp32. */
 int da_op_linear(int32_t mode, const float* a, const float* w, const float* bias, float* y,
                  int32_t M, int32_t N, int32_t K, int32_t act, void* stream);
@@ -245,6 +245,20 @@ int da_adafactor_step(const da_adafactor_param* params, int32_t n, float eps1, f
  * scope row N4; the point-wise layers of that encoder are da_op_linear calls with eval-mode BatchNorm folded in. */
 int da_op_segment_max(const float* x, int32_t ld, const int32_t* seg_ptr, int32_t n_seg, int32_t cols, float* out,
                       void* stream);
+/* Scope row N4, 2-D side -- the pieces of the EfficientNet-B0 patch encoder that are not plain GEMMs (Eff_GAT.visual_features,
+ * efficient_gat.py:40-42,149-189; timm's efficientnet_b0 feature pyramid).  All tensors NHWC fp32 on the device, eval-mode
+ * BatchNorm folded into w / bias by the caller, act as in da_op_linear plus 4 = SiLU, 5 = sigmoid.  The point-wise (1x1)
+ * convolutions and the squeeze-excite FCs are da_op_linear calls over [N*H*W, C] rows.
+ *   da_op_conv2d_nhwc   : dense k x k convolution, w [Cout][k][k][Cin] (the 3 -> 32 stem)
+ *   da_op_dwconv2d_nhwc : depth-wise k x k convolution, w [k][k][C], C % 4 == 0
+ *   da_op_spatial_mean  : y[n, c] = mean over the HW pixels (squeeze), y row stride ldy
+ *   da_op_channel_scale : x[n, p, c] *= gate[n, c] in place (excite), gate row stride ldg */
+int da_op_conv2d_nhwc(const float* x, const float* w, const float* bias, float* y, int32_t N, int32_t H, int32_t W, int32_t Cin,
+                      int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t act, void* stream);
+int da_op_dwconv2d_nhwc(const float* x, const float* w, const float* bias, float* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                        int32_t k, int32_t stride, int32_t pad, int32_t act, void* stream);
+int da_op_spatial_mean(const float* x, float* y, int32_t ldy, int32_t N, int32_t HW, int32_t C, void* stream);
+int da_op_channel_scale(float* x, const float* gate, int32_t ldg, int32_t N, int32_t HW, int32_t C, void* stream);
 /* Same operator with caller-provided scratch (split-bf16 operand planes): no allocation, no synchronisation. */
 size_t da_op_linear_workspace_bytes(int32_t mode, int32_t M, int32_t N, int32_t K);
 int da_op_linear_ws(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,
