@@ -7,6 +7,7 @@ The public names mirror the reference's (``puzzle_diff/model``): ``GNN_Diffusion
 """
 from .backbones import Eff_GAT, Eff_GAT_3d, Exophormer_GNN, Transformer_GNN, TransformerConv  # noqa: F401
 from .engine import DenoiserEngine, op_graph_attention, op_graph_attention_dense, op_linear, op_segment_max  # noqa: F401
+from .efficientnet import EfficientNetB0Features  # noqa: F401
 from .pointnet import PointNet  # noqa: F401
 from .spatial_diffusion import (  # noqa: F401
     GNN_Diffusion,

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "da_launch_count", "da_graph_stats", "da_set_profiling", "da_get_profile", "da_profile_tag_name",
     "da_op_linear", "da_op_graph_attention", "da_op_graph_attention_dense", "da_greedy_cost_assignment", "da_expander_edge_index", "da_graph_create", "da_graph_destroy",
     "da_op_graph_attention_fwd", "da_op_graph_attention_bwd", "da_op_linear_wgrad", "da_op_linear_ws", "da_op_segment_max", "da_adafactor_step", "da_graph_set_batch",
-    "da_op_linear_workspace_bytes", "da_graph_plan_info", "da_ddpm_step_t", "da_ddim_step_t", "da_forward_attn", "da_op_conv2d_nhwc", "da_op_dwconv2d_nhwc", "da_op_spatial_mean", "da_op_channel_scale",
+    "da_op_linear_workspace_bytes", "da_graph_plan_info", "da_ddpm_step_t", "da_ddim_step_t", "da_forward_attn", "da_op_conv2d_nhwc", "da_op_dwconv2d_nhwc", "da_op_spatial_mean", "da_op_channel_scale", "da_op_normalize_to_nhwc", "da_op_add_inplace",
 ]
 
 
@@ -113,6 +113,8 @@ def load_library():
     lib.da_op_dwconv2d_nhwc.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.da_op_spatial_mean.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.da_op_channel_scale.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.da_op_normalize_to_nhwc.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.da_op_add_inplace.argtypes = [vp, vp, i64, vp]
     lib.da_op_segment_max.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     lib.da_adafactor_step.argtypes = [vp, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp]
     lib.da_op_graph_attention.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp, vp, vp]

@@ -263,6 +263,26 @@ class _EngineMixin:
         self._prefetched = None
         return True
 
+    def zero_feature_engine(self, edge_index: Tensor, batch: Tensor) -> DenoiserEngine:
+        """A second engine bound to the same graph with all-zero features (the unconditional pass of classifier-free
+        guidance, ``spatial_diffusion.py:578-586``), kept next to the main one so that neither re-binds per step."""
+        dev = torch.device("cuda", edge_index.device.index if edge_index.device.index is not None else torch.cuda.current_device())
+        eng = getattr(self, "_zero_engine", None)
+        if eng is None or eng.device != dev:
+            eng = self._make_engine(dev)
+            self._zero_engine, self._zero_wkey, self._zero_gkey = eng, None, None
+        wkey = self._weights_state_key()
+        if wkey != self._zero_wkey:
+            eng.load_weights(self._denoiser_state())
+            self._zero_wkey, self._zero_gkey = wkey, None
+        gkey = (self._tensor_key(edge_index), self._tensor_key(batch))
+        if gkey != self._zero_gkey:
+            ext, num_total, virt_ids = self.gnn_backbone.extend_graph(edge_index, batch)
+            eng.set_graph(ext, batch, num_real=len(batch), num_total=num_total, virt_ids=virt_ids)
+            eng.set_features(None)
+            self._zero_gkey, self._zero_refs = gkey, (edge_index, batch)
+        return eng
+
     def engine_for(self, edge_index: Tensor, feats: Optional[Tensor], batch: Tensor) -> DenoiserEngine:
         """Engine with this graph and these features bound (used by the fused sampler steps)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and feats is not None and feats.requires_grad:
@@ -288,7 +308,14 @@ class Eff_GAT(nn.Module, _EngineMixin):
                  freeze_backbone=False, model="efficientnet_b0", architecture="transformer", virt_nodes=4,
                  all_equivariant=False, gemm_mode="bf16x3", attn_mode="auto") -> None:
         super().__init__()
-        self.visual_backbone = None  # encoder is upstream of the hot path; attach one to use visual_features
+        # efficient_gat.py:40-42: timm's efficientnet_b0 feature pyramid -> the CUDA encoder of efficientnet.py (scope
+        # row N4; random-init unless a checkpoint is loaded: there is no network for `visual_pretrained` weights).
+        # Other encoders (resnet18 / resnet50 / resnet18equiv) stay upstream: attach a module or pass patch_feats.
+        self.visual_backbone = None
+        if model == "efficientnet_b0":
+            from .efficientnet import EfficientNetB0Features
+
+            self.visual_backbone = EfficientNetB0Features()
         self.all_equivariant = all_equivariant
         self.model = model
         self.combined_features_dim = {
@@ -364,8 +391,14 @@ class Eff_GAT(nn.Module, _EngineMixin):
                 "the CNN patch encoder is upstream of the B200 hot path (SURVEY.md section 2.1); "
                 "attach a module as `visual_backbone` or pass pre-computed patch_feats"
             )
-        patch_rgb = (patch_rgb - self.mean) / self.std
-        feats = self.visual_backbone.forward(patch_rgb)
+        from .efficientnet import EfficientNetB0Features
+
+        if isinstance(self.visual_backbone, EfficientNetB0Features):
+            # frozen backbone in eval mode, as the shipped configuration runs it (freeze_backbone=True, :153-155)
+            self.visual_backbone.eval()
+            feats = self.visual_backbone.forward(patch_rgb, self.mean, self.std)   # normalisation fused into the layout kernel
+        else:
+            feats = self.visual_backbone.forward((patch_rgb - self.mean) / self.std)
         return torch.cat([feats[2].reshape(patch_rgb.shape[0], -1), feats[3].reshape(patch_rgb.shape[0], -1)], -1)
 
 

@@ -1120,6 +1120,19 @@ int da_op_channel_scale(float* x, const float* gate, int32_t ldg, int32_t N, int
   return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
 }
 
+int da_op_normalize_to_nhwc(const float* x, const float* mean, const float* stdv, float* y, int32_t N, int32_t C, int32_t HW, void* stream) {
+  if (!x || !mean || !stdv || !y || N <= 0 || C <= 0 || HW <= 0) return DA_ERR_INVALID;
+  cudaError_t ce = launch_normalize_to_nhwc(x, mean, stdv, y, N, C, HW, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
+int da_op_add_inplace(float* y, const float* x, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return DA_ERR_INVALID;
+  if (n % 4) return DA_ERR_UNSUPPORTED;
+  cudaError_t ce = launch_add_inplace(y, x, (size_t)n, (cudaStream_t)stream);
+  return ce == cudaSuccess ? DA_OK : DA_ERR_CUDA;
+}
+
 int da_op_graph_attention_dense(const float* qkvs, const int64_t* edge_src, const int64_t* edge_dst, int64_t E,
                                 const int64_t* batch, int32_t n, int32_t H, int32_t C, float* y, int64_t* n_dense_edges,
                                 void* stream) {

@@ -305,6 +305,8 @@ cudaError_t launch_dwconv2d_nhwc(const float* x, const float* w, const float* b,
                                  int stride, int pad, int act, cudaStream_t s);           // w [k][k][C]
 cudaError_t launch_spatial_mean(const float* x, float* y, int ldy, int N, int HW, int C, cudaStream_t s);   // y[n, c] = mean over HW
 cudaError_t launch_channel_scale(float* x, const float* gate, int ldg, int N, int HW, int C, cudaStream_t s);   // x[n, :, c] *= gate[n, c]
+cudaError_t launch_normalize_to_nhwc(const float* x, const float* mean, const float* stdv, float* y, int N, int C, int HW, cudaStream_t s);
+cudaError_t launch_add_inplace(float* y, const float* x, size_t n, cudaStream_t s);   // y += x (n % 4 == 0)
 
 cudaError_t launch_fill_rows(float* dst, int ld, const float* table, const int32_t* ids, int rows, int cols,
                              cudaStream_t s);

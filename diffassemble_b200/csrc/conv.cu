@@ -90,7 +90,41 @@ __global__ void channel_scale_kernel(float* __restrict__ x, const float* __restr
   *reinterpret_cast<float4*>(x + idx * 4) = v;
 }
 
+// input layout + normalisation in one pass: y[n, h, w, c] = (x[n, c, h, w] - mean[c]) / std[c]  (efficient_gat.py:150)
+__global__ void normalize_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                         float* __restrict__ y, int N, int C, int HW) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * HW * C) return;
+  const int c = (int)(idx % C);
+  const size_t p = idx / C;
+  const int hw = (int)(p % HW), n = (int)(p / HW);
+  y[idx] = (x[((size_t)n * C + c) * HW + hw] - __ldg(mean + c)) / __ldg(stdv + c);
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n4) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4) return;
+  float4 a = reinterpret_cast<float4*>(y)[idx];
+  const float4 b = __ldg(reinterpret_cast<const float4*>(x) + idx);
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  reinterpret_cast<float4*>(y)[idx] = a;
+}
+
 }  // namespace
+
+cudaError_t launch_normalize_to_nhwc(const float* x, const float* mean, const float* stdv, float* y, int N, int C, int HW, cudaStream_t s) {
+  const size_t total = (size_t)N * C * HW;
+  if (total == 0) return cudaSuccess;
+  normalize_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, mean, stdv, y, N, C, HW);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_add_inplace(float* y, const float* x, size_t n, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  if (n % 4) return cudaErrorInvalidValue;
+  add_inplace_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(y, x, n / 4);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_conv2d_nhwc(const float* x, const float* w, const float* b, float* y, int N, int H, int W, int Cin, int Cout,
                                int k, int stride, int pad, int act, cudaStream_t s) {

@@ -25,14 +25,24 @@ class PointNet(nn.Module):
             setattr(self, f"conv{i + 1}", nn.Conv1d(dims[i], dims[i + 1], kernel_size=1, bias=False))
             setattr(self, f"bn{i + 1}", nn.BatchNorm1d(dims[i + 1]))
         self.global_feat = global_feat
+        self._folded_cache, self._folded_key = None, None
 
-    def _folded(self, i):
-        """Eval-mode BatchNorm folded into the 1x1 convolution: (W', b') with y = x W'^T + b'."""
-        conv, bn = getattr(self, f"conv{i}"), getattr(self, f"bn{i}")
-        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-        w = conv.weight[:, :, 0] * scale[:, None]
-        b = bn.bias - bn.running_mean * scale
-        return w, b
+    def _folded(self):
+        """Eval-mode BatchNorm folded into the 1x1 convolutions: five (W', b') pairs with y = x W'^T + b', computed once
+        per weight version (not on every forward); the first layer's K = 3 is padded to 4 (16-byte rows)."""
+        key = tuple((k, v.data_ptr(), v._version) for k, v in self.state_dict().items())
+        if self._folded_cache is None or key != self._folded_key:
+            out = []
+            for i in range(1, 6):
+                conv, bn = getattr(self, f"conv{i}"), getattr(self, f"bn{i}")
+                scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+                w = conv.weight[:, :, 0] * scale[:, None]
+                b = bn.bias - bn.running_mean * scale
+                if i == 1:
+                    w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1)
+                out.append((w.float().contiguous(), b.float().contiguous()))
+            self._folded_cache, self._folded_key = out, key
+        return self._folded_cache
 
     @torch.no_grad()
     def forward(self, x: Tensor) -> Tensor:
@@ -44,10 +54,7 @@ class PointNet(nn.Module):
         B, N, _ = x.shape
         h = torch.zeros((B * N, 4), dtype=torch.float32, device=x.device)   # K padded to 4 (16-byte rows)
         h[:, :3] = x.reshape(B * N, 3)
-        for i in range(1, 6):
-            w, b = self._folded(i)
-            if i == 1:
-                w = torch.cat([w, w.new_zeros(w.shape[0], 1)], 1)
+        for i, (w, b) in enumerate(self._folded(), start=1):
             h = op_linear(h, w, b, act=ACT_RELU if i < 5 else ACT_NONE, mode="fp32")
         if not self.global_feat:
             return h.reshape(B, N, -1)

@@ -368,14 +368,41 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             # the blended model output goes through the update alone, with the scalar coefficients of t_index (the
             # reference's loop always passes t == t_index; a non-uniform t is not defined for the guidance branch here)
             coef = self._step_coef(int(t_index), self._pred_code())
-            eng = self.model.engine_for(edge_index, patch_feats, batch)
-            out_cond = eng.forward(x, t)
-            eng = self.model.engine_for(edge_index, None, batch)  # patch_feats = zeros (:578-586)
-            out_uncond = eng.forward(x, t)
+            out_cond, out_uncond, eng = self._cfg_pair(x, t, edge_index, patch_feats, batch)
             model_output = (1 + self.classifier_free_w) * out_cond - self.classifier_free_w * out_uncond
             return eng.ddim_update(x, model_output, coef, noise if self.eta > 0 else None), None
         eng = self.model.engine_for(edge_index, patch_feats, batch)
         return eng.ddim_step_t(x, t, self._pred_code(), float(self.eta), self._device_schedule(), noise if self.eta > 0 else None), None
+
+    def _cfg_pair(self, x, t, edge_index, patch_feats, batch):
+        """Conditional and unconditional (patch_feats = 0) model outputs of classifier-free guidance
+        (``spatial_diffusion.py:568-589``: two denoiser calls per step in the reference).
+
+        Graphs of a batch are independent for the transformer architecture and for exophormer without virtual nodes, so
+        there the pair runs as ONE pass over a doubled batch -- the graphs once with their features and once with zero
+        features, bound to the engine once per sampling loop (one hoisted product, twice the rows per kernel launch).
+        With virtual nodes the reference's wiring couples the graphs of a batch, so a doubled batch would change the
+        result: the two passes then run on two engines (one bound to the features, one to zeros), which at least
+        avoids re-binding the features -- i.e. re-running the hoisted GEMM -- twice per step."""
+        M = x.shape[0]
+        gnn = self.model.gnn_backbone
+        if gnn.arch == _cabi.DA_ARCH_TRANSFORMER or gnn.virt_nodes == 0:
+            key = (self.model._tensor_key(edge_index), self.model._tensor_key(batch), self.model._tensor_key(patch_feats))
+            c = self.__dict__.get("_cfg_cache")
+            if c is None or c[0] != key:
+                n_graphs = int(batch.max()) + 1
+                ei2 = torch.cat([edge_index, edge_index + M], 1)
+                b2 = torch.cat([batch, batch + n_graphs])
+                f2 = torch.cat([patch_feats, torch.zeros_like(patch_feats)])
+                c = (key, ei2, b2, f2, (edge_index, batch, patch_feats))
+                self.__dict__["_cfg_cache"] = c
+            eng = self.model.engine_for(c[1], c[3], c[2])
+            out2 = eng.forward(torch.cat([x, x]), torch.cat([t, t]))
+            return out2[:M], out2[M:], eng
+        eng = self.model.engine_for(edge_index, patch_feats, batch)
+        out_cond = eng.forward(x, t)
+        eng0 = self.model.zero_feature_engine(edge_index, batch)
+        return out_cond, eng0.forward(x, t), eng
 
     @torch.no_grad()
     def _p_sample(self, x, t, t_index, cond, edge_index, sampling_func, patch_feats, batch, noise=None):

@@ -259,6 +259,10 @@ int da_op_dwconv2d_nhwc(const float* x, const float* w, const float* bias, float
                         int32_t k, int32_t stride, int32_t pad, int32_t act, void* stream);
 int da_op_spatial_mean(const float* x, float* y, int32_t ldy, int32_t N, int32_t HW, int32_t C, void* stream);
 int da_op_channel_scale(float* x, const float* gate, int32_t ldg, int32_t N, int32_t HW, int32_t C, void* stream);
+/* y[n, h, w, c] = (x[n, c, h, w] - mean[c]) / std[c]: the reference's input normalisation (efficient_gat.py:150) fused with the
+ * NCHW -> NHWC layout change;  da_op_add_inplace: y += x over n floats (the residual of the repeated MBConv blocks). */
+int da_op_normalize_to_nhwc(const float* x, const float* mean, const float* stdv, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
+int da_op_add_inplace(float* y, const float* x, int64_t n, void* stream);
 /* Same operator with caller-provided scratch (split-bf16 operand planes): no allocation, no synchronisation. */
 size_t da_op_linear_workspace_bytes(int32_t mode, int32_t M, int32_t N, int32_t K);
 int da_op_linear_ws(int32_t mode, const float* a, const float* w, const float* bias, float* y, int32_t M, int32_t N,

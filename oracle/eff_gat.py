@@ -69,6 +69,19 @@ class EffGATRef(nn.Module):
         self.linear2 = nn.Linear(4096, 544)
         self.register_buffer("mean", torch.tensor([0.4850, 0.4560, 0.4060])[None, :, None, None])
         self.register_buffer("std", torch.tensor([0.2290, 0.2240, 0.2250])[None, :, None, None])
+        # efficient_gat.py:40-42: timm.create_model(model, features_only=True); restated for efficientnet_b0
+        # (oracle/efficientnet.py).  Created LAST so that the denoiser's default-initialised weights under a given
+        # torch.manual_seed stay what they were when the self-generated fixtures of tests/golden/make_golden.py were made.
+        self.visual_backbone = None
+        if model == "efficientnet_b0":
+            from .efficientnet import EfficientNetB0FeaturesRef
+
+            self.visual_backbone = EfficientNetB0FeaturesRef()
+
+    def visual_features(self, patch_rgb):  # :149-189 (frozen backbone, eval-mode BatchNorm)
+        from .efficientnet import visual_features_ref
+
+        return visual_features_ref(self.visual_backbone.eval(), patch_rgb, self.mean, self.std)
 
     def forward_with_feats(self, xy_pos, time, patch_rgb, edge_index, patch_feats, batch):
         time_feats = self.time_emb(time)  # :131

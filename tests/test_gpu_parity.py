@@ -678,3 +678,26 @@ def test_p_sample_with_per_node_timesteps(sampling, mean, lo, attn):
         got, _ = mod.p_sample(x.to(DEV), t.to(DEV), 7, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV),
                               batch=batch.to(DEV), noise=noise.to(DEV))
         assert rel_err(got, want) < TOL, (per_graph, rel_err(got, want))
+
+
+@pytest.mark.parametrize("arch,V", [("exophormer", 4), ("exophormer", 0), ("transformer", 0)])
+def test_classifier_free_guidance_paths(arch, V):
+    """spatial_diffusion.py:568-589.  Without virtual nodes the conditional / unconditional pair runs as ONE pass over a
+    doubled batch; with virtual nodes (graphs coupled by the reference's wiring) on two engines.  Both against the oracle."""
+    ref, mod = make_pair_2d(seed=12, steps=300, sampling="DDIM", architecture=arch, virt_nodes=V, model_mean_type="START_X",
+                            inference_ratio=10, gemm_mode="bf16x3", attn_mode="auto", classifier_free_prob=0.1, classifier_free_w=0.7)
+    mod = mod.to(DEV)
+    sizes = [64, 49]
+    ei, batch = synth_graph_batch(sizes, kind="expander", degree="60%")
+    M = sum(sizes)
+    g = torch.Generator().manual_seed(8)
+    feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, 4, generator=g)
+    ei_d, b_d, f_d = ei.to(DEV), batch.to(DEV), feats.to(DEV)
+    xg = x.to(DEV)
+    for i in (290, 280, 0):
+        t = torch.full((M,), i, dtype=torch.long)
+        with torch.no_grad():
+            x, _ = ref.p_sample(x, t, i, edge_index=ei, patch_feats=feats, batch=batch)
+        xg, _ = mod.p_sample(xg, t.to(DEV), i, cond=None, edge_index=ei_d, patch_feats=f_d, batch=b_d)
+        assert rel_err(xg, x) < TOL, (i, rel_err(xg, x))
+        xg = x.to(DEV)

@@ -290,7 +290,10 @@ def test_mirror_state_dict_layout_equals_reference_checkpoint_layout():
                 m = dab.GNN_Diffusion(steps=30, rotation=True, architecture=parts[1], virt_nodes=int(parts[2]))
         else:
             m = dab.GNN_Diffusion_3d(steps=30, sampling="DDIM", backbone="pointnet", architecture=parts[1])
-        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        # (the fixture was read from the reference with timm replaced by a placeholder, so it has no visual_backbone
+        # entries; the encoder's timm-style keys are held to the oracle's, which are pinned against torchvision's
+        # implementation by a key map: tests/test_oracle_efficientnet.py)
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("model.visual_backbone.")}
         assert mine == want, (key, sorted(set(mine) ^ set(want))[:8])
 
 
@@ -336,3 +339,17 @@ def test_dense_attention_kernel_keeps_two_ctas_per_sm(lib_built):
     m = re.search(r"attn_dense_kernelILi32ELi4E.*?Used (\d+) registers", log, re.S)
     assert m, "attn_dense_kernel<32, 4> not found in the ptxas log"
     assert int(m.group(1)) <= 168, f"attn_dense_kernel<32, 4> uses {m.group(1)} registers: only one CTA per SM would fit"
+
+
+def test_visual_backbone_state_dict_uses_timm_names():
+    """N4: the mirror's EfficientNet-B0 encoder carries timm's parameter names (all 7 stages, so that a reference
+    checkpoint's `model.visual_backbone.*` entries load strictly), identical to the oracle's."""
+    from oracle.efficientnet import EfficientNetB0FeaturesRef
+
+    mine = {k: tuple(v.shape) for k, v in dab.EfficientNetB0Features().state_dict().items()}
+    want = {k: tuple(v.shape) for k, v in EfficientNetB0FeaturesRef().state_dict().items()}
+    assert mine == want
+    for k in ("conv_stem.weight", "bn1.running_var", "blocks.0.0.conv_dw.weight", "blocks.0.0.se.conv_reduce.bias",
+              "blocks.2.1.conv_pwl.weight", "blocks.4.2.bn3.weight", "blocks.6.0.conv_pw.weight"):
+        assert k in mine, k
+    assert mine["blocks.2.0.conv_dw.weight"] == (144, 1, 5, 5) and mine["blocks.4.0.se.conv_reduce.weight"] == (20, 480, 1, 1)

@@ -11,7 +11,10 @@ G = Path(__file__).resolve().parent / "golden"
 
 
 def _checksum(module):
-    return float(sum(v.double().abs().sum() for k, v in sorted(module.state_dict().items()) if v.is_floating_point()))
+    # (the patch encoder was added to the oracle after these fixtures were made; it is constructed last, so the
+    # denoiser's seeded default weights are unchanged, and it is left out of the checksum)
+    return float(sum(v.double().abs().sum() for k, v in sorted(module.state_dict().items())
+                     if v.is_floating_point() and ".visual_backbone." not in k))
 
 
 @pytest.mark.parametrize("name", ["c1_dense36_ddpm", "dense_ragged_ddim", "exph_2x64_ddim"])

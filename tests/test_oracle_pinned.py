@@ -23,7 +23,10 @@ EXACT = 2e-6  # same torch, same op order: only the reduction order of a few sum
 
 
 def checksum(module):
-    return float(sum(v.double().abs().sum() for k, v in sorted(module.state_dict().items()) if v.is_floating_point()))
+    # (the fixtures were generated with timm replaced by a placeholder: the reference module had no visual_backbone
+    # parameters, so the encoder the oracle now carries is left out of the checksum)
+    return float(sum(v.double().abs().sum() for k, v in sorted(module.state_dict().items())
+                     if v.is_floating_point() and ".visual_backbone." not in k))
 
 
 def oracle_2d(d, steps=None):
