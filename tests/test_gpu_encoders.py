@@ -49,7 +49,11 @@ def test_visual_features_and_forward_with_patches():
 
     ref = oracle.GNNDiffusionRef(steps=100, sampling="DDIM", rotation=True, architecture="exophormer", virt_nodes=4,
                                  model_mean_type=oracle.ModelMeanType.START_X, inference_ratio=10).eval()
+    enc_state = {k: v.clone() for k, v in ref.model.visual_backbone.state_dict().items()}
     reseed_parameters(ref, 5)
+    # (the encoder keeps torch's default initialisation: the x1.5 gains of reseed_parameters compound over its 16 blocks
+    # into activations of 1e16, where a comparison is meaningless)
+    ref.model.visual_backbone.load_state_dict(enc_state)
     _randomize_bn(ref, 6)
     mod = dab.GNN_Diffusion(steps=100, sampling="DDIM", rotation=True, architecture="exophormer", virt_nodes=4,
                             model_mean_type=dab.ModelMeanType.START_X, inference_ratio=10)
@@ -68,7 +72,7 @@ def test_visual_features_and_forward_with_patches():
     feats = mod.visual_features(patches.to(DEV))
     assert feats.shape == (M, 1088)
     assert rel_err(feats, feats_ref) < 2e-5
-    got = mod.forward(x.to(DEV), t.to(DEV), patches.to(DEV), ei.to(DEV), batch.to(DEV))
+    got = mod.forward(x.to(DEV), t.to(DEV), patches.to(DEV), ei.to(DEV), batch.to(DEV))[0]   # (final_feats, attentions), efficient_gat.py:146
     assert rel_err(got, want) < TOL
     # the sampling loop takes patches as `cond` (spatial_diffusion.py:653 runs the encoder once per loop)
     imgs, _ = mod.p_sample_loop((M, 4), patches.to(DEV), ei.to(DEV), batch.to(DEV), generator=torch.Generator(device=DEV).manual_seed(0))

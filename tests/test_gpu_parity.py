@@ -687,7 +687,7 @@ def test_classifier_free_guidance_paths(arch, V):
     ref, mod = make_pair_2d(seed=12, steps=300, sampling="DDIM", architecture=arch, virt_nodes=V, model_mean_type="START_X",
                             inference_ratio=10, gemm_mode="bf16x3", attn_mode="auto", classifier_free_prob=0.1, classifier_free_w=0.7)
     mod = mod.to(DEV)
-    sizes = [64, 49]
+    sizes = [64, 50]
     ei, batch = synth_graph_batch(sizes, kind="expander", degree="60%")
     M = sum(sizes)
     g = torch.Generator().manual_seed(8)
