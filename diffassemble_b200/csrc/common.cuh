@@ -353,7 +353,7 @@ struct DensePlan {
   uint32_t* bitmap = nullptr;      // device
   size_t bitmap_words = 0;
   CsrGraph residual;               // CSR by target over the edges not in the bitmap
-  // targets split by residual in-degree: "light" rows (<= 16 edges) take the warp-per-node kernel,
+  // targets split by residual in-degree: "light" rows (<= HEAVY_MIN_DEG = 96 edges, plan.cu) take the warp-per-node kernel,
   // "heavy" rows (virtual nodes with hundreds of in-edges) the edge-parallel one.  Real nodes first.
   int32_t* light = nullptr; int n_light = 0, n_light_real = 0;
   int32_t* heavy = nullptr; int n_heavy = 0, n_heavy_real = 0;

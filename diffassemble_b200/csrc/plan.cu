@@ -17,6 +17,11 @@ namespace da {
 namespace {
 
 constexpr int MIN_DENSE_NODES = 48;   // smaller graphs stay on the CSR warp kernel
+// residual in-degree above which a row gets a whole CTA per (row, head) (virtual hub nodes: ~1000 in-edges).  Rows of a few
+// dozen in-edges -- every node of the 2..20-fragment graphs of the 3-D configuration -- stay on the warp-per-node kernel:
+// with the threshold at 16 those graphs launched 2 400 CTAs of 1024 threads per layer for 17..20 edges each (64 us per
+// launch, 8 launches per step = 5/6 of the whole step).
+constexpr int HEAVY_MIN_DEG = 96;
 constexpr int DENSITY_DIV = 16;       // dense if in-graph edges >= n^2 / 16
 
 __global__ void count_ingraph_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t E,
@@ -449,7 +454,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
         plan->n_light_nf_real = (int)light_nf.size();
       }
       const int deg = rp[i + 1] - rp[i];
-      if (deg <= 16) {
+      if (deg <= HEAVY_MIN_DEG) {
         light.push_back(i);
         if (node_slot[i] >= 0 && deg <= DA_FUSE_MAX_RESIDUAL) { fused[i] = 1; ++plan->n_fused; }
         else light_nf.push_back(i);
@@ -488,7 +493,7 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
           // fused rows take Q from TMEM inside the dense kernel: only the CSR kernels read fp32 Q
           if (rp[i + 1] > rp[i] && !fused[i]) fl[i >> 7] |= 1;
           // heavy rows read dense-tile sources from the K / V operand images, light rows from the fp32 row
-          const bool heavy_row = rp[i + 1] - rp[i] > 16;
+          const bool heavy_row = rp[i + 1] - rp[i] > HEAVY_MIN_DEG;
           for (int e = rp[i]; e < rp[i + 1]; ++e)
             if (!(heavy_row && node_slot[colv[e]] >= 0)) fl[colv[e] >> 7] |= 2;
         }
