@@ -442,7 +442,8 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
 
     # -- whole-loop CUDA graph ---------------------------------------------------------------------
     @torch.no_grad()
-    def p_sample_loop_graphed(self, shape, cond, edge_index, batch, generator: Optional[torch.Generator] = None):
+    def p_sample_loop_graphed(self, shape, cond, edge_index, batch, generator: Optional[torch.Generator] = None,
+                              steps_limit: Optional[int] = None):
         """Same result as :meth:`p_sample_loop`, but the WHOLE sampling loop (every fused step of every
         timestep) is captured once into a CUDA graph and replayed with one launch -- for small puzzles
         (6x6 ... 12x12) a step is ~16 kernels of a few microseconds each and launch latency dominates.
@@ -456,14 +457,17 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
         patch_feats = self._features_from_cond(cond)
         eng = self.model.engine_for(edge_index, patch_feats, batch)
         sched = list(reversed(range(0, self.steps, self.inference_ratio)))
+        if steps_limit is not None:
+            sched = sched[:max(1, int(steps_limit))]
         ddpm = self.sampling == "DDPM"
         if ddpm and self.model_mean_type != ModelMeanType.EPSILON:
             raise NotImplementedError("p_sample_ddpm treats the model output as epsilon")
         pred = _cabi.DA_PRED_EPSILON if ddpm else self._pred_code()
         needs_noise = ddpm or self.eta > 0
         key = (self.model._graph_key, self.model._feats_key, self.model._weights_key, tuple(shape), self.sampling,
-               self.steps, self.inference_ratio, float(self.eta), pred)
-        cache = getattr(self, "_loop_graph", None)
+               self.steps, self.inference_ratio, float(self.eta), pred, len(sched))
+        graphs = self.__dict__.setdefault("_loop_graphs", {})
+        cache = graphs.get(len(sched))
         if cache is None or cache["key"] != key:
             T = len(sched)
             traj = torch.empty((T + 1,) + tuple(shape), device=device)      # traj[0] = x_T, traj[k + 1] = output of step k
@@ -487,6 +491,7 @@ class GNN_Diffusion(_Base, DiffusionScheduleMixin):
             with torch.cuda.graph(graph):
                 run_all()
             cache = {"key": key, "graph": graph, "traj": traj, "noise": noise, "coefs": coefs}
+            graphs[len(sched)] = cache
             self._loop_graph = cache
         traj, noise = cache["traj"], cache["noise"]
         traj[0].copy_(torch.randn(shape, device=device, generator=generator) * self.noise_weight)
