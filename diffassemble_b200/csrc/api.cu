@@ -71,6 +71,16 @@ struct da_handle {
   bool no_side = getenv("DA_NO_SIDE") != nullptr && getenv("DA_NO_SIDE")[0] == '1';
   bool no_vrows = getenv("DA_NO_VROWS") != nullptr && getenv("DA_NO_VROWS")[0] == '1';
   bool no_head_fuse = getenv("DA_NO_HEAD_FUSE") != nullptr && getenv("DA_NO_HEAD_FUSE")[0] == '1';
+  // Weight folding of the 2-D denoiser (fold.cu).  fold_cfg: the configuration allows it (decided in da_create; the trunk
+  // hidden h is then kept with row stride Kf = mlp_hidden + 64 one-hot columns for the virtual rows); fold_ready: the
+  // folded weights exist (da_load_weights).  A step takes the folded path when additionally every real row of the bound
+  // batch is finalised by the dense-tile kernel (DensePlan::real_rows_clean) -- otherwise the unfolded pipeline runs.
+  bool no_fold = getenv("DA_NO_FOLD") != nullptr && getenv("DA_NO_FOLD")[0] == '1';
+  bool fold_persist = !(getenv("DA_FOLD_PERSIST") != nullptr && getenv("DA_FOLD_PERSIST")[0] == '0');
+  bool fold_cfg = false, fold_ready = false;
+  int Kf = 0;
+  Linear fold0, fold3;
+  DevBuf fold_wt, fold_wt_hi, fold_wt_lo, fold_b, fold_g, vimg_f, partial;
   // side stream: the CSR kernels of rows outside every dense tile (virtual nodes) run next to the dense kernel
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -168,6 +178,8 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
   const da_config& c = h->cfg;
   const int Mr = h->num_real, Mt = h->num_total, D = h->D, Hm = c.mlp_hidden, L = h->L;
   const bool umma = use_umma(h);
+  const bool fold = h->fold_ready && umma && h->use_plan && h->plan.n_tiles > 0 && h->plan.real_rows_clean && !alpha_last && !alpha_all;
+  const int ld_h = h->fold_cfg ? h->Kf : Hm;   // row stride of the split-bf16 trunk hidden
   cudaError_t ce;
 #define DA_CK(call, where) do { ce = (call); if (ce != cudaSuccess) return h->cuda_fail(ce, where); } while (0)
 
@@ -183,16 +195,16 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     a.M = Mr; a.C_in = c.in_channels; a.Hm = Hm; a.T = c.steps;
     a.act = (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_GELU;
     a.row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;   // internal node order of the planner (x / t are the caller's)
-    if (umma) { a.out.hi = h->h_hi.as<__nv_bfloat16>(); a.out.lo = h->h_lo.as<__nv_bfloat16>(); a.out.ld_split = Hm; }
+    if (umma) { a.out.hi = h->h_hi.as<__nv_bfloat16>(); a.out.lo = h->h_lo.as<__nv_bfloat16>(); a.out.ld_split = ld_h; }
     else { a.out.f32 = h->hbuf.as<float>(); a.out.ldc = Hm; }
     Scoped sc(h, s, TAG_PROLOGUE);
     DA_CK(launch_prologue(a, s), "prologue");
   }
-  // 2. combined = act2(h @ W2^T + b2) -> [Mr, D] (fp32 kept for the trunk residual)
-  {
+  // 2. combined = act2(h @ W2^T + b2) -> [Mr, D] (fp32 kept for the trunk residual); folded away on the folded path
+  if (!fold) {
     LinearOut o; o.f32 = h->combined.as<float>(); o.ldc = D;
     if (umma) { o.hi = h->comb_hi.as<__nv_bfloat16>(); o.lo = h->comb_lo.as<__nv_bfloat16>(); o.ld_split = D; }
-    DA_CK(run_linear(h, h->mlp2, h->hbuf.as<float>(), Hm, h->h_hi.as<__nv_bfloat16>(), h->h_lo.as<__nv_bfloat16>(), Hm,
+    DA_CK(run_linear(h, h->mlp2, h->hbuf.as<float>(), Hm, h->h_hi.as<__nv_bfloat16>(), h->h_lo.as<__nv_bfloat16>(), ld_h,
                      Mr, (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_NONE, o, TAG_MLP2_GEMM, s),
           "mlp2 gemm");
   }
@@ -201,11 +213,39 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
   const __nv_bfloat16* xin_hi = h->comb_hi.as<__nv_bfloat16>();
   const __nv_bfloat16* xin_lo = h->comb_lo.as<__nv_bfloat16>();
   int ld_in = D;
+  if (fold) {   // first projection straight from h (and the one-hot columns of the virtual rows): K = Kf instead of D
+    xin = nullptr; xin_hi = h->h_hi.as<__nv_bfloat16>(); xin_lo = h->h_lo.as<__nv_bfloat16>(); ld_in = h->Kf;
+  }
   for (int l = 0; l < L; ++l) {
     const int HC = layer_hc(h, l), C = HC / c.heads;
     const bool last = (l == L - 1);
     const bool dense = h->use_plan && h->plan.n_tiles > 0;
     const int Cpad = (C + 15) / 16 * 16;
+    if (fold && last) {
+      // folded last layer: [Q | K | V'] projection, scores on the C-channel images, aggregation of the 32-channel V'
+      const int N3 = h->fold3.N;
+      LinearOut o; o.f32 = h->qkvs.as<float>(); o.ldc = N3;
+      o.img_node_slot = h->plan.node_slot; o.qimg = h->qimg_l.as<__nv_bfloat16>(); o.kimg = h->kimg_l.as<__nv_bfloat16>();
+      o.vimg = h->vimg_f.as<__nv_bfloat16>();
+      o.img_H = c.heads; o.img_C = C; o.img_Cpad = Cpad; o.img_rows = Mr; o.img_Cv = 32; o.img_Cvpad = 32;
+      o.f32_tile_flags = h->plan.f32_tile_flags[1];   // fp32 K / V' rows only where the gather below reads them
+      DA_CK(run_linear(h, h->fold3, nullptr, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, TAG_QKVS_GEMM_LAST, s), "folded qkv gemm");
+      if (h->plan.n_extra > 0) {
+        PackArgs pa{};
+        pa.qkvs = h->qkvs.as<float>(); pa.ld = N3; pa.node_slot = h->plan.node_slot; pa.n = Mr;
+        pa.H = c.heads; pa.C = C; pa.Cpad = Cpad; pa.Cv = 32; pa.Cvpad = 32;
+        pa.qimg = o.qimg; pa.kimg = o.kimg; pa.vimg = o.vimg;
+        Scoped sc(h, s, TAG_PACK_LAST);
+        DA_CK(launch_gather_extra(pa, h->plan.x_src, h->plan.x_slot, h->plan.n_extra, s), "gather extra sources");
+      }
+      AttnFoldArgs fa{};
+      fa.qimg = o.qimg; fa.kimg = o.kimg; fa.vimg = o.vimg;
+      fa.tiles = h->plan.tiles; fa.n_tiles = h->plan.n_tiles; fa.bitmap = h->plan.bitmap; fa.blk_list = h->plan.blk_list;
+      fa.H = c.heads; fa.C = C; fa.Cpad = Cpad; fa.partial = h->partial.as<float>(); fa.persistent = h->fold_persist ? 1 : 0;
+      Scoped sc(h, s, TAG_ATTN_DENSE_LAST);
+      DA_CK(launch_attn_dense_fold(fa, s), "folded dense attention");
+      break;
+    }
     __nv_bfloat16* qimg = (last ? h->qimg_l : h->qimg).as<__nv_bfloat16>();
     __nv_bfloat16* kimg = (last ? h->kimg_l : h->kimg).as<__nv_bfloat16>();
     __nv_bfloat16* vimg = (last ? h->vimg_l : h->vimg).as<__nv_bfloat16>();
@@ -222,7 +262,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
           o.f32_tile_flags = h->plan.f32_tile_flags[last ? 1 : 0];
       }
       int tag = l == 0 ? TAG_QKVS_GEMM_FIRST : (last ? TAG_QKVS_GEMM_LAST : TAG_QKVS_GEMM_MID);
-      DA_CK(run_linear(h, h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
+      DA_CK(run_linear(h, (fold && l == 0) ? h->fold0 : h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
     const CsrGraph& csr = h->use_plan ? h->plan.residual : h->csr;
     if (dense) {  // bitmap edges on the tensor cores; the CSR kernel below continues with the residual edges
@@ -369,6 +409,17 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       a.tabs.sched = *sched; a.tabs.t = t_arr; a.tabs.tmin = h->tmin.as<int32_t>();
     }
     // 2-D head on the tensor-core path: final_mlp[2] + the sampler update ride in the GEMM epilogue (one launch)
+    if (fold) {   // h (W_a W_2)^T + x3 (W_a W_skip)^T + per-head aggregates -> GELU -> final_mlp[2] -> sampler update
+      HeadFoldArgs f{};
+      f.partial = h->partial.as<float>(); f.H = c.heads;
+      f.h_hi = h->h_hi.as<__nv_bfloat16>(); f.h_lo = h->h_lo.as<__nv_bfloat16>(); f.ld_h = h->Kf; f.Hm = Hm;
+      f.x_hi = xin_hi; f.x_lo = xin_lo; f.ld_x = ld_in; f.hid = c.hidden;
+      f.w_hi = h->fold_wt_hi.as<__nv_bfloat16>(); f.w_lo = h->fold_wt_lo.as<__nv_bfloat16>(); f.bias = h->fold_b.as<float>();
+      f.fin = a;
+      Scoped sc(h, s, TAG_HEAD_FINAL);
+      DA_CK(launch_head_fold(f, s), "folded head");
+      return DA_OK;
+    }
     const bool fused_head = umma && c.head_kind == DA_HEAD_2D && h->Nh == 32 && !h->no_head_fuse;
     LinearOut o;
     if (fused_head) o.head = &a; else { o.f32 = h->u.as<float>(); o.ldc = h->Nh; }
@@ -440,6 +491,14 @@ int da_create(da_handle** out, const da_config* cfg) {
   h->L = c.n_layers;
   h->Nh = (c.head_kind == DA_HEAD_SE3) ? 512 : 32;
   h->layer.resize(h->L);
+  {
+    const int c_last = D / c.heads, cpad_last = (c_last + 15) / 16 * 16;
+    const bool virt = c.arch == DA_ARCH_EXOPHORMER && c.virt_nodes > 0;
+    h->fold_cfg = !h->no_fold && c.gemm_mode == DA_GEMM_BF16X3_UMMA && c.attn_mode == DA_ATTN_AUTO && c.head_kind == DA_HEAD_2D &&
+                  h->Nh == 32 && c.virt_nodes <= 64 && c_last % 8 == 0 && (c.heads * c_last) % 32 == 0 &&
+                  (2 * D + c.heads * 32) % 128 == 0 && c.hidden % 64 == 0 && c.mlp_hidden % 16 == 0 && attn_dense_fold_supported(cpad_last);
+    h->Kf = c.mlp_hidden + (h->fold_cfg && virt ? 64 : 0);
+  }
   *out = h;
   return DA_OK;
 }
@@ -448,7 +507,8 @@ void da_destroy(da_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   drain_profile(h);
-  h->hoist.release(); h->mlp2.release(); h->head1.release();
+  h->hoist.release(); h->mlp2.release(); h->head1.release(); h->fold0.release(); h->fold3.release();
+  h->fold_wt.release(); h->fold_wt_hi.release(); h->fold_wt_lo.release(); h->fold_b.release(); h->fold_g.release(); h->vimg_f.release(); h->partial.release();
   for (auto& l : h->layer) l.release();
   DevBuf* all[] = {&h->pos_w0, &h->pos_b0, &h->pos_w2, &h->pos_b2, &h->time_emb, &h->w1pt_T, &h->b1, &h->headb_w,
                    &h->headb_b, &h->headr_w, &h->headr_b, &h->virt_emb, &h->P, &h->hbuf, &h->combined, &h->qkvs,
@@ -585,6 +645,55 @@ int da_load_weights(da_handle* h, const da_weight_desc* w, int32_t n) {
     DA_NEED(v4, "mlp_r.2.weight", 3, 256); DA_CK(up_direct(h->headr_w, v4));
     DA_NEED(v5, "mlp_r.2.bias", 3, 1); DA_CK(up_direct(h->headr_b, v5));
   }
+  h->fold_ready = false;
+  if (h->fold_cfg) {
+    // folded products in fp64 on the device (fold.cu): first projection from h, last layer's V' / skip / trunk residual
+    // pulled through final_mlp[0]
+    const int hid = c.hidden, H = c.heads, Cl = D / H, L = h->L, Kf = h->Kf, N0 = 4 * hid, N3 = 2 * D + H * 32;
+    const float* W0 = h->layer[0].w.as<float>(); const float* b0 = h->layer[0].b.as<float>();
+    const float* W2 = h->mlp2.w.as<float>(); const float* b2 = h->mlp2.b.as<float>();
+    const float* W3 = h->layer[L - 1].w.as<float>(); const float* b3 = h->layer[L - 1].b.as<float>();
+    const float* Wa = h->head1.w.as<float>(); const float* ba = h->head1.b.as<float>();
+    auto alloc_linear = [&](Linear& lin, int N, int K) -> cudaError_t {
+      lin.N = N; lin.K = K;
+      cudaError_t e = lin.w.ensure((size_t)N * K * sizeof(float)); if (e != cudaSuccess) return e;
+      e = lin.b.ensure((size_t)N * sizeof(float)); if (e != cudaSuccess) return e;
+      e = lin.w_hi.ensure((size_t)N * K * sizeof(__nv_bfloat16)); if (e != cudaSuccess) return e;
+      e = lin.w_lo.ensure((size_t)N * K * sizeof(__nv_bfloat16)); if (e != cudaSuccess) return e;
+      return cudaMemset(lin.w.p, 0, (size_t)N * K * sizeof(float));
+    };
+    DA_CK(alloc_linear(h->fold0, N0, Kf));
+    DA_CK(alloc_linear(h->fold3, N3, hid));
+    DA_CK(h->fold_g.ensure((size_t)N0 * sizeof(float)));
+    DA_CK(h->fold_wt.ensure((size_t)(Hm + hid) * 32 * sizeof(float)));
+    DA_CK(h->fold_b.ensure(32 * sizeof(float)));
+    float* F0 = h->fold0.w.as<float>(); float* g = h->fold_g.as<float>();
+    DA_CK(launch_matmul_f64(W0, D, W2, Hm, 1, nullptr, 0, 0, 0.f, F0, Kf, 1, N0, Hm, D, 0));               // W_0 W_2
+    DA_CK(launch_matmul_f64(W0, D, b2, 1, 0, nullptr, 0, 0, 0.f, g, 1, 0, N0, 1, D, 0));                    // g = W_0 b_2
+    DA_CK(launch_matmul_f64(W0, D, b2, 1, 0, b0, 1, 0, 1.f, h->fold0.b.as<float>(), 1, 0, N0, 1, D, 0));    // W_0 b_2 + b_0
+    if (Kf > Hm && c.virt_nodes > 0)   // one-hot columns of the virtual rows: W_0 (virt_emb[v] - b_2)
+      DA_CK(launch_matmul_f64(W0, D, h->virt_emb.as<float>(), 1, D, g, 1, 0, -1.f, F0 + Hm, Kf, 1, N0, c.virt_nodes, D, 0));
+    float* F3 = h->fold3.w.as<float>(); float* fb3 = h->fold3.b.as<float>();
+    DA_CK(cudaMemcpy(F3, W3, (size_t)2 * D * hid * sizeof(float), cudaMemcpyDeviceToDevice));   // Q and K rows unchanged
+    DA_CK(cudaMemcpy(fb3, b3, (size_t)2 * D * sizeof(float), cudaMemcpyDeviceToDevice));
+    for (int hh = 0; hh < H; ++hh) {   // V'_h = W_a[:, head block] W_v[head block, :]
+      DA_CK(launch_matmul_f64(Wa + hh * Cl, D, W3 + (size_t)(2 * D + hh * Cl) * hid, hid, 1, nullptr, 0, 0, 0.f,
+                              F3 + (size_t)(2 * D + hh * 32) * hid, hid, 1, 32, hid, Cl, 0));
+      DA_CK(launch_matmul_f64(Wa + hh * Cl, D, b3 + 2 * D + hh * Cl, 1, 0, nullptr, 0, 0, 0.f, fb3 + 2 * D + hh * 32, 1, 0, 32, 1, Cl, 0));
+    }
+    float* wt = h->fold_wt.as<float>(); float* fb = h->fold_b.as<float>();
+    const int Kt = Hm + hid;   // [32, Kt] = [W_a W_2 | W_a W_skip]
+    DA_CK(h->fold_wt_hi.ensure((size_t)Kt * 32 * sizeof(__nv_bfloat16)));
+    DA_CK(h->fold_wt_lo.ensure((size_t)Kt * 32 * sizeof(__nv_bfloat16)));
+    DA_CK(launch_matmul_f64(Wa, D, W2, Hm, 1, nullptr, 0, 0, 0.f, wt, Kt, 1, 32, Hm, D, 0));
+    DA_CK(launch_matmul_f64(Wa, D, W3 + (size_t)3 * D * hid, hid, 1, nullptr, 0, 0, 0.f, wt + Hm, Kt, 1, 32, hid, D, 0));
+    DA_CK(launch_split_bf16(wt, Kt, h->fold_wt_hi.as<__nv_bfloat16>(), h->fold_wt_lo.as<__nv_bfloat16>(), Kt, 32, Kt, 0));
+    DA_CK(launch_matmul_f64(Wa, D, b3 + 3 * D, 1, 0, ba, 1, 0, 1.f, fb, 1, 0, 32, 1, D, 0));    // b_a + W_a b_skip
+    DA_CK(launch_matmul_f64(Wa, D, b2, 1, 0, fb, 1, 0, 1.f, fb, 1, 0, 32, 1, D, 0));            // ... + W_a b_2
+    DA_CK(launch_split_bf16(F0, Kf, h->fold0.w_hi.as<__nv_bfloat16>(), h->fold0.w_lo.as<__nv_bfloat16>(), Kf, N0, Kf, 0));
+    DA_CK(launch_split_bf16(F3, hid, h->fold3.w_hi.as<__nv_bfloat16>(), h->fold3.w_lo.as<__nv_bfloat16>(), hid, N3, hid, 0));
+    h->fold_ready = true;
+  }
   DA_CK(cudaDeviceSynchronize());
 #undef DA_NEED
 #undef DA_CK
@@ -631,7 +740,20 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
   DA_CK(h->model_out.ensure(Mr * c.out_channels * sizeof(float)));
   if (umma) {
     const size_t b2 = sizeof(__nv_bfloat16);
-    DA_CK(h->h_hi.ensure(Mr * Hm * b2)); DA_CK(h->h_lo.ensure(Mr * Hm * b2));
+    if (h->fold_cfg) {
+      // trunk hidden with row stride Kf and one row per node INCLUDING the virtual ones: columns >= Hm are the one-hot
+      // selectors of the folded first projection (zero on real rows), see fold.cu
+      const size_t hb = Mt * (size_t)h->Kf * b2;
+      DA_CK(h->h_hi.ensure(hb)); DA_CK(h->h_lo.ensure(hb));
+      DA_CK(cudaMemsetAsync(h->h_hi.p, 0, hb, s)); DA_CK(cudaMemsetAsync(h->h_lo.p, 0, hb, s));
+      if (num_total > num_real && h->Kf > Hm) {
+        h->launches++;
+        DA_CK(launch_onehot_rows(h->h_hi.as<__nv_bfloat16>() + Mr * (size_t)h->Kf, h->Kf, Hm, virt_ids, num_total - num_real, s));
+      }
+      DA_CK(h->partial.ensure(Mr * (size_t)c.heads * 32 * sizeof(float)));
+    } else {
+      DA_CK(h->h_hi.ensure(Mr * Hm * b2)); DA_CK(h->h_lo.ensure(Mr * Hm * b2));
+    }
     DA_CK(h->comb_hi.ensure(Mt * D * b2)); DA_CK(h->comb_lo.ensure(Mt * D * b2));
     DA_CK(h->xa_hi.ensure(Mt * hid * b2)); DA_CK(h->xa_lo.ensure(Mt * hid * b2));
     DA_CK(h->xb_hi.ensure(Mt * hid * b2)); DA_CK(h->xb_lo.ensure(Mt * hid * b2));
@@ -651,6 +773,10 @@ int da_set_graph(da_handle* h, const int64_t* edge_src, const int64_t* edge_dst,
     for (int i = 0; i < 6; ++i) {
       DA_CK(imgs[i]->ensure(i < 3 ? img_h : img_l));
       DA_CK(cudaMemsetAsync(imgs[i]->p, 0, imgs[i]->bytes, s));
+    }
+    if (h->fold_cfg) {
+      DA_CK(h->vimg_f.ensure(dense_image_elems(h->plan.n_tiles, c.heads, 32) * sizeof(__nv_bfloat16)));
+      DA_CK(cudaMemsetAsync(h->vimg_f.p, 0, h->vimg_f.bytes, s));
     }
     DA_CK(h->dacc.ensure(Mr * (size_t)(D > hid ? D : hid) * sizeof(float)));
     DA_CK(h->dstats.ensure(Mr * (size_t)c.heads * 2 * sizeof(float)));
@@ -811,6 +937,10 @@ int da_graph_plan_info(const da_handle* h, int64_t* out, int32_t n) {
   out[5] = on ? p.n_extra : 0;             // promoted extra sources
   out[6] = on ? p.n_fused : 0;             // rows finalised inside the dense kernel
   out[7] = on ? p.n_csr_rows : 0;          // rows served by the CSR kernels
+  if (n >= 10) {
+    out[8] = (on && p.n_tiles > 0 && p.real_rows_clean) ? 1 : 0;                       // no real row needs a CSR kernel
+    out[9] = (h->fold_ready && on && p.n_tiles > 0 && p.real_rows_clean) ? 1 : 0;      // steps take the folded path (fold.cu)
+  }
   return DA_OK;
 }
 

@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -201,15 +202,17 @@ __global__ void gather_extra_kernel(PackArgs a, const int32_t* __restrict__ x_sr
   if (wg >= n_extra * 2) return;
   const int ent = wg >> 1, part = 1 + (wg & 1);   // 1 = K, 2 = V
   const int node = x_src[ent], slot = x_slot[ent];
-  const int HC = a.H * a.C, chunks = a.Cpad / 8;
+  // folded last layer: the V' part has its own head dim (rows are [Q | K | V'], so its offset is still 2 * H * C)
+  const int C_ = (part == 2 && a.Cv > 0) ? a.Cv : a.C, Cpad_ = (part == 2 && a.Cv > 0) ? a.Cvpad : a.Cpad;
+  const int HC = a.H * a.C, chunks = Cpad_ / 8;
   const int blk = slot >> 6, rb = slot & 63;
   const float* row = a.qkvs + (size_t)node * a.ld + part * HC;
   for (int it = lane; it < a.H * chunks; it += 32) {
     const int h = it / chunks, ch = it % chunks, c = ch * 8;
     __nv_bfloat16 hi[8], lo[8];
-    if (c < a.C) {
-      const float4 v0 = *reinterpret_cast<const float4*>(row + h * a.C + c);
-      const float4 v1 = *reinterpret_cast<const float4*>(row + h * a.C + c + 4);
+    if (c < C_) {
+      const float4 v0 = *reinterpret_cast<const float4*>(row + h * C_ + c);
+      const float4 v1 = *reinterpret_cast<const float4*>(row + h * C_ + c + 4);
       const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -220,10 +223,10 @@ __global__ void gather_extra_kernel(PackArgs a, const int32_t* __restrict__ x_sr
 #pragma unroll
       for (int e = 0; e < 8; ++e) { hi[e] = __float2bfloat16_rn(0.f); lo[e] = hi[e]; }
     }
-    __nv_bfloat16* base = (part == 1 ? a.kimg : a.vimg) + ((size_t)blk * a.H + h) * kv_block_elems(a.Cpad);
+    __nv_bfloat16* base = (part == 1 ? a.kimg : a.vimg) + ((size_t)blk * a.H + h) * kv_block_elems(Cpad_);
     const size_t off = (size_t)ch * (TS * 8) + (size_t)rb * 8;
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
-    *reinterpret_cast<uint4*>(base + (size_t)TS * a.Cpad + off) = *reinterpret_cast<uint4*>(lo);
+    *reinterpret_cast<uint4*>(base + (size_t)TS * Cpad_ + off) = *reinterpret_cast<uint4*>(lo);
   }
 }
 
@@ -812,6 +815,597 @@ attn_dense_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Folded last layer (fold.cu): S = Q K^T over the C-channel images as above, but the aggregated values are the
+// 32-channel V' = x (W_a^h W_v^h)^T of final_mlp[0] folded into lin_value, and there is no skip / residual / activation:
+// the epilogue is "normalise and store 32 floats per (row, head)".  P V' costs 12 MMAs of N = 32 per block instead of
+// 12 of N = 144, the V ring shrinks to 8 KB per stage (ring depth 4 at C = 144), O to 32 TMEM columns.
+// Same roles, barriers and softmax loop as attn_dense_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FV = 32;   // channels of V' per head = width of final_mlp[0]
+
+template <int CQ_T, int ST>
+__global__ void __launch_bounds__(NT)
+attn_dense_fold_kernel(AttnFoldArgs a, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Cq = CQ_T ? CQ_T : a.Cpad;
+  const uint32_t k_plane = TS * Cq * 2, v_plane = TS * FV * 2;   // bytes
+  uint8_t* k_sm = smem;
+  uint8_t* v_sm = k_sm + ST * 2 * k_plane;
+  DenseSmem* sh = reinterpret_cast<DenseSmem*>(v_sm + ST * 2 * v_plane);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / a.H, head = blockIdx.x % a.H;
+  const TileInfo ti = a.tiles[tile];
+  const int nblk = ti.n_list;
+  const uint16_t* __restrict__ blist = a.blk_list + ti.list_off;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sh->q_full, 4);
+    for (int i = 0; i < MAXST; ++i) {
+      mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1);
+      mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"((uint32_t)tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const uint32_t tmem_s = tmem_base;             // 2 x TS columns: S_j (fp32), later P_j (bf16 hi | lo)
+  const uint32_t tmem_o = tmem_base + 2 * TS;    // FV columns
+  const uint32_t tmem_q = tmem_o + FV;           // Cq columns: Q as packed bf16 pairs, hi plane then lo plane
+
+  if (warp == 0) {  // ===== bulk-copy producer =====
+    auto blk_idx = [&](int j) { return (size_t)(ti.gblock0 + (int)(__ldg(blist + j) >> 1)) * a.H + head; };
+    auto load_k = [&](int j) {
+      if (elect_one()) {
+        const int st = j % ST;
+        mbar_expect_tx(&sh->k_full[st], 2 * k_plane);
+        bulk_load(k_sm + st * 2 * k_plane, a.kimg + blk_idx(j) * kv_block_elems(Cq), 2 * k_plane, &sh->k_full[st]);
+      }
+      __syncwarp();
+    };
+    auto load_v = [&](int j) {
+      if (elect_one()) {
+        const int st = j % ST;
+        mbar_expect_tx(&sh->v_full[st], 2 * v_plane);
+        bulk_load(v_sm + st * 2 * v_plane, a.vimg + blk_idx(j) * kv_block_elems(FV), 2 * v_plane, &sh->v_full[st]);
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < ST && j < nblk; ++j) load_k(j);
+    for (int j = 0; j < ST && j < nblk; ++j) load_v(j);
+    for (int j = 0; j < nblk; ++j) {
+      if (j + ST < nblk) {
+        mbar_wait(&sh->k_empty[j % ST], (j / ST) & 1);
+        load_k(j + ST);
+        mbar_wait(&sh->v_empty[j % ST], (j / ST) & 1);
+        load_v(j + ST);
+      }
+    }
+  } else if (warp == 1) {  // ===== MMA issuer =====
+    const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, FV) | (1u << 16);  // bit 16: B is MN-major
+    const int ksteps = Cq / 16;
+    const uint32_t tq_hi = tmem_q, tq_lo = tmem_q + Cq / 2;
+    const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
+    const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);
+    const uint32_t kstage_u = (2 * k_plane) >> 4, kplane_u = k_plane >> 4;
+    const uint32_t vstage_u = (2 * v_plane) >> 4, vplane_u = v_plane >> 4;
+    auto issue_s = [&](int j) {
+      if (elect_one()) {
+        const uint64_t dk_hi = dk0 + (uint32_t)(j % ST) * kstage_u, dk_lo = dk_hi + kplane_u;
+        const uint32_t d = tmem_s + (uint32_t)((j & 1) * TS);
+#pragma unroll
+        for (int kk = 0; kk < (CQ_T ? CQ_T / 16 : 16); ++kk) {
+          if (!CQ_T && kk >= ksteps) break;
+          const uint32_t ko = (uint32_t)kk * ((2 * TS * 16) >> 4);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_hi + ko, idesc_s, kk ? 1u : 0u);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_lo + ko, idesc_s, 1u);
+          tc_mma_bf16_ts(d, tq_lo + kk * 8, dk_hi + ko, idesc_s, 1u);
+        }
+        tc_commit(&sh->s_full[j & 1]);
+        tc_commit(&sh->k_empty[j % ST]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&sh->q_full, 0);
+    mbar_wait(&sh->k_full[0], 0);
+    tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < nblk; ++j) {
+      if (j + 1 < nblk) {
+        const int jn = j + 1;
+        mbar_wait(&sh->k_full[jn % ST], (jn / ST) & 1);
+        if (jn >= 2) mbar_wait(&sh->pv_done[jn & 1], ((jn >> 1) - 1) & 1);
+        tc_fence_after();
+        issue_s(jn);
+      }
+      const int b = j & 1, vs = j % ST;
+      mbar_wait(&sh->p_full[b], (j >> 1) & 1);
+      mbar_wait(&sh->v_full[vs], (j / ST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;
+        const uint64_t dv_hi = dv0 + (uint32_t)vs * vstage_u, dv_lo = dv_hi + vplane_u;
+#pragma unroll
+        for (int kk = 0; kk < TS / 16; ++kk) {
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, dv_hi + kk * 16, idesc_o, (j | kk) ? 1u : 0u);
+          tc_mma_bf16_ts(tmem_o, p_hi + kk * 8, dv_lo + kk * 16, idesc_o, 1u);
+          tc_mma_bf16_ts(tmem_o, p_lo + kk * 8, dv_hi + kk * 16, idesc_o, 1u);
+        }
+        tc_commit(&sh->pv_done[b]);
+        tc_commit(&sh->v_empty[vs]);
+      }
+      __syncwarp();
+    }
+  } else {  // ===== softmax warps =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const bool row_valid = r < ti.rows;
+    const float c_log2 = 1.4426950408889634f / sqrtf((float)a.C);
+    const float tau_raw = LAZY_LOG2 / c_log2;
+    const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
+    {  // park this row's Q in TMEM
+      const uint4* qsrc = reinterpret_cast<const uint4*>(a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cq));
+      for (int pl_ = 0; pl_ < 2; ++pl_) {
+        for (int ch0 = 0; ch0 < Cq / 8; ch0 += 4) {
+          uint32_t qv[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (ch0 + u < Cq / 8) t = __ldg(qsrc + (size_t)pl_ * (TM * Cq / 8) + (size_t)(ch0 + u) * TM + r);
+            qv[4 * u] = t.x; qv[4 * u + 1] = t.y; qv[4 * u + 2] = t.z; qv[4 * u + 3] = t.w;
+          }
+          const uint32_t dst = tmem_q + lane_off + (uint32_t)(pl_ * (Cq / 2) + ch0 * 4);
+          if (ch0 + 4 <= Cq / 8) tmem_st16(dst, qv);
+          else {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(dst), "r"(qv[0]),
+                         "r"(qv[1]), "r"(qv[2]), "r"(qv[3]), "r"(qv[4]), "r"(qv[5]), "r"(qv[6]), "r"(qv[7]) : "memory");
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->q_full);
+    }
+    float m = -INFINITY, l = 0.f;
+    uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist) >> 1) * 2) : make_uint2(0u, 0u);
+    for (int j = 0; j < nblk; ++j) {
+      const int b = j & 1;
+      const uint2 bits = bits_next;
+      if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist + j + 1) >> 1) * 2);
+      mbar_wait(&sh->s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
+      if (j == 0) {
+        uint32_t v[TS];
+#pragma unroll
+        for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < TS; ++e) {
+          const uint32_t w = (e < 32) ? bits.x : bits.y;
+          if ((w >> (e & 31)) & 1u) m = fmaxf(m, __uint_as_float(v[e]));
+        }
+      }
+      bool prev_done = (j == 0);
+      uint32_t ph[TS / 2], pl[TS / 2];
+      float lsum, bmax;
+      while (true) {
+        const float m_sub = (m == -INFINITY) ? 0.f : m * c_log2;
+        lsum = 0.f; bmax = -INFINITY;
+        uint32_t v[TS];
+#pragma unroll
+        for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < TS; e += 2) {
+          const uint32_t w = (e < 32) ? bits.x : bits.y;
+          const float s0 = ((w >> (e & 31)) & 1u) ? __uint_as_float(v[e]) : -INFINITY;
+          const float s1 = ((w >> ((e + 1) & 31)) & 1u) ? __uint_as_float(v[e + 1]) : -INFINITY;
+          bmax = fmaxf(bmax, fmaxf(s0, s1));
+          const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
+          const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
+          lsum += p0 + p1;
+          const uint32_t h2 = pack_bf16x2(p0, p1);
+          ph[e >> 1] = h2;
+          pl[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
+        }
+        const bool exceeded = bmax > m + tau_raw;
+        if (!__any_sync(0xffffffffu, exceeded)) break;
+        const float m_new = exceeded ? bmax : m;
+        const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
+        if (!prev_done) {
+          mbar_wait(&sh->pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          prev_done = true;
+        }
+        if (j > 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < FV; c0 += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + lane_off + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st16(tmem_o + lane_off + c0, o);
+          }
+          tmem_st_wait();
+        }
+        l *= alpha;
+        m = m_new;
+      }
+      l += lsum;
+      tmem_st16(s_addr, ph);
+      tmem_st16(s_addr + 16, ph + 16);
+      tmem_st16(s_addr + 32, pl);
+      tmem_st16(s_addr + 48, pl + 16);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->p_full[b]);
+    }
+    mbar_wait(&sh->pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
+    tc_fence_after();
+    // epilogue: partial[node, head, :] = O / (l + 1e-16)   (rows without an in-edge: O = 0 exactly)
+    uint32_t o[FV];
+    tmem_ld16(tmem_o + lane_off, o);
+    tmem_ld16(tmem_o + lane_off + 16, o + 16);
+    tmem_ld_wait();
+    if (row_valid) {
+      const float inv = 1.f / (l + 1e-16f);
+      float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)(ti.node0 + r) * a.H + head) * FV);
+#pragma unroll
+      for (int e = 0; e < FV; e += 4)
+        dst[e >> 2] = make_float4(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv, __uint_as_float(o[e + 2]) * inv,
+                                  __uint_as_float(o[e + 3]) * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form of the folded last layer: one CTA per SM walks (tile, head) items w = blockIdx.x, + gridDim.x, ...
+// With a 73 KB Q tile and a 180 KB K / V ring only one CTA fits an SM, so in the one-item-per-CTA kernel above nothing
+// hides an item's fixed cost (TMEM allocation, barrier set-up, the Q tile's trip from global memory, the first K block,
+// the epilogue): ~1/3 of its run time.  Here the pipeline never drains:
+//   warp 0      K / V producer, ring counters run across items (the next item's blocks are requested while this one computes)
+//   warp 1      MMA issue; S of the NEXT item's first block is issued before the last P V' of the current one
+//   warps 2-5   softmax (as above), hands the row sums l to the epilogue warps through shared memory
+//   warps 6-9   park the next item's Q tile in the second TMEM Q buffer, then finalise the current item:
+//               O (double-buffered in TMEM) / l -> partial[node, head, :]
+// TMEM: S/P 2 x 64 | O 2 x 32 | Q 2 x Cq columns (480 of 512 at Cq = 144).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int NTP = 320;
+
+struct FoldSmem {
+  uint64_t k_full[MAXST], k_empty[MAXST], v_full[MAXST], v_empty[MAXST];
+  uint64_t s_full[2], p_full[2], pv_done[2];
+  uint64_t q_full[2];    // Q-park warps -> MMA: item's Q tile is in TMEM buffer (item & 1)
+  uint64_t q_free[2];    // MMA -> Q-park warps: every S of the item that used the buffer has retired
+  uint64_t o_full[2];    // MMA -> epilogue: every P V' of the item has retired (O buffer item & 1)
+  uint64_t o_empty[2];   // epilogue -> MMA / softmax: O buffer and l buffer (item & 1) have been read
+  uint64_t l_full[2];    // softmax -> epilogue: the item's row sums are in lbuf[item & 1]
+  uint32_t tmem_base;
+  float lbuf[2][TM];
+};
+
+template <int CQ_T, int ST>
+__global__ void __launch_bounds__(NTP, 1)
+attn_fold_persist_kernel(AttnFoldArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int Cq = CQ_T ? CQ_T : a.Cpad;
+  const uint32_t k_plane = TS * Cq * 2, v_plane = TS * FV * 2;   // bytes
+  uint8_t* k_sm = smem;
+  uint8_t* v_sm = k_sm + ST * 2 * k_plane;
+  FoldSmem* sh = reinterpret_cast<FoldSmem*>(v_sm + ST * 2 * v_plane);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = a.n_tiles * a.H;
+  const int w0 = blockIdx.x, wstep = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAXST; ++i) {
+      mbar_init(&sh->k_full[i], 1); mbar_init(&sh->k_empty[i], 1);
+      mbar_init(&sh->v_full[i], 1); mbar_init(&sh->v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh->s_full[i], 1); mbar_init(&sh->p_full[i], 4); mbar_init(&sh->pv_done[i], 1);
+      mbar_init(&sh->q_full[i], 4); mbar_init(&sh->q_free[i], 1);
+      mbar_init(&sh->o_full[i], 1); mbar_init(&sh->o_empty[i], 4); mbar_init(&sh->l_full[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  const uint32_t tmem_s = tmem_base;                  // 2 x TS columns
+  const uint32_t tmem_o0 = tmem_base + 2 * TS;        // 2 x FV columns
+  const uint32_t tmem_q0 = tmem_o0 + 2 * FV;          // 2 x Cq columns
+
+  if (warp == 0) {  // ===== bulk-copy producer: running block counter kc over all items =====
+    int kc = 0;
+    for (int w = w0; w < n_items; w += wstep) {
+      const int tile = w / a.H, head = w - tile * a.H;
+      const TileInfo ti = a.tiles[tile];
+      const uint16_t* __restrict__ blist = a.blk_list + ti.list_off;
+      for (int j = 0; j < ti.n_list; ++j, ++kc) {
+        const int st = kc % ST;
+        const uint32_t par = (uint32_t)((kc / ST) - 1) & 1u;
+        const size_t blk = (size_t)(ti.gblock0 + (int)(__ldg(blist + j) >> 1)) * a.H + head;
+        if (kc >= ST) mbar_wait(&sh->k_empty[st], par);
+        if (elect_one()) {
+          mbar_expect_tx(&sh->k_full[st], 2 * k_plane);
+          bulk_load(k_sm + st * 2 * k_plane, a.kimg + blk * kv_block_elems(Cq), 2 * k_plane, &sh->k_full[st]);
+        }
+        __syncwarp();
+        if (kc >= ST) mbar_wait(&sh->v_empty[st], par);
+        if (elect_one()) {
+          mbar_expect_tx(&sh->v_full[st], 2 * v_plane);
+          bulk_load(v_sm + st * 2 * v_plane, a.vimg + blk * kv_block_elems(FV), 2 * v_plane, &sh->v_full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {  // ===== MMA issuer =====
+    const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, FV) | (1u << 16);
+    const int ksteps = Cq / 16;
+    const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
+    const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);
+    const uint32_t kstage_u = (2 * k_plane) >> 4, kplane_u = k_plane >> 4;
+    const uint32_t vstage_u = (2 * v_plane) >> 4, vplane_u = v_plane >> 4;
+    // S of running block gs from the Q buffer qb; last_of_item: also tell the Q-park warps that the buffer is free
+    auto issue_s = [&](int gs, int qb, bool last_of_item) {
+      mbar_wait(&sh->k_full[gs % ST], (uint32_t)(gs / ST) & 1u);
+      if (gs >= 2) mbar_wait(&sh->pv_done[gs & 1], (uint32_t)((gs >> 1) - 1) & 1u);   // P of block gs - 2 consumed
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t tq_hi = tmem_q0 + (uint32_t)(qb * Cq), tq_lo = tq_hi + Cq / 2;
+        const uint64_t dk_hi = dk0 + (uint32_t)(gs % ST) * kstage_u, dk_lo = dk_hi + kplane_u;
+        const uint32_t d = tmem_s + (uint32_t)((gs & 1) * TS);
+#pragma unroll
+        for (int kk = 0; kk < (CQ_T ? CQ_T / 16 : 16); ++kk) {
+          if (!CQ_T && kk >= ksteps) break;
+          const uint32_t ko = (uint32_t)kk * ((2 * TS * 16) >> 4);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_hi + ko, idesc_s, kk ? 1u : 0u);
+          tc_mma_bf16_ts(d, tq_hi + kk * 8, dk_lo + ko, idesc_s, 1u);
+          tc_mma_bf16_ts(d, tq_lo + kk * 8, dk_hi + ko, idesc_s, 1u);
+        }
+        tc_commit(&sh->s_full[gs & 1]);
+        tc_commit(&sh->k_empty[gs % ST]);
+        if (last_of_item) tc_commit(&sh->q_free[qb]);
+      }
+      __syncwarp();
+    };
+    if (w0 < n_items) {
+      int g = 0, it = 0, w = w0;
+      int nblk_cur = a.tiles[w / a.H].n_list;
+      mbar_wait(&sh->q_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0, nblk_cur == 1);
+      while (true) {
+        const int w_next = w + wstep;
+        const bool has_next = w_next < n_items;
+        const int nblk_next = has_next ? a.tiles[w_next / a.H].n_list : 0;
+        const int ob = it & 1;
+        for (int j = 0; j < nblk_cur; ++j, ++g) {
+          if (j + 1 < nblk_cur) {
+            issue_s(g + 1, it & 1, j + 2 == nblk_cur);
+          } else if (has_next) {   // the next item's first S goes in front of this item's last P V'
+            mbar_wait(&sh->q_full[(it + 1) & 1], (uint32_t)((it + 1) >> 1) & 1u);
+            tc_fence_after();
+            issue_s(g + 1, (it + 1) & 1, nblk_next == 1);
+          }
+          const int b = g & 1, vs = g % ST;
+          mbar_wait(&sh->p_full[b], (uint32_t)(g >> 1) & 1u);
+          mbar_wait(&sh->v_full[vs], (uint32_t)(g / ST) & 1u);
+          if (j == 0 && it >= 2) mbar_wait(&sh->o_empty[ob], (uint32_t)((it >> 1) - 1) & 1u);   // epilogue of item it - 2 has read O
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;
+            const uint32_t o_t = tmem_o0 + (uint32_t)(ob * FV);
+            const uint64_t dv_hi = dv0 + (uint32_t)vs * vstage_u, dv_lo = dv_hi + vplane_u;
+#pragma unroll
+            for (int kk = 0; kk < TS / 16; ++kk) {
+              tc_mma_bf16_ts(o_t, p_hi + kk * 8, dv_hi + kk * 16, idesc_o, (j | kk) ? 1u : 0u);
+              tc_mma_bf16_ts(o_t, p_hi + kk * 8, dv_lo + kk * 16, idesc_o, 1u);
+              tc_mma_bf16_ts(o_t, p_lo + kk * 8, dv_hi + kk * 16, idesc_o, 1u);
+            }
+            tc_commit(&sh->pv_done[b]);
+            tc_commit(&sh->v_empty[vs]);
+            if (j == nblk_cur - 1) tc_commit(&sh->o_full[ob]);
+          }
+          __syncwarp();
+        }
+        if (!has_next) break;
+        ++it; w = w_next; nblk_cur = nblk_next;
+      }
+    }
+  } else if (warp < 6) {  // ===== softmax warps =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const float c_log2 = 1.4426950408889634f / sqrtf((float)a.C);
+    const float tau_raw = LAZY_LOG2 / c_log2;
+    int g = 0, it = 0;
+    for (int w = w0; w < n_items; w += wstep, ++it) {
+      const int tile = w / a.H;
+      const TileInfo ti = a.tiles[tile];
+      const int nblk = ti.n_list;
+      const uint16_t* __restrict__ blist = a.blk_list + ti.list_off;
+      const bool row_valid = r < ti.rows;
+      const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
+      const uint32_t o_t = tmem_o0 + (uint32_t)((it & 1) * FV) + lane_off;
+      float m = -INFINITY, l = 0.f;
+      uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist) >> 1) * 2) : make_uint2(0u, 0u);
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int b = g & 1;
+        const uint2 bits = bits_next;
+        if (j + 1 < nblk && row_valid) bits_next = *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist + j + 1) >> 1) * 2);
+        mbar_wait(&sh->s_full[b], (uint32_t)(g >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s_addr = tmem_s + lane_off + (uint32_t)(b * TS);
+        if (j == 0) {
+          uint32_t v[TS];
+#pragma unroll
+          for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < TS; ++e) {
+            const uint32_t wd = (e < 32) ? bits.x : bits.y;
+            if ((wd >> (e & 31)) & 1u) m = fmaxf(m, __uint_as_float(v[e]));
+          }
+        }
+        bool prev_done = (j == 0);
+        uint32_t ph[TS / 2], pl[TS / 2];
+        float lsum, bmax;
+        while (true) {
+          const float m_sub = (m == -INFINITY) ? 0.f : m * c_log2;
+          lsum = 0.f; bmax = -INFINITY;
+          uint32_t v[TS];
+#pragma unroll
+          for (int c0 = 0; c0 < TS; c0 += 16) tmem_ld16(s_addr + c0, v + c0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < TS; e += 2) {
+            const uint32_t wd = (e < 32) ? bits.x : bits.y;
+            const float s0 = ((wd >> (e & 31)) & 1u) ? __uint_as_float(v[e]) : -INFINITY;
+            const float s1 = ((wd >> ((e + 1) & 31)) & 1u) ? __uint_as_float(v[e + 1]) : -INFINITY;
+            bmax = fmaxf(bmax, fmaxf(s0, s1));
+            const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
+            const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
+            lsum += p0 + p1;
+            const uint32_t h2 = pack_bf16x2(p0, p1);
+            ph[e >> 1] = h2;
+            pl[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
+          }
+          const bool exceeded = bmax > m + tau_raw;
+          if (!__any_sync(0xffffffffu, exceeded)) break;
+          const float m_new = exceeded ? bmax : m;
+          const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
+          if (!prev_done) {
+            mbar_wait(&sh->pv_done[(g - 1) & 1], (uint32_t)((g - 1) >> 1) & 1u);   // O holds every earlier block of this item
+            tc_fence_after();
+            prev_done = true;
+          }
+          if (j > 0) {
+#pragma unroll
+            for (int c0 = 0; c0 < FV; c0 += 16) {
+              uint32_t o[16];
+              tmem_ld16(o_t + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st16(o_t + c0, o);
+            }
+            tmem_st_wait();
+          }
+          l *= alpha;
+          m = m_new;
+        }
+        l += lsum;
+        tmem_st16(s_addr, ph);
+        tmem_st16(s_addr + 16, ph + 16);
+        tmem_st16(s_addr + 32, pl);
+        tmem_st16(s_addr + 48, pl + 16);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->p_full[b]);
+      }
+      // hand the row sums to the epilogue warps
+      if (it >= 2) mbar_wait(&sh->o_empty[it & 1], (uint32_t)((it >> 1) - 1) & 1u);   // lbuf[it & 1] of item it - 2 has been read
+      sh->lbuf[it & 1][r] = l;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->l_full[it & 1]);
+    }
+  } else {  // ===== Q-park + epilogue warps =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto park = [&](int itn, int wn) {   // Q tile of item itn (work index wn) -> TMEM Q buffer itn & 1
+      const int qb = itn & 1;
+      if (itn >= 2) { mbar_wait(&sh->q_free[qb], (uint32_t)((itn >> 1) - 1) & 1u); tc_fence_after(); }
+      const int tile = wn / a.H, head = wn - tile * a.H;
+      const uint4* qsrc = reinterpret_cast<const uint4*>(a.qimg + ((size_t)tile * a.H + head) * q_block_elems(Cq));
+      const uint32_t tq = tmem_q0 + (uint32_t)(qb * Cq) + lane_off;
+      for (int pl_ = 0; pl_ < 2; ++pl_) {
+        for (int ch0 = 0; ch0 < Cq / 8; ch0 += 4) {
+          uint32_t qv[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (ch0 + u < Cq / 8) t = __ldg(qsrc + (size_t)pl_ * (TM * Cq / 8) + (size_t)(ch0 + u) * TM + r);
+            qv[4 * u] = t.x; qv[4 * u + 1] = t.y; qv[4 * u + 2] = t.z; qv[4 * u + 3] = t.w;
+          }
+          const uint32_t dst = tq + (uint32_t)(pl_ * (Cq / 2) + ch0 * 4);
+          if (ch0 + 4 <= Cq / 8) tmem_st16(dst, qv);
+          else {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(dst), "r"(qv[0]),
+                         "r"(qv[1]), "r"(qv[2]), "r"(qv[3]), "r"(qv[4]), "r"(qv[5]), "r"(qv[6]), "r"(qv[7]) : "memory");
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->q_full[qb]);
+    };
+    if (w0 < n_items) park(0, w0);
+    int it = 0;
+    for (int w = w0; w < n_items; w += wstep, ++it) {
+      if (w + wstep < n_items) park(it + 1, w + wstep);
+      const int tile = w / a.H, head = w - tile * a.H;
+      const TileInfo ti = a.tiles[tile];
+      const int ob = it & 1;
+      mbar_wait(&sh->l_full[ob], (uint32_t)(it >> 1) & 1u);
+      mbar_wait(&sh->o_full[ob], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      uint32_t o[FV];
+      tmem_ld16(tmem_o0 + (uint32_t)(ob * FV) + lane_off, o);
+      tmem_ld16(tmem_o0 + (uint32_t)(ob * FV) + lane_off + 16, o + 16);
+      tmem_ld_wait();
+      const float l = sh->lbuf[ob][r];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->o_empty[ob]);
+      if (r < ti.rows) {   // partial[node, head, :] = O / (l + 1e-16)   (rows without an in-edge: O = 0 exactly)
+        const float inv = 1.f / (l + 1e-16f);
+        float4* dst = reinterpret_cast<float4*>(a.partial + ((size_t)(ti.node0 + r) * a.H + head) * FV);
+#pragma unroll
+        for (int e = 0; e < FV; e += 4)
+          dst[e >> 2] = make_float4(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv, __uint_as_float(o[e + 2]) * inv,
+                                    __uint_as_float(o[e + 3]) * inv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
@@ -829,6 +1423,7 @@ cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s) {
 cudaError_t launch_gather_extra(const PackArgs& a, const int32_t* x_src, const int32_t* x_slot, int n_extra, cudaStream_t s) {
   if (n_extra <= 0) return cudaSuccess;
   if ((a.C % 8) || (a.ld % 4) || a.Cpad % 16 || a.Cpad < a.C) return cudaErrorInvalidValue;
+  if (a.Cv > 0 && ((a.Cv % 8) || a.Cvpad % 16 || a.Cvpad < a.Cv)) return cudaErrorInvalidValue;
   const long long threads = (long long)n_extra * 2 * 32;
   gather_extra_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, x_src, x_slot, n_extra);
   return cudaGetLastError();
@@ -899,6 +1494,81 @@ cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s) {
   else if (st == 3) DA_LAUNCH(0, 3);
   else DA_LAUNCH(0, 2);
 #undef DA_LAUNCH
+  return cudaGetLastError();
+}
+
+namespace {
+bool fold_config(int Cq, int* cols_out, int* st_out, size_t* smem_out) {
+  if (Cq % 16 || Cq > 256 || Cq < 16) return false;
+  int need = 2 * TS + FV + Cq, cols = 32;   // S/P double buffer + O + Q
+  while (cols < need) cols <<= 1;
+  if (cols > 512) return false;
+  auto smem_for = [&](int st) { return (size_t)st * 2 * TS * (Cq + FV) * 2 + sizeof(DenseSmem) + 128; };
+  const size_t limit = 227 * 1024;
+  int st = 4;
+  if (cols <= 256 ? (2 * smem_for(4) + 2048 > limit) : (smem_for(4) > limit)) st = (smem_for(3) <= limit) ? 3 : 2;
+  if (smem_for(st) > limit) return false;
+  *cols_out = cols; *st_out = st; *smem_out = smem_for(st);
+  return true;
+}
+}  // namespace
+
+bool attn_dense_fold_supported(int Cpad) {
+  int cols, st; size_t smem;
+  return fold_config(Cpad, &cols, &st, &smem);
+}
+
+cudaError_t launch_attn_dense_fold(const AttnFoldArgs& a, cudaStream_t s) {
+  if (a.n_tiles <= 0) return cudaSuccess;
+  int cols, st; size_t smem;
+  if (!fold_config(a.Cpad, &cols, &st, &smem)) return cudaErrorInvalidValue;
+  // persistent form (one CTA per SM over the (tile, head) items, Q / O double-buffered in TMEM): whenever both Q tiles fit
+  if (a.persistent && 2 * TS + 2 * FV + 2 * a.Cpad <= 512) {
+    auto smem_p = [&](int st_) { return (size_t)st_ * 2 * TS * (a.Cpad + FV) * 2 + sizeof(FoldSmem) + 128; };
+    const int stp = smem_p(4) <= 227 * 1024 ? 4 : (smem_p(3) <= 227 * 1024 ? 3 : 2);
+    const size_t smp = smem_p(stp);
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const int items = a.n_tiles * a.H;
+    const unsigned gridp = items < sms ? items : sms;
+#define DA_LAUNCH_P(CP, ST_)                                                                                        \
+    do {                                                                                                            \
+      static size_t smem_set = 0;                                                                                   \
+      if (smp > smem_set) {                                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(attn_fold_persist_kernel<CP, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp); \
+        if (e != cudaSuccess) return e;                                                                             \
+        smem_set = smp;                                                                                             \
+      }                                                                                                             \
+      attn_fold_persist_kernel<CP, ST_><<<gridp, NTP, smp, s>>>(a);                                                 \
+    } while (0)
+    if (a.Cpad == 144 && stp == 4) DA_LAUNCH_P(144, 4);
+    else if (stp == 4) DA_LAUNCH_P(0, 4);
+    else if (stp == 3) DA_LAUNCH_P(0, 3);
+    else DA_LAUNCH_P(0, 2);
+#undef DA_LAUNCH_P
+    return cudaGetLastError();
+  }
+  const unsigned grid = a.n_tiles * a.H;
+#define DA_LAUNCH_F(CP, ST_)                                                                                        \
+  do {                                                                                                              \
+    static size_t smem_set = 0;                                                                                     \
+    if (smem > smem_set) {                                                                                          \
+      cudaError_t e = cudaFuncSetAttribute(attn_dense_fold_kernel<CP, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return e;                                                                               \
+      smem_set = smem;                                                                                              \
+    }                                                                                                               \
+    attn_dense_fold_kernel<CP, ST_><<<grid, NT, smem, s>>>(a, cols);                                                \
+  } while (0)
+  if (a.Cpad == 144 && st == 4) DA_LAUNCH_F(144, 4);
+  else if (st == 4) DA_LAUNCH_F(0, 4);
+  else if (st == 3) DA_LAUNCH_F(0, 3);
+  else DA_LAUNCH_F(0, 2);
+#undef DA_LAUNCH_F
   return cudaGetLastError();
 }
 

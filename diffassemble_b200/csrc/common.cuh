@@ -73,6 +73,9 @@ struct LinearOut {
   // optional (N == 32 tiles only): the 2-D head's last linear + sampler update fused behind the activation
   // (efficient_gat.py:144 final_mlp[2], spatial_diffusion.py:485-627): see HeadFinalArgs; nothing else is stored then
   const struct HeadFinalArgs* head = nullptr;
+  // optional (with img_node_slot): folded last layer (fold.cu) -- the output columns are [Q | K | V'] with Q / K
+  // img_H * img_C wide and V' img_H * img_Cv wide (its own image, padded head dim img_Cvpad); no skip part
+  int img_Cv = 0, img_Cvpad = 0;
 };
 
 // y = act(a @ w^T + bias) on CUDA cores, exact fp32 FMA.  a:[M,lda] w:[N,ldw] (both K-contiguous).
@@ -193,6 +196,24 @@ struct HeadFinalArgs {
   StepTables tabs;                    // tabs.t != null: per-node schedule coefficients (gathered on the device)
 };
 cudaError_t launch_min_t(const int64_t* t, int n, int32_t* out, cudaStream_t s);
+
+// Folded 2-D head (fold.cu): u = GELU(sum_heads partial + h (W_a W_2)^T + x3 (W_a W_skip)^T + bias), then `fin`
+struct HeadFoldArgs {
+  const float* partial;            // [M, H, 32] per-head normalised aggregates of the 32-channel folded values
+  int H;
+  const __nv_bfloat16* h_hi; const __nv_bfloat16* h_lo; int ld_h, Hm;     // trunk hidden h (split-bf16), first Hm columns
+  const __nv_bfloat16* x_hi; const __nv_bfloat16* x_lo; int ld_x, hid;    // input of the last graph layer
+  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;   // [32, Hm + hid] split-bf16: columns (W_a W_2) then (W_a W_skip)
+  const float* bias;               // [32]
+  HeadFinalArgs fin;               // final_mlp[2], sampler update, outputs (u / Nh unused: Nh must be 32)
+};
+cudaError_t launch_head_fold(const HeadFoldArgs& a, cudaStream_t s);
+// fp64-accumulated product of fp32 matrices with free strides (weight folding, once per da_load_weights):
+// out[i*ldo_r + j*ldo_c] = sum_t A[i*lda + t] * B[t*ldb_r + j*ldb_c] + add_scale * add[i*add_si + j*add_sj]
+cudaError_t launch_matmul_f64(const float* A, int lda, const float* B, int ldb_r, int ldb_c, const float* add, int add_si,
+                              int add_sj, float add_scale, float* out, int ldo_r, int ldo_c, int m, int n, int k, cudaStream_t s);
+// hi[r, col0 + ids[r]] = 1 (one-hot columns of the virtual rows, see fold.cu)
+cudaError_t launch_onehot_rows(__nv_bfloat16* hi, int ld, int col0, const int32_t* ids, int rows, cudaStream_t s);
 cudaError_t launch_head_final(const HeadFinalArgs& a, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------------
@@ -374,6 +395,8 @@ struct DensePlan {
   // true when no row handled by the CSR kernels (heavy rows, un-fused light rows) lies inside a dense tile: those
   // kernels then neither read the dense kernel's (acc, stats) nor race with its output rows, and can run next to it
   bool csr_rows_independent = false;
+  // every real node sits in a dense tile and has no residual in-edge left (the folded last layer needs this)
+  bool real_rows_clean = false;
   int32_t* csr_rows = nullptr; int n_csr_rows = 0, n_csr_rows_real = 0;   // heavy rows then un-fused light rows, one list
   // per 128-row tile of the node index space: bit 0 = a row has residual in-edges (its fp32 Q is read),
   // bit 1 = a row is a residual source (fp32 K / V read); [0] all targets, [1] last layer (real targets only)
@@ -403,6 +426,7 @@ struct PackArgs {
   const int32_t* node_slot; int n;
   int H, C, Cpad;
   __nv_bfloat16* qimg; __nv_bfloat16* kimg; __nv_bfloat16* vimg;
+  int Cv = 0, Cvpad = 0;   // gather_extra only, folded last layer: rows are [Q | K | V'] with V' H*Cv wide (0 = same as C)
 };
 cudaError_t launch_pack_images(const PackArgs& a, cudaStream_t s);
 // copies the fp32 K / V rows of the plan's extra sources into their image rows (PackArgs: node_slot unused)
@@ -429,6 +453,19 @@ struct AttnDenseArgs {
   LinearOut out;
   const uint16_t* blk_list = nullptr;   // DensePlan::blk_list (required)
 };
+// Folded last layer (fold.cu): scores from the C-channel Q / K images, aggregation of the Cv = 32-channel folded
+// values V'; every row of every tile is finalised here (the planner guarantees no residual in-edge on a real row):
+// partial[node, head, :] = sum_j alpha_ij V'_j
+struct AttnFoldArgs {
+  const __nv_bfloat16* qimg; const __nv_bfloat16* kimg; const __nv_bfloat16* vimg;
+  const TileInfo* tiles; int n_tiles;
+  const uint32_t* bitmap; const uint16_t* blk_list;
+  int H, C, Cpad;      // score head dim (scale = 1 / sqrt(C)) and its padding in the Q / K images
+  float* partial;      // [n, H, 32]
+  int persistent;      // 1: one CTA per SM walks the (tile, head) items (needs 2 * Cpad + 192 <= 512 TMEM columns)
+};
+bool attn_dense_fold_supported(int Cpad);
+cudaError_t launch_attn_dense_fold(const AttnFoldArgs& a, cudaStream_t s);
 constexpr int DA_FUSE_MAX_RESIDUAL = 2;
 // true when the fused epilogue's staging area (128 skip rows of C floats) fits the kernel's K ring
 bool attn_dense_can_fuse(int C);

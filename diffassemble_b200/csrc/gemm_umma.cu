@@ -143,8 +143,10 @@ struct EpiParams {
 struct EpiNone { const void* unused; };
 template <int MODE> struct EpiExtraT { using type = EpiNone; };
 template <> struct EpiExtraT<2> { using type = HeadFinalArgs; };
+struct EpiFold { int Cv, Cvpad; };   // MODE 3: [Q | K | V'] columns of the folded last layer (LinearOut::img_Cv)
+template <> struct EpiExtraT<3> { using type = EpiFold; };
 
-// MODE 0: plain epilogue; 2: fused 2-D head (BN == 32).  Compile-time so that the plain, store-bound epilogue keeps its
+// MODE 0: plain epilogue; 2: fused 2-D head (BN == 32); 3: as 0 with the third image part V' in its own geometry.  Compile-time so that the plain, store-bound epilogue keeps its
 // code shape.  (Measured and dropped: MODE 1, the per-layer gather of the promoted extra sources folded into this
 // epilogue -- the extra code moved ptxas to a 144-register allocation of the whole epilogue and cost the QKVS GEMMs
 // 15-50 %, far more than the four 7 us gather launches it saved.)
@@ -332,7 +334,11 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
           const int part = g_col / HC;
           if (part < 3) {
             const int within = g_col - part * HC;
-            const int h = within / p.iC, c = within - h * p.iC;
+            int iC = p.iC, iCpad = p.iCpad;
+            if constexpr (MODE == 3) {
+              if (part == 2) { iC = ex.Cv; iCpad = ex.Cvpad; }
+            }
+            const int h = within / iC, c = within - h * iC;
             float4 bb0 = make_float4(0.f, 0.f, 0.f, 0.f), bb1 = bb0;
             if (p.bias) { bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col)); bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col + 4)); }
 #pragma unroll
@@ -355,16 +361,16 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
               }
               if (part == 0) {
                 const int tile_i = slot >> 7, r_ = slot & 127;
-                __nv_bfloat16* base = p.qimg + ((size_t)tile_i * p.iH + h) * ((size_t)2 * 128 * p.iCpad);
+                __nv_bfloat16* base = p.qimg + ((size_t)tile_i * p.iH + h) * ((size_t)2 * 128 * iCpad);
                 const size_t off = (size_t)(c >> 3) * (128 * 8) + (size_t)r_ * 8;
                 *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
-                *reinterpret_cast<uint4*>(base + (size_t)128 * p.iCpad + off) = *reinterpret_cast<uint4*>(lo);
+                *reinterpret_cast<uint4*>(base + (size_t)128 * iCpad + off) = *reinterpret_cast<uint4*>(lo);
               } else {
                 const int blk = slot >> 6, rb = slot & 63;
-                __nv_bfloat16* base = (part == 1 ? p.kimg : p.vimg) + ((size_t)blk * p.iH + h) * ((size_t)2 * 64 * p.iCpad);
+                __nv_bfloat16* base = (part == 1 ? p.kimg : p.vimg) + ((size_t)blk * p.iH + h) * ((size_t)2 * 64 * iCpad);
                 const size_t off = (size_t)(c >> 3) * (64 * 8) + (size_t)rb * 8;   // K and V share one layout
                 *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
-                *reinterpret_cast<uint4*>(base + (size_t)64 * p.iCpad + off) = *reinterpret_cast<uint4*>(lo);
+                *reinterpret_cast<uint4*>(base + (size_t)64 * iCpad + off) = *reinterpret_cast<uint4*>(lo);
               }
             }
           }
@@ -516,6 +522,14 @@ cudaError_t launch_linear_umma(const __nv_bfloat16* a_hi, const __nv_bfloat16* a
   if (out.head != nullptr) {
     if (N != 32 || out.head->Nh != 32 || out.head->head_kind != DA_HEAD_2D) return cudaErrorInvalidValue;
     return launch_bn<32, 2>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, *out.head, s);
+  }
+  if (out.img_node_slot && out.img_Cv > 0) {   // folded last layer: [Q | K | V']
+    if (act != ACT_NONE || out.img_C % 8 || out.img_Cv % 8 || (out.img_H * out.img_C) % 32 ||
+        N != 2 * out.img_H * out.img_C + out.img_H * out.img_Cv || N % 128)
+      return cudaErrorInvalidValue;
+    const EpiFold fold{out.img_Cv, out.img_Cvpad};
+    if (N % 256 == 0 && K <= 256 && M >= 4096) return launch_bn<256, 3>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, fold, s);
+    return launch_bn<128, 3>(a_hi, a_lo, lda, w_hi, w_lo, ldw, p, fold, s);
   }
   if (out.img_node_slot && (act != ACT_NONE || out.img_C % 8 || N != 4 * out.img_H * out.img_C)) return cudaErrorInvalidValue;
   // short-K GEMMs (K <= 256) are bound by the L2 -> SM operand traffic (a 128 x 128 tile loads 256 KB of split-bf16

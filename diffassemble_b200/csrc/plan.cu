@@ -448,6 +448,9 @@ cudaError_t build_dense_plan(const int64_t* src, const int64_t* dst, int64_t E, 
     std::vector<uint8_t> fused((size_t)num_total, 0);
     DA_TRY(copy_sync(rp.data(), plan->residual.rowptr, sizeof(int32_t) * rp.size(), cudaMemcpyDeviceToHost, s));
     plan->n_fused = 0;
+    plan->real_rows_clean = plan->n_tiles > 0;
+    for (int i = 0; i < num_real; ++i)
+      if (node_slot[i] < 0 || rp[i + 1] != rp[i]) { plan->real_rows_clean = false; break; }
     for (int i = 0; i < num_total; ++i) {
       if (i == num_real) {
         plan->n_light_real = (int)light.size(); plan->n_heavy_real = (int)heavy.size();

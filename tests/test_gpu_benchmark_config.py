@@ -165,3 +165,51 @@ def test_c5_training_gradients_at_144_node_graphs(gemm, attn):
         assert e < 1e-3, (k, e)
     assert n_checked >= 38, n_checked
     print(f"gradient parity at 2 x 144 nodes [{gemm}/{attn}]: {n_checked} tensors, worst {worst[0]:.2e} ({worst[1]})")
+
+
+def test_folded_path_runs_at_c3_and_matches_the_unfolded_pipeline(monkeypatch):
+    """csrc/fold.cu: at the benchmarked configuration the steps take the weight-folded path (first projection from the
+    128-wide trunk hidden incl. the one-hot columns of the virtual rows, last layer aggregated on 32-channel values);
+    `DA_NO_FOLD=1` keeps the unfolded pipeline.  Both must agree with the live oracle, and with each other far inside
+    the parity bar."""
+    ei, batch = synth_graph_batch([900, 900], kind="expander", degree="60%", seed=40)
+    M = 1800
+    g = torch.Generator().manual_seed(7)
+    feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, 4, generator=g)
+    outs = {}
+    for no_fold, persist in (("0", "1"), ("0", "0"), ("1", "1")):
+        monkeypatch.setenv("DA_NO_FOLD", no_fold)
+        monkeypatch.setenv("DA_FOLD_PERSIST", persist)   # "0": one (tile, head) item per CTA instead of the persistent kernel
+        ref, mod = _pair("exophormer", 8, "bf16x3", "auto")
+        t = torch.full((M,), 290, dtype=torch.long, device=DEV)
+        got, _ = mod.p_sample(x.to(DEV), t, 290, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV), batch=batch.to(DEV))
+        info = mod.model._engine.plan_info()
+        assert info["real_rows_clean"] == 1, info
+        assert info["folded"] == (1 if no_fold == "0" else 0), info
+        if no_fold == "0" and persist == "0":
+            assert rel_err(got.cpu(), outs["0"]) < 1e-6, rel_err(got.cpu(), outs["0"])   # same arithmetic, different scheduling
+            continue
+        outs[no_fold] = got.cpu()
+    want = _oracle_steps(("exph", 2, "fold"), ref, x, ei, feats, batch, (290,))[290]
+    assert rel_err(outs["0"], want) < TOL, rel_err(outs["0"], want)
+    assert rel_err(outs["1"], want) < TOL, rel_err(outs["1"], want)
+    assert rel_err(outs["0"], outs["1"]) < 2e-5, rel_err(outs["0"], outs["1"])
+
+
+def test_folded_path_small_mixed_batches():
+    """The folded path is per batch: dense-tile graphs whose rows are all clean take it (ragged sizes, non-multiple-of-128
+    tails, transformer architecture without virtual rows); a batch with a graph too small for the tiles does not."""
+    for arch, V, sizes, expect in (("transformer", 0, [144, 100, 64], 1), ("exophormer", 4, [200, 130], 1),
+                                   ("exophormer", 4, [200, 20], 0)):
+        ref, mod = _pair(arch, V, "bf16x3", "auto", seed=19)
+        ei, batch = synth_graph_batch(sizes, kind="expander", degree="60%", seed=3)
+        M = sum(sizes)
+        g = torch.Generator().manual_seed(2)
+        feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, 4, generator=g)
+        with torch.no_grad():
+            t = torch.full((M,), 150, dtype=torch.long)
+            want = ref.p_sample(x, t, 150, edge_index=ei, patch_feats=feats, batch=batch)[0]
+        got, _ = mod.p_sample(x.to(DEV), t.to(DEV), 150, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV), batch=batch.to(DEV))
+        info = mod.model._engine.plan_info()
+        assert info["folded"] == expect, (arch, sizes, info)
+        assert rel_err(got, want) < TOL, (arch, sizes, rel_err(got, want))
