@@ -77,6 +77,9 @@ struct da_handle {
   // batch is finalised by the dense-tile kernel (DensePlan::real_rows_clean) -- otherwise the unfolded pipeline runs.
   bool no_fold = getenv("DA_NO_FOLD") != nullptr && getenv("DA_NO_FOLD")[0] == '1';
   bool fold_persist = !(getenv("DA_FOLD_PERSIST") != nullptr && getenv("DA_FOLD_PERSIST")[0] == '0');
+  // hidden layers on the persistent two-stream kernel (attn_hidden.cu) whenever its preconditions hold; "0": one CTA per (tile, head)
+  bool hidden_persist = !(getenv("DA_HIDDEN_PERSIST") != nullptr && getenv("DA_HIDDEN_PERSIST")[0] == '0');
+  int hidden_stagger_ns = getenv("DA_HIDDEN_STAGGER_NS") != nullptr ? atoi(getenv("DA_HIDDEN_STAGGER_NS")) : 8000;
   bool fold_cfg = false, fold_ready = false;
   int Kf = 0;
   Linear fold0, fold3;
@@ -93,6 +96,7 @@ struct da_handle {
   DevBuf feats_perm;   // exact-fp32 mode: features gathered into the planner's internal node order
   DevBuf feats_sp_hi, feats_sp_lo, h_hi, h_lo, comb_hi, comb_lo, xa_hi, xa_lo, xb_hi, xb_lo, r_hi, r_lo;
   int64_t launches = 0;
+  int64_t persist_launches = 0;   // hidden layers that ran on attn_hidden.cu's persistent kernel (da_graph_plan_info [10])
   bool profiling = false;
   std::vector<ProfEvent> prof_events;
   double prof_ms[TAG_COUNT] = {0};
@@ -342,7 +346,27 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     };
     // With every in-tile row finalised by the dense kernel, the CSR kernels only serve rows outside the tiles
     // (virtual nodes): they depend on the GEMM alone and run on a side stream next to the dense kernel.
-    const bool side_rows = rows_path && dense && fuse && h->plan.csr_rows_independent && !h->no_side &&
+    // Persistent form of the hidden-layer kernel (one CTA per SM, every register of it): nothing can run next to it, so the
+    // rows outside the tiles go first on the same stream.
+    AttnDenseArgs da_{};
+    if (dense) {
+      da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;
+      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap; da_.blk_list = h->plan.blk_list;
+      da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
+      da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
+      da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
+      da_.stagger_ns = h->hidden_stagger_ns;
+      if (fuse) {
+        da_.row_fused = h->plan.row_fused;
+        da_.qkvs = a.qkvs; da_.ld = a.ld; da_.n_rows = Mt; da_.n_rows_resid = Mt;   // combined has Mt rows too
+        da_.n_rows_out = last ? Mr : Mt;   // r_hi / r_lo are [Mr, D], xa / xb planes [Mt, 256]
+        da_.rowptr = csr.rowptr; da_.col = csr.col; da_.weight = csr.weight;
+        da_.resid = a.resid; da_.ld_resid = a.ld_resid; da_.act = a.act; da_.out = a.out;
+      }
+    }
+    const bool persist = rows_path && dense && fuse && umma && !last && h->hidden_persist && h->plan.real_rows_clean &&
+                         h->plan.csr_rows_independent && attn_hidden_persist_supported(da_);
+    const bool side_rows = rows_path && dense && fuse && h->plan.csr_rows_independent && !h->no_side && !persist &&
                            (hv.n_targets > 0 || lt.n_targets > 0);
     if (side_rows) {
       if (!h->side) {
@@ -355,22 +379,11 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       }
       DA_CK(cudaEventRecord(h->ev_fork, s), "fork");   // the GEMM (and the gather) of this layer
     }
+    if (persist && rows_path) DA_CK(launch_rows(s), "graph attention (rows outside the dense tiles)");
     if (dense) {
-      AttnDenseArgs da_{};
-      da_.qimg = qimg; da_.kimg = kimg; da_.vimg = vimg;
-      da_.tiles = h->plan.tiles; da_.n_tiles = h->plan.n_tiles; da_.bitmap = h->plan.bitmap; da_.blk_list = h->plan.blk_list;
-      da_.H = c.heads; da_.C = C; da_.Cpad = Cpad;
-      da_.acc = h->dacc.as<float>(); da_.stats = h->dstats.as<float>();
-      da_.dbg = (l == h->dbg_layer) ? (long long*)h->dbg_trace : nullptr;
-      if (fuse) {
-        da_.row_fused = h->plan.row_fused;
-        da_.qkvs = a.qkvs; da_.ld = a.ld; da_.n_rows = Mt; da_.n_rows_resid = Mt;   // combined has Mt rows too
-        da_.n_rows_out = last ? Mr : Mt;   // r_hi / r_lo are [Mr, D], xa / xb planes [Mt, 256]
-        da_.rowptr = csr.rowptr; da_.col = csr.col; da_.weight = csr.weight;
-        da_.resid = a.resid; da_.ld_resid = a.ld_resid; da_.act = a.act; da_.out = a.out;
-      }
       Scoped sc(h, s, last ? TAG_ATTN_DENSE_LAST : TAG_ATTN_DENSE_HIDDEN);
-      DA_CK(launch_attn_dense(da_, s), "dense attention");
+      if (persist) { h->persist_launches++; DA_CK(launch_attn_hidden_persist(da_, s), "dense attention (persistent)"); }
+      else DA_CK(launch_attn_dense(da_, s), "dense attention");
     }
     if (side_rows) {   // launched AFTER the dense kernel so that its CTAs fill the slots the dense grid leaves in its tail
       DA_CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0), "fork");
@@ -380,7 +393,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     if (side_rows) {
       DA_CK(cudaStreamWaitEvent(s, h->ev_join, 0), "join");
     } else if (rows_path) {
-      DA_CK(launch_rows(s), "graph attention (residual rows)");
+      if (!persist) DA_CK(launch_rows(s), "graph attention (residual rows)");
     } else {
       Scoped sc(h, s, last ? TAG_ATTN_LAST : TAG_ATTN_HIDDEN);
       DA_CK(launch_attn_csr(a, s), "graph attention");
@@ -941,6 +954,7 @@ int da_graph_plan_info(const da_handle* h, int64_t* out, int32_t n) {
     out[8] = (on && p.n_tiles > 0 && p.real_rows_clean) ? 1 : 0;                       // no real row needs a CSR kernel
     out[9] = (h->fold_ready && on && p.n_tiles > 0 && p.real_rows_clean) ? 1 : 0;      // steps take the folded path (fold.cu)
   }
+  if (n >= 11) out[10] = h->persist_launches;   // hidden-layer launches of the persistent kernel so far (attn_hidden.cu)
   return DA_OK;
 }
 

@@ -452,6 +452,7 @@ struct AttnDenseArgs {
   int act = 0;
   LinearOut out;
   const uint16_t* blk_list = nullptr;   // DensePlan::blk_list (required)
+  int stagger_ns = 0;                   // attn_hidden.cu: start delay of every CTA's second stream
 };
 // Folded last layer (fold.cu): scores from the C-channel Q / K images, aggregation of the Cv = 32-channel folded
 // values V'; every row of every tile is finalised here (the planner guarantees no residual in-edge on a real row):
@@ -470,6 +471,10 @@ constexpr int DA_FUSE_MAX_RESIDUAL = 2;
 // true when the fused epilogue's staging area (128 skip rows of C floats) fits the kernel's K ring
 bool attn_dense_can_fuse(int C);
 cudaError_t launch_attn_dense(const AttnDenseArgs& a, cudaStream_t s);
+// Persistent two-stream form for the 32-channel hidden layers (attn_hidden.cu): every valid tile row must be finalised by
+// the kernel without residual in-edges (DensePlan::real_rows_clean); same results as launch_attn_dense
+bool attn_hidden_persist_supported(const AttnDenseArgs& a);
+cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s);
 size_t dense_image_elems(int n_tiles, int H, int Cpad);  // elements of ONE of the q / k / v image buffers
 
 }  // namespace da

@@ -196,10 +196,10 @@ class DenoiserEngine:
 
     def plan_info(self):
         """What the dense-tile planner made of the bound graph (``da_graph_plan_info``)."""
-        out = (C.c_int64 * 10)()
-        self._check(self._lib.da_graph_plan_info(self._h, out, 10))
+        out = (C.c_int64 * 11)()
+        self._check(self._lib.da_graph_plan_info(self._h, out, 11))
         keys = ("tiles", "blocks_total", "blocks_visited", "blocks_full", "reordered_graphs", "extra_sources", "fused_rows", "csr_rows",
-                "real_rows_clean", "folded")
+                "real_rows_clean", "folded", "persistent_hidden_launches")
         return dict(zip(keys, [int(v) for v in out]))
 
     def set_profiling(self, enable: bool):

@@ -210,7 +210,8 @@ int da_graph_stats(const da_handle* h, int64_t* n_dense_edges, int64_t* n_csr_ed
  * order), [5] promoted extra sources, [6] rows finalised inside the tensor-core kernel, [7] rows served by the CSR kernels; with n >= 10 also
  * [8] 1 when every real row is finalised by the tensor-core kernel without residual in-edges, [9] 1 when steps on this batch
  * take the weight-folded path (csrc/fold.cu: first projection from the 128-wide trunk hidden, last layer aggregated on the
- * 32-channel values of final_mlp[0] folded into lin_value; efficient_gat.py:135-145). */
+ * 32-channel values of final_mlp[0] folded into lin_value; efficient_gat.py:135-145); with n >= 11 also [10] the number of
+ * hidden-layer attention launches that took the persistent two-stream kernel (csrc/attn_hidden.cu) on this handle so far. */
 int da_graph_plan_info(const da_handle* h, int64_t* out, int32_t n);
 /* Built-in CUDA-event profiler: with da_set_profiling(h, 1) every kernel launch is bracketed
  * by events on its own stream and accumulated per launch site ("tag").  da_get_profile fills

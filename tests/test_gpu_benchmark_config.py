@@ -213,3 +213,39 @@ def test_folded_path_small_mixed_batches():
         info = mod.model._engine.plan_info()
         assert info["folded"] == expect, (arch, sizes, info)
         assert rel_err(got, want) < TOL, (arch, sizes, rel_err(got, want))
+
+
+@pytest.mark.parametrize("arch,V,sizes", [("exophormer", 8, [900, 900, 900]), ("transformer", 0, [900, 300, 144, 64]),
+                                          ("exophormer", 4, [130] * 40)])
+def test_persistent_hidden_layer_kernel_equals_the_per_tile_kernel(monkeypatch, arch, V, sizes):
+    """csrc/attn_hidden.cu: the 32-channel hidden layers run on ONE persistent CTA per SM with two independent streams of
+    (tile, head) items whenever every real row is finalised on the tensor cores.  Same scores, same masked online softmax,
+    same split-bf16 products as `attn_dense_kernel<32, 4>`; only the P V accumulation is grouped differently (P_hi [V_hi |
+    V_lo] as one N = 64 instruction, two accumulators summed at the end), so a free-running 3-step DDIM trajectory must
+    agree with `DA_HIDDEN_PERSIST=0` (per-(tile, head) CTAs) to fp32 rounding -- with full and partial tiles, more items
+    than streams (3 x 8 x 8 and 40 x 2 x 8 items), fewer items than streams, GELU between the layers (transformer) and
+    none (exophormer) -- and both with the live oracle."""
+    ei, batch = synth_graph_batch(sizes, kind="expander", degree="60%", seed=21)
+    M = sum(sizes)
+    g = torch.Generator().manual_seed(3)
+    feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, 4, generator=g)
+    outs = {}
+    for persist in ("1", "0"):
+        monkeypatch.setenv("DA_HIDDEN_PERSIST", persist)
+        ref, mod = _pair(arch, V, "bf16x3", "auto", seed=23)
+        xt = x.to(DEV)
+        traj = []
+        for i in (290, 280, 270):
+            t = torch.full((M,), i, dtype=torch.long, device=DEV)
+            xt, _ = mod.p_sample(xt, t, i, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV), batch=batch.to(DEV))
+            traj.append(xt.cpu())
+        info = mod.model._engine.plan_info()
+        assert info["real_rows_clean"] == 1, info
+        assert info["persistent_hidden_launches"] == (9 if persist == "1" else 0), info
+        outs[persist] = traj
+    for a, b in zip(outs["1"], outs["0"]):
+        assert rel_err(a, b) < 2e-6, (arch, sizes, rel_err(a, b))
+    with torch.no_grad():
+        t = torch.full((M,), 290, dtype=torch.long)
+        want = ref.p_sample(x, t, 290, edge_index=ei, patch_feats=feats, batch=batch)[0]
+    assert rel_err(outs["1"][0], want) < TOL, rel_err(outs["1"][0], want)
