@@ -334,12 +334,19 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
   const int beg = rowptr[node], end = rowptr[node + 1];
   const size_t lo_off = (size_t)64 * Cpad;
   float m = -INFINITY, l = 0.f, acc = 0.f;   // acc: channel `lane` of this warp's partial sum
-  for (int base = beg + wstart * 32; base < end; base += 32 * wstep) {
+  // edge indices run one chunk ahead of the K / V rows (col -> img_slot -> row address is a chain of dependent loads)
+  auto fetch_edge = [&](int base, int& j_, float& w_, int& sj_, bool& valid_) {
     const int e = base + lane;
-    const bool valid = e < end;
-    const int j = valid ? col[e] : node;
-    const float w = (valid && weight != nullptr) ? weight[e] : 1.f;
-    const int sj = (img_slot != nullptr) ? __ldg(img_slot + j) : -1;
+    valid_ = e < end;
+    j_ = valid_ ? __ldg(col + e) : node;
+    w_ = (valid_ && weight != nullptr) ? __ldg(weight + e) : 1.f;
+    sj_ = (img_slot != nullptr) ? __ldg(img_slot + j_) : -1;
+  };
+  int j_n, sj_n; float w_n; bool valid_n;
+  fetch_edge(beg + wstart * 32, j_n, w_n, sj_n, valid_n);
+  for (int base = beg + wstart * 32; base < end; base += 32 * wstep) {
+    const int j = j_n, sj = sj_n; const float w = w_n; const bool valid = valid_n;
+    if (base + 32 * wstep < end) fetch_edge(base + 32 * wstep, j_n, w_n, sj_n, valid_n);
     const __nv_bfloat16* kb = sj >= 0 ? kimg + ((size_t)(sj >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (sj & 63) * 8 : nullptr;
     const __nv_bfloat16* vb = sj >= 0 ? vimg + ((size_t)(sj >> 6) * H + head) * ((size_t)2 * 64 * Cpad) + (sj & 63) * 8 : nullptr;
     float kf[C], vf[C];

@@ -958,7 +958,7 @@ attn_dense_fold_kernel(AttnFoldArgs a, int tmem_cols) {
 //   warps 2-5   softmax (as above), hands the row sums l to the epilogue warps through shared memory
 //   warps 6-9   park the next item's Q tile in the second TMEM Q buffer, then finalise the current item:
 //               O (double-buffered in TMEM) / l -> partial[node, head, :]
-// TMEM: S/P 2 x 64 | O 2 x 32 | Q 2 x Cq columns (480 of 512 at Cq = 144).
+// TMEM: S/P 2 x 64 | O 2 x 32 (hi / lo halves of ONE buffer) | Q 2 x Cq columns (480 of 512 at Cq = 144).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int NTP = 320;
 
@@ -1009,7 +1009,7 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   const uint32_t tmem_s = tmem_base;                  // 2 x TS columns
-  const uint32_t tmem_o0 = tmem_base + 2 * TS;        // 2 x FV columns
+  const uint32_t tmem_o0 = tmem_base + 2 * TS;        // 2 x FV columns: O_a = P_hi V'_hi + P_lo V'_hi | O_b = P_hi V'_lo (one buffer)
   const uint32_t tmem_q0 = tmem_o0 + 2 * FV;          // 2 x Cq columns
 
   if (warp == 0) {  // ===== bulk-copy producer: running block counter kc over all items =====
@@ -1037,7 +1037,11 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
       }
     }
   } else if (warp == 1) {  // ===== MMA issuer =====
-    const uint32_t idesc_s = make_idesc(TM, TS), idesc_o = make_idesc(TM, FV) | (1u << 16);
+    // P_hi [V'_hi | V'_lo] is ONE N = 64 instruction (the lo plane continues the hi plane's chunk sequence in the stage, and
+    // an MMA of this shape costs ~45 cycles for any N <= 64: profiles/r2_mma_issue_rate_b200.txt): 8 instead of 12 per block
+    const uint32_t idesc_s = make_idesc(TM, TS);
+    const uint32_t idesc_o2 = make_idesc(TM, 2 * FV) | (1u << 16), idesc_o1 = make_idesc(TM, FV) | (1u << 16);
+    static_assert(TS * FV * 2 == 4 * TS * 16, "the lo plane must continue the hi plane's chunk sequence");
     const int ksteps = Cq / 16;
     const uint64_t dk0 = make_desc_nosw(smem_u32(k_sm), TS * 16, 128);
     const uint64_t dv0 = make_desc_nosw(smem_u32(v_sm), 128, TS * 16);
@@ -1088,17 +1092,16 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
           const int b = g & 1, vs = g % ST;
           mbar_wait(&sh->p_full[b], (uint32_t)(g >> 1) & 1u);
           mbar_wait(&sh->v_full[vs], (uint32_t)(g / ST) & 1u);
-          if (j == 0 && it >= 2) mbar_wait(&sh->o_empty[ob], (uint32_t)((it >> 1) - 1) & 1u);   // epilogue of item it - 2 has read O
+          if (j == 0 && it >= 1) mbar_wait(&sh->o_empty[(it - 1) & 1], (uint32_t)((it - 1) >> 1) & 1u);   // epilogue of item it - 1 has read O
           tc_fence_after();
           if (elect_one()) {
             const uint32_t p_hi = tmem_s + (uint32_t)(b * TS), p_lo = p_hi + TS / 2;
-            const uint32_t o_t = tmem_o0 + (uint32_t)(ob * FV);
-            const uint64_t dv_hi = dv0 + (uint32_t)vs * vstage_u, dv_lo = dv_hi + vplane_u;
+            const uint32_t o_t = tmem_o0;
+            const uint64_t dv_hi = dv0 + (uint32_t)vs * vstage_u;
 #pragma unroll
             for (int kk = 0; kk < TS / 16; ++kk) {
-              tc_mma_bf16_ts(o_t, p_hi + kk * 8, dv_hi + kk * 16, idesc_o, (j | kk) ? 1u : 0u);
-              tc_mma_bf16_ts(o_t, p_hi + kk * 8, dv_lo + kk * 16, idesc_o, 1u);
-              tc_mma_bf16_ts(o_t, p_lo + kk * 8, dv_hi + kk * 16, idesc_o, 1u);
+              tc_mma_bf16_ts(o_t, p_hi + kk * 8, dv_hi + kk * 16, idesc_o2, (j | kk) ? 1u : 0u);
+              tc_mma_bf16_ts(o_t, p_lo + kk * 8, dv_hi + kk * 16, idesc_o1, 1u);
             }
             tc_commit(&sh->pv_done[b]);
             tc_commit(&sh->v_empty[vs]);
@@ -1124,7 +1127,7 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
       const uint16_t* __restrict__ blist = a.blk_list + ti.list_off;
       const bool row_valid = r < ti.rows;
       const uint32_t* bm_row = a.bitmap + ti.bm_off + (size_t)(ti.row0 + r) * ti.bm_words;
-      const uint32_t o_t = tmem_o0 + (uint32_t)((it & 1) * FV) + lane_off;
+      const uint32_t o_t = tmem_o0 + lane_off;
       float m = -INFINITY, l = 0.f;
       uint2 bits_next = row_valid ? *reinterpret_cast<const uint2*>(bm_row + (int)(__ldg(blist) >> 1) * 2) : make_uint2(0u, 0u);
       for (int j = 0; j < nblk; ++j, ++g) {
@@ -1179,7 +1182,7 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
           }
           if (j > 0) {
 #pragma unroll
-            for (int c0 = 0; c0 < FV; c0 += 16) {
+            for (int c0 = 0; c0 < 2 * FV; c0 += 16) {
               uint32_t o[16];
               tmem_ld16(o_t + c0, o);
               tmem_ld_wait();
@@ -1250,10 +1253,14 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
       mbar_wait(&sh->l_full[ob], (uint32_t)(it >> 1) & 1u);
       mbar_wait(&sh->o_full[ob], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      uint32_t o[FV];
-      tmem_ld16(tmem_o0 + (uint32_t)(ob * FV) + lane_off, o);
-      tmem_ld16(tmem_o0 + (uint32_t)(ob * FV) + lane_off + 16, o + 16);
+      uint32_t o[FV], o2[FV];
+      tmem_ld16(tmem_o0 + lane_off, o);
+      tmem_ld16(tmem_o0 + lane_off + 16, o + 16);
+      tmem_ld16(tmem_o0 + lane_off + 32, o2);
+      tmem_ld16(tmem_o0 + lane_off + 48, o2 + 16);
       tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < FV; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
       const float l = sh->lbuf[ob][r];
       tc_fence_before();
       __syncwarp();

@@ -472,8 +472,10 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (a.dbg) attn_hidden_persist_kernel<true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, a);
-  else attn_hidden_persist_kernel<false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, a);
+  AttnDenseArgs b = a;
+  if (items < 8 * (int)grid) b.stagger_ns = 0;   // short streams (small batches): the start delay would cost more than it hides
+  if (a.dbg) attn_hidden_persist_kernel<true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
+  else attn_hidden_persist_kernel<false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
   return cudaGetLastError();
 }
 
