@@ -59,6 +59,8 @@ struct da_handle {
   Linear hoist, mlp2, head1;
   std::vector<Linear> layer;
   DevBuf pos_w0, pos_b0, pos_w2, pos_b2, time_emb, w1pt_T, b1, headb_w, headb_b, headr_w, headr_b, virt_emb;
+  DevBuf pro_wc, pro_tt;   // table form of the prologue (pointwise.cu): composed pos_mlp[2] / time_emb products
+  bool no_pro_table = getenv("DA_NO_PRO_TABLE") != nullptr && getenv("DA_NO_PRO_TABLE")[0] == '1';
   // graph
   CsrGraph csr;        // every edge (attn_mode = CSR)
   DensePlan plan;      // bitmap tiles + residual CSR (attn_mode = AUTO)
@@ -196,6 +198,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     a.pos_w0 = h->pos_w0.as<float>(); a.pos_b0 = h->pos_b0.as<float>();
     a.pos_w2 = h->pos_w2.as<float>(); a.pos_b2 = h->pos_b2.as<float>();
     a.time_emb = h->time_emb.as<float>(); a.w1pt_T = h->w1pt_T.as<float>();
+    if (!h->no_pro_table && h->pro_wc.p && h->pro_tt.p) { a.wc_T = h->pro_wc.as<float>(); a.tt = h->pro_tt.as<float>(); }
     a.M = Mr; a.C_in = c.in_channels; a.Hm = Hm; a.T = c.steps;
     a.act = (c.head_kind == DA_HEAD_SE3) ? ACT_LRELU : ACT_GELU;
     a.row_ext = h->use_plan ? h->plan.ext_of_int : nullptr;   // internal node order of the planner (x / t are the caller's)
@@ -528,7 +531,7 @@ void da_destroy(da_handle* h) {
                    &h->xa, &h->xb, &h->r, &h->u, &h->model_out, &h->scores, &h->stats, &h->feats_sp_hi,
                    &h->feats_sp_lo, &h->h_hi, &h->h_lo, &h->comb_hi, &h->comb_lo, &h->xa_hi, &h->xa_lo, &h->xb_hi,
                    &h->xb_lo, &h->r_hi, &h->r_lo, &h->qimg, &h->kimg, &h->vimg, &h->qimg_l, &h->kimg_l, &h->vimg_l, &h->dacc, &h->dstats,
-                   &h->feats_perm, &h->tmin};
+                   &h->feats_perm, &h->tmin, &h->pro_wc, &h->pro_tt};
   for (auto* b : all) b->release();
   free_csr(&h->csr);
   free_plan(&h->plan);
@@ -590,12 +593,13 @@ int da_load_weights(da_handle* h, const da_weight_desc* w, int32_t n) {
     return cudaSuccess;
   };
 
+  std::vector<float> pw2, pb2, temb;   // kept for the composed prologue tables below
   {
     DA_NEED(v0, "pos_mlp.0.weight", 16, Cin); DA_CK(up_direct(h->pos_w0, v0));
     DA_NEED(v1, "pos_mlp.0.bias", 16, 1); DA_CK(up_direct(h->pos_b0, v1));
-    DA_NEED(v2, "pos_mlp.2.weight", 32, 16); DA_CK(up_direct(h->pos_w2, v2));
-    DA_NEED(v3, "pos_mlp.2.bias", 32, 1); DA_CK(up_direct(h->pos_b2, v3));
-    DA_NEED(v4, "time_emb.weight", c.steps, 32); DA_CK(up_direct(h->time_emb, v4));
+    DA_NEED(v2, "pos_mlp.2.weight", 32, 16); DA_CK(up_direct(h->pos_w2, v2)); DA_CK(fetch(v2, pw2));
+    DA_NEED(v3, "pos_mlp.2.bias", 32, 1); DA_CK(up_direct(h->pos_b2, v3)); DA_CK(fetch(v3, pb2));
+    DA_NEED(v4, "time_emb.weight", c.steps, 32); DA_CK(up_direct(h->time_emb, v4)); DA_CK(fetch(v4, temb));
   }
   {  // mlp[0]: split into the step-invariant feature block and the 64 pose+time columns
     DA_NEED(vw, "mlp.0.weight", Hm, D);
@@ -610,6 +614,26 @@ int da_load_weights(da_handle* h, const da_weight_desc* w, int32_t n) {
     DA_CK(finish_linear(h->hoist, wf, bias, Hm, Dv));
     DA_CK(upload(h->w1pt_T, wpt.data(), wpt.size()));
     DA_CK(upload(h->b1, bias.data(), bias.size()));
+    {  // table form of the prologue (pointwise.cu: prologue_table_kernel), composed in fp64
+      std::vector<float> wc((size_t)16 * Hm), ttab((size_t)c.steps * Hm);
+      for (int n_ = 0; n_ < Hm; ++n_) {
+        const float* wrow = &tmp[(size_t)n_ * D + Dv];   // [pos 32 | time 32] columns of W1 row n_
+        for (int u = 0; u < 16; ++u) {
+          double acc = 0.0;
+          for (int v = 0; v < 32; ++v) acc += (double)wrow[v] * (double)pw2[(size_t)v * 16 + u];
+          wc[(size_t)u * Hm + n_] = (float)acc;
+        }
+        double bc = 0.0;
+        for (int v = 0; v < 32; ++v) bc += (double)wrow[v] * (double)pb2[v];
+        for (int t_ = 0; t_ < c.steps; ++t_) {
+          double acc = bc;
+          for (int v = 0; v < 32; ++v) acc += (double)wrow[32 + v] * (double)temb[(size_t)t_ * 32 + v];
+          ttab[(size_t)t_ * Hm + n_] = (float)acc;
+        }
+      }
+      DA_CK(upload(h->pro_wc, wc.data(), wc.size()));
+      DA_CK(upload(h->pro_tt, ttab.data(), ttab.size()));
+    }
   }
   {
     DA_NEED(vw, "mlp.2.weight", D, Hm);

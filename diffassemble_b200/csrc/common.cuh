@@ -144,6 +144,8 @@ struct PrologueArgs {
   const float* pos_b2;   // [32]
   const float* time_emb; // [T, 32]
   const float* w1pt_T;   // [64, Hm]  transposed W1[:, Dv:Dv+64]
+  // table form (optional, both or neither): wc_T [16, Hm] = (W1[:, pos] W_p2)^T, tt [T, Hm] = time_emb W1[:, time]^T + W1[:, pos] b_p2
+  const float* wc_T = nullptr; const float* tt = nullptr;
   int M, C_in, Hm, T, act;
   LinearOut out;         // [M, Hm]
   // optional: the engine's internal node order (DensePlan::ext_of_int): internal row r reads x / t of the caller's row

@@ -12,6 +12,8 @@
 // The products are formed once per da_load_weights in fp64 on the device and rounded to fp32 (then split to bf16 hi / lo
 // like every other weight).  Virtual-node rows (exophormer_gnn.py:169-178) enter the first projection through one-hot
 // columns appended to h: column 128 + v of the folded weight holds W_0 (virt_emb[v] - b_2).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace da {
@@ -76,32 +78,47 @@ head_fold_kernel(HeadFoldArgs a) {
   for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-#pragma unroll 2
-  for (int k0 = 0; k0 < Kt; k0 += 16) {
-    const bool from_h = k0 < a.Hm;
+  // A fragments of KB k-steps are requested together (KB x 8 independent 4-byte loads per thread) before their MMAs:
+  // the loop is pure load latency otherwise.  KB = 8 when both inputs are multiples of 128 columns wide, else 1.
+  auto k_block = [&](const int k_base, auto kb_tag) {
+    constexpr int KB = decltype(kb_tag)::value;
+    const bool from_h = k_base < a.Hm;
     const __nv_bfloat16* ph = from_h ? a.h_hi : a.x_hi;
     const __nv_bfloat16* pl = from_h ? a.h_lo : a.x_lo;
-    const int ld = from_h ? a.ld_h : a.ld_x, kk = (from_h ? k0 : k0 - a.Hm) + 2 * t;
-    uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
-    if (v0) {
-      const size_t o = (size_t)r0 * ld + kk;
-      ah[0] = __ldg(reinterpret_cast<const uint32_t*>(ph + o)); ah[2] = __ldg(reinterpret_cast<const uint32_t*>(ph + o + 8));
-      al[0] = __ldg(reinterpret_cast<const uint32_t*>(pl + o)); al[2] = __ldg(reinterpret_cast<const uint32_t*>(pl + o + 8));
-    }
-    if (v1) {
-      const size_t o = (size_t)r1 * ld + kk;
-      ah[1] = __ldg(reinterpret_cast<const uint32_t*>(ph + o)); ah[3] = __ldg(reinterpret_cast<const uint32_t*>(ph + o + 8));
-      al[1] = __ldg(reinterpret_cast<const uint32_t*>(pl + o)); al[3] = __ldg(reinterpret_cast<const uint32_t*>(pl + o + 8));
+    const int ld = from_h ? a.ld_h : a.ld_x, kk0 = (from_h ? k_base : k_base - a.Hm) + 2 * t;
+    uint32_t ah[KB][4], al[KB][4];
+#pragma unroll
+    for (int s_ = 0; s_ < KB; ++s_) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { ah[s_][e] = 0u; al[s_][e] = 0u; }
+      if (v0) {
+        const size_t o = (size_t)r0 * ld + kk0 + 16 * s_;
+        ah[s_][0] = __ldg(reinterpret_cast<const uint32_t*>(ph + o)); ah[s_][2] = __ldg(reinterpret_cast<const uint32_t*>(ph + o + 8));
+        al[s_][0] = __ldg(reinterpret_cast<const uint32_t*>(pl + o)); al[s_][2] = __ldg(reinterpret_cast<const uint32_t*>(pl + o + 8));
+      }
+      if (v1) {
+        const size_t o = (size_t)r1 * ld + kk0 + 16 * s_;
+        ah[s_][1] = __ldg(reinterpret_cast<const uint32_t*>(ph + o)); ah[s_][3] = __ldg(reinterpret_cast<const uint32_t*>(ph + o + 8));
+        al[s_][1] = __ldg(reinterpret_cast<const uint32_t*>(pl + o)); al[s_][3] = __ldg(reinterpret_cast<const uint32_t*>(pl + o + 8));
+      }
     }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const size_t wo = (size_t)(nt * 8 + g) * KP + k0 + 2 * t;
-      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh + wo), bh1 = *reinterpret_cast<const uint32_t*>(wh + wo + 8);
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl + wo), bl1 = *reinterpret_cast<const uint32_t*>(wl + wo + 8);
-      mma_bf16_16816(acc[nt], ah, bh0, bh1);
-      mma_bf16_16816(acc[nt], ah, bl0, bl1);
-      mma_bf16_16816(acc[nt], al, bh0, bh1);
+    for (int s_ = 0; s_ < KB; ++s_) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const size_t wo = (size_t)(nt * 8 + g) * KP + k_base + 16 * s_ + 2 * t;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wh + wo), bh1 = *reinterpret_cast<const uint32_t*>(wh + wo + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wl + wo), bl1 = *reinterpret_cast<const uint32_t*>(wl + wo + 8);
+        mma_bf16_16816(acc[nt], ah[s_], bh0, bh1);
+        mma_bf16_16816(acc[nt], ah[s_], bl0, bl1);
+        mma_bf16_16816(acc[nt], al[s_], bh0, bh1);
+      }
     }
+  };
+  if (((a.Hm | a.hid) & 127) == 0) {
+    for (int k0 = 0; k0 < Kt; k0 += 128) k_block(k0, std::integral_constant<int, 8>{});
+  } else {
+    for (int k0 = 0; k0 < Kt; k0 += 16) k_block(k0, std::integral_constant<int, 1>{});
   }
   // + per-head aggregates + bias, GELU -> u (this warp's 16 x 32 tile in shared memory)
   float* u_s = u_all + (size_t)warp * HF_ROWS * HF_PITCH;

@@ -246,12 +246,14 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int row_base = m0 + q * 32;
       int slots[4] = {-1, -1, -1, -1};
+      int my_slot = -1;   // image row of THIS thread's accumulator row (direct path below)
       if (p.node_slot != nullptr) {   // issued before the accumulator wait so the latency is hidden
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = row_base + i * 8 + (lane >> 2);
           if (row < p.irows) slots[i] = __ldg(p.node_slot + row);
         }
+        if (row_base + lane < p.irows) my_slot = __ldg(p.node_slot + row_base + lane);
       }
       const uint32_t tflags = p.f32_tile_flags ? (uint32_t)__ldg(p.f32_tile_flags + (m0 >> 7)) : 3u;   // BM == 128
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -262,6 +264,23 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         const int col = n0 + c0 + sub_col;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        // operand-image path (below): its bias words and its (part, head, channel) split are requested / computed here, in
+        // front of the accumulator load -- the ncu source view had the epilogue warps waiting on exactly these loads
+        const int ig_col = n0 + c0 + (lane & 3) * 8;
+        float4 ibb0 = make_float4(0.f, 0.f, 0.f, 0.f), ibb1 = ibb0;
+        int ipart = 3, ih = 0, ic = 0, iC_ = p.iC, iCpad_ = p.iCpad;
+        if (p.node_slot != nullptr) {
+          const int HC = p.iH * p.iC;
+          ipart = ig_col / HC;
+          if (ipart < 3) {
+            const int within = ig_col - ipart * HC;
+            if constexpr (MODE == 3) {
+              if (ipart == 2) { iC_ = ex.Cv; iCpad_ = ex.Cvpad; }
+            }
+            ih = within / iC_; ic = within - ih * iC_;
+            if (p.bias) { ibb0 = __ldg(reinterpret_cast<const float4*>(p.bias + ig_col)); ibb1 = __ldg(reinterpret_cast<const float4*>(p.bias + ig_col + 4)); }
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_addr + c0, r);
         tmem_ld_wait();
@@ -290,6 +309,55 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
             }
           }
           continue;
+        }
+        if constexpr (MODE == 3) {
+          // (folded last layer only: measured on the hidden-layer GEMMs, whose skip quarter keeps the staging tile in use,
+          // the same path was 9 % SLOWER than the staged one -- 0.162 vs 0.149 ms for the two K = 256 launches -- and 6 %
+          // faster here.)
+          // Q / K / V chunks that nobody reads in fp32 go straight from the accumulator registers to the operand images:
+          // thread == row, and within an 8-channel chunk the image rows of consecutive nodes are 16 bytes apart, so the
+          // 32 lanes of a store instruction already write 512 contiguous bytes -- no transpose through shared memory
+          const int HC = p.iH * p.iC;
+          const int part = (n0 + c0) / HC;   // a 32-column chunk lies in one part (HC % 32 == 0)
+          const bool f32_needed = p.cf != nullptr && (tflags == 3u || (part == 0 ? (tflags & 1u) : (tflags & 2u)) != 0u);
+          if (p.node_slot != nullptr && p.chi == nullptr && part < 3 && !f32_needed) {
+            if (my_slot >= 0) {
+              int iC = p.iC, iCpad = p.iCpad;
+              if (part == 2) { iC = ex.Cv; iCpad = ex.Cvpad; }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int g_col = n0 + c0 + u * 8;
+                const int within = g_col - part * HC;
+                const int h = within / iC, c = within - h * iC;
+                float4 bb0 = make_float4(0.f, 0.f, 0.f, 0.f), bb1 = bb0;
+                if (p.bias) { bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col)); bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col + 4)); }
+                const float vv[8] = {__uint_as_float(r[8 * u]) + bb0.x, __uint_as_float(r[8 * u + 1]) + bb0.y,
+                                     __uint_as_float(r[8 * u + 2]) + bb0.z, __uint_as_float(r[8 * u + 3]) + bb0.w,
+                                     __uint_as_float(r[8 * u + 4]) + bb1.x, __uint_as_float(r[8 * u + 5]) + bb1.y,
+                                     __uint_as_float(r[8 * u + 6]) + bb1.z, __uint_as_float(r[8 * u + 7]) + bb1.w};
+                __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  hi[e] = __float2bfloat16_rn(vv[e]);
+                  lo[e] = __float2bfloat16_rn(vv[e] - __bfloat162float(hi[e]));
+                }
+                if (part == 0) {
+                  const int tile_i = my_slot >> 7, r_ = my_slot & 127;
+                  __nv_bfloat16* base = p.qimg + ((size_t)tile_i * p.iH + h) * ((size_t)2 * 128 * iCpad);
+                  const size_t off = (size_t)(c >> 3) * (128 * 8) + (size_t)r_ * 8;
+                  *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+                  *reinterpret_cast<uint4*>(base + (size_t)128 * iCpad + off) = *reinterpret_cast<uint4*>(lo);
+                } else {
+                  const int blk = my_slot >> 6, rb = my_slot & 63;
+                  __nv_bfloat16* base = (part == 1 ? p.kimg : p.vimg) + ((size_t)blk * p.iH + h) * ((size_t)2 * 64 * iCpad);
+                  const size_t off = (size_t)(c >> 3) * (64 * 8) + (size_t)rb * 8;
+                  *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+                  *reinterpret_cast<uint4*>(base + (size_t)64 * iCpad + off) = *reinterpret_cast<uint4*>(lo);
+                }
+              }
+            }
+            continue;
+          }
         }
         // thread == row: park the 32 columns of this row in the staging tile
         float4* srow = reinterpret_cast<float4*>(stage + lane * EPI_PITCH);
@@ -329,18 +397,9 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
         }
         if (p.node_slot != nullptr) {
           // operand images: 8 consecutive channels (16 bytes of bf16) per lane, 8 rows per instruction
-          const int HC = p.iH * p.iC;
-          const int g_col = n0 + c0 + (lane & 3) * 8;
-          const int part = g_col / HC;
+          const int part = ipart, h = ih, c = ic, iCpad = iCpad_;
+          const float4 bb0 = ibb0, bb1 = ibb1;
           if (part < 3) {
-            const int within = g_col - part * HC;
-            int iC = p.iC, iCpad = p.iCpad;
-            if constexpr (MODE == 3) {
-              if (part == 2) { iC = ex.Cv; iCpad = ex.Cvpad; }
-            }
-            const int h = within / iC, c = within - h * iC;
-            float4 bb0 = make_float4(0.f, 0.f, 0.f, 0.f), bb1 = bb0;
-            if (p.bias) { bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col)); bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + g_col + 4)); }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int rr = i * 8 + (lane >> 2);

@@ -102,6 +102,109 @@ prologue_kernel(PrologueArgs a) {
   }
 }
 
+// Table form of the prologue (round 2).  Two more products of the same line are step-invariant LINEAR maps of tiny inputs
+// and are composed once per da_load_weights (fp64 on the host, api.cu):
+//   W1[:, pos] pos_mlp[2](g)   = (W1[:, pos] W_p2) g + W1[:, pos] b_p2        g = GELU(pos_mlp[0](x)), 16 values per node
+//   W1[:, time] time_emb[t]    = row t of a [T, Hm] table
+// so a node costs 16 x Hm FMAs instead of (16 x 32 + 64 x Hm), no 32 KB weight stage per CTA and no shared memory at
+// all: one warp owns one node at a time, lane l the VPL = Hm / 32 contiguous columns [l * VPL, (l + 1) * VPL) (its slice
+// of the composed matrix stays in registers), lanes 0-15 evaluate the 16 hidden units and hand them round by shuffles;
+// P / table rows / outputs are fully coalesced row accesses.  tt[t, :] already holds W1[:, pos] b_p2.
+template <int VPL>
+__global__ void __launch_bounds__(PRO_NT)
+prologue_table_kernel(PrologueArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+  const int Hm = a.Hm, c0 = lane * VPL;
+  float wc[16][VPL];
+#pragma unroll
+  for (int u = 0; u < 16; ++u)
+#pragma unroll
+    for (int i = 0; i < VPL; i += 2) {
+      const float2 t2 = __ldg(reinterpret_cast<const float2*>(a.wc_T + (size_t)u * Hm + c0 + i));
+      wc[u][i] = t2.x; wc[u][i + 1] = t2.y;
+    }
+  float w0[8]; float b0 = 0.f;   // lanes 0-15: row `lane` of pos_mlp[0]
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w0[c] = (lane < 16 && c < a.C_in) ? __ldg(a.pos_w0 + lane * a.C_in + c) : 0.f;
+  if (lane < 16) b0 = __ldg(a.pos_b0 + lane);
+  float bias[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) bias[i] = __ldg(a.b1 + c0 + i);
+  // NPW nodes per warp and iteration, their (dependent) index / row loads issued together
+  constexpr int NPW = 4;
+  for (int nb = gw * NPW; nb < a.M; nb += nw * NPW) {
+    int ext[NPW], tt[NPW];
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      const int node = min(nb + q, a.M - 1);
+      ext[q] = a.row_ext ? __ldg(a.row_ext + node) : node;   // the caller's row of this internal node
+    }
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      int tq = a.t_uniform;
+      if (a.t) tq = (int)__ldg(a.t + ext[q]);
+      tt[q] = min(max(tq, 0), a.T - 1);
+    }
+    float s[NPW][VPL], g[NPW];
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      const int node = min(nb + q, a.M - 1);
+      if (a.P) {
+#pragma unroll
+        for (int i = 0; i < VPL; i += (VPL % 4 == 0 ? 4 : 2)) {
+          if (VPL % 4 == 0) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.P + (size_t)node * Hm + c0 + i)); s[q][i] = t4.x; s[q][i + 1] = t4.y; s[q][i + 2] = t4.z; s[q][i + 3] = t4.w; }
+          else { const float2 t2 = __ldg(reinterpret_cast<const float2*>(a.P + (size_t)node * Hm + c0 + i)); s[q][i] = t2.x; s[q][i + 1] = t2.y; }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s[q][i] = bias[i];
+      }
+      g[q] = b0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < a.C_in) g[q] = fmaf(w0[c], __ldg(a.x + (size_t)ext[q] * a.C_in + c), g[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) s[q][i] += __ldg(a.tt + (size_t)tt[q] * Hm + c0 + i);
+      g[q] = gelu_erf(g[q]);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+#pragma unroll
+      for (int q = 0; q < NPW; ++q) {
+        const float gu = __shfl_sync(0xffffffffu, g[q], u);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) s[q][i] = fmaf(wc[u][i], gu, s[q][i]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NPW; ++q) {
+      const int node = nb + q;
+      if (node >= a.M) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) s[q][i] = apply_act_rt(s[q][i], a.act);
+      if (a.out.f32) {
+#pragma unroll
+        for (int i = 0; i < VPL; i += 2)
+          *reinterpret_cast<float2*>(a.out.f32 + (size_t)node * a.out.ldc + c0 + i) = make_float2(s[q][i], s[q][i + 1]);
+      }
+      if (a.out.hi) {
+#pragma unroll
+        for (int i = 0; i < VPL; i += 2) {
+          __nv_bfloat162 h2, l2;
+          h2.x = __float2bfloat16_rn(s[q][i]); h2.y = __float2bfloat16_rn(s[q][i + 1]);
+          l2.x = __float2bfloat16_rn(s[q][i] - __bfloat162float(h2.x)); l2.y = __float2bfloat16_rn(s[q][i + 1] - __bfloat162float(h2.y));
+          *reinterpret_cast<__nv_bfloat162*>(a.out.hi + (size_t)node * a.out.ld_split + c0 + i) = h2;
+          *reinterpret_cast<__nv_bfloat162*>(a.out.lo + (size_t)node * a.out.ld_split + c0 + i) = l2;
+        }
+      }
+    }
+  }
+}
+
 // 2D head: out = W_b @ u + b_b (final_mlp[2], efficient_gat.py:91), fused with the sampler update.
 __global__ void head_final_2d_kernel(HeadFinalArgs a) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +308,15 @@ __global__ void fill_rows_kernel(float* __restrict__ dst, int ld, const float* _
 cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
   if (a.M <= 0) return cudaSuccess;
   if (a.C_in > 8) return cudaErrorInvalidValue;
+  if (a.wc_T != nullptr && a.tt != nullptr && (a.Hm == 64 || a.Hm == 128 || a.Hm == 256) && (a.out.ldc % 2 == 0) && (a.out.ld_split % 2 == 0)) {
+    // table form: 4 nodes per warp at a time; 8 per warp amortise the register-resident weight slice on large batches
+    const long long warps = ((long long)a.M + (a.M >= 148 * 256 / 4 ? 7 : 3)) / (a.M >= 148 * 256 / 4 ? 8 : 4);
+    const unsigned grid = (unsigned)((warps * 32 + PRO_NT - 1) / PRO_NT);
+    if (a.Hm == 64) prologue_table_kernel<2><<<grid, PRO_NT, 0, s>>>(a);
+    else if (a.Hm == 128) prologue_table_kernel<4><<<grid, PRO_NT, 0, s>>>(a);
+    else prologue_table_kernel<8><<<grid, PRO_NT, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)64 * a.Hm * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {   // static (23 KB) + dynamic shared memory exceeds the 48 KB default
