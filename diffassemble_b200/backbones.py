@@ -218,6 +218,10 @@ class _EngineMixin:
         with torch.cuda.stream(st):
             if self._spare_last_use is not None:
                 st.wait_event(self._spare_last_use)   # its buffers may still be read by launches of the previous batch
+            if any(isinstance(t_, Tensor) and t_.is_cuda for t_ in (edge_index, feats, batch)):
+                # device inputs (e.g. the encoder's output for the next batch) may still be being written on the compute
+                # stream: order this stream behind everything enqueued there so far.  Pinned host inputs keep full overlap.
+                st.wait_stream(main)
             wkey = self._weights_state_key()
             if wkey != self._spare_weights_key:
                 st.wait_stream(main)                  # parameters may have been written on the compute stream

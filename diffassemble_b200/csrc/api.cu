@@ -81,6 +81,7 @@ struct da_handle {
   bool fold_persist = !(getenv("DA_FOLD_PERSIST") != nullptr && getenv("DA_FOLD_PERSIST")[0] == '0');
   // hidden layers on the persistent two-stream kernel (attn_hidden.cu) whenever its preconditions hold; "0": one CTA per (tile, head)
   bool hidden_persist = !(getenv("DA_HIDDEN_PERSIST") != nullptr && getenv("DA_HIDDEN_PERSIST")[0] == '0');
+  bool no_gather_ride = getenv("DA_NO_GATHER_RIDE") != nullptr && getenv("DA_NO_GATHER_RIDE")[0] == '1';
   int hidden_stagger_ns = getenv("DA_HIDDEN_STAGGER_NS") != nullptr ? atoi(getenv("DA_HIDDEN_STAGGER_NS")) : 8000;
   bool fold_cfg = false, fold_ready = false;
   int Kf = 0;
@@ -272,6 +273,8 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
       DA_CK(run_linear(h, (fold && l == 0) ? h->fold0 : h->layer[l], xin, ld_in, xin_hi, xin_lo, ld_in, Mt, ACT_NONE, o, tag, s), "qkvs gemm");
     }
     const CsrGraph& csr = h->use_plan ? h->plan.residual : h->csr;
+    bool gather_pending = false;
+    PackArgs gather_args{};
     if (dense) {  // bitmap edges on the tensor cores; the CSR kernel below continues with the residual edges
       PackArgs pa{};
       pa.qkvs = h->qkvs.as<float>(); pa.ld = 4 * HC; pa.node_slot = h->plan.node_slot; pa.n = Mr;
@@ -281,10 +284,10 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
         Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
         DA_CK(launch_pack_images(pa, s), "pack images");
       }
-      if (h->plan.n_extra > 0) {  // copies of the promoted residual sources' K / V rows into the padding image rows
-        Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
-        DA_CK(launch_gather_extra(pa, h->plan.x_src, h->plan.x_slot, h->plan.n_extra, s), "gather extra sources");
-      }
+      // copies of the promoted residual sources' K / V rows into the padding image rows: a launch of its own, unless it
+      // can ride with the rows-outside-the-tiles launch of the persistent path (decided below)
+      gather_pending = h->plan.n_extra > 0;
+      gather_args = pa;
     }
     AttnCsrArgs a{};
     a.qkvs = h->qkvs.as<float>(); a.ld = 4 * HC;
@@ -325,6 +328,7 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
     // hidden layers (32-channel heads), every CSR-served row outside the tiles: one lane-per-edge launch
     const bool vrows = rows_path && dense && fuse && !last && h->plan.csr_rows_independent && attn_csr_vrows_supported(c.heads, C) &&
                        !(dense && umma && Cpad != 32) && !h->no_vrows;
+    bool gather_rides = false;
     auto launch_rows = [&](cudaStream_t st) -> cudaError_t {
       cudaError_t e = cudaSuccess;
       if (vrows) {
@@ -332,6 +336,10 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
           AttnCsrArgs vr = hv;
           vr.node_list = h->plan.csr_rows; vr.n_targets = h->plan.n_csr_rows; vr.n_coop = h->plan.n_heavy;   // hubs first
           vr.init_acc = nullptr; vr.init_stats = nullptr; vr.init_slot = nullptr;
+          if (gather_rides) {
+            vr.gx_n = h->plan.n_extra; vr.gx_src = h->plan.x_src; vr.gx_slot = h->plan.x_slot;
+            vr.gx_kimg = gather_args.kimg; vr.gx_vimg = gather_args.vimg;
+          }
           Scoped sc(h, st, TAG_ATTN_HIDDEN);
           e = launch_attn_csr_vrows(vr, st);
         }
@@ -381,6 +389,11 @@ int forward_impl(da_handle* h, const float* x, const int64_t* t_arr, int t_unifo
         DA_CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "side stream");
       }
       DA_CK(cudaEventRecord(h->ev_fork, s), "fork");   // the GEMM (and the gather) of this layer
+    }
+    gather_rides = gather_pending && persist && vrows && h->plan.n_csr_rows > 0 && umma && Cpad == 32 && !h->no_gather_ride;
+    if (gather_pending && !gather_rides) {
+      Scoped sc(h, s, last ? TAG_PACK_LAST : TAG_PACK_HIDDEN);
+      DA_CK(launch_gather_extra(gather_args, h->plan.x_src, h->plan.x_slot, h->plan.n_extra, s), "gather extra sources");
     }
     if (persist && rows_path) DA_CK(launch_rows(s), "graph attention (rows outside the dense tiles)");
     if (dense) {

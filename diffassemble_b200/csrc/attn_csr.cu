@@ -311,11 +311,42 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
                        const float* __restrict__ resid, int ld_resid, int act, float* __restrict__ yf, int ldc,
                        __nv_bfloat16* __restrict__ yhi, __nv_bfloat16* __restrict__ ylo, int ldsp,
                        const int32_t* __restrict__ img_slot, const __nv_bfloat16* __restrict__ kimg,
-                       const __nv_bfloat16* __restrict__ vimg, int Cpad) {
+                       const __nv_bfloat16* __restrict__ vimg, int Cpad,
+                       int n_vrow_ctas, int gx_n, const int32_t* __restrict__ gx_src, const int32_t* __restrict__ gx_slot,
+                       __nv_bfloat16* __restrict__ gx_kimg, __nv_bfloat16* __restrict__ gx_vimg) {
   constexpr int C = 32;
   __shared__ float acc_s[VROW_WARPS][C];
   __shared__ float m_s[VROW_WARPS], l_s[VROW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x >= n_vrow_ctas) {
+    // Riders of the same launch (persistent dense path, api.cu): the per-layer gather of the planner's promoted extra
+    // sources -- fp32 K / V rows -> split-bf16 rows of the padding area of the operand images (gather_extra_kernel of
+    // attn_dense.cu, 32-channel heads).  One warp per (entry, K | V); it touches image rows no CSR row reads.
+    const int wg = ((int)blockIdx.x - n_vrow_ctas) * VROW_WARPS + warp;
+    if (wg >= gx_n * 2) return;
+    const int ent = wg >> 1, part = 1 + (wg & 1);
+    const int node = __ldg(gx_src + ent), slot = __ldg(gx_slot + ent);
+    const int blk = slot >> 6, rb = slot & 63;
+    const float* row = qkvs + (size_t)node * ld + part * H * C;
+    __nv_bfloat16* img = part == 1 ? gx_kimg : gx_vimg;
+    for (int it = lane; it < H * 4; it += 32) {
+      const int h = it >> 2, ch = it & 3;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(row + h * C + ch * 8));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(row + h * C + ch * 8 + 4));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hi[e] = __float2bfloat16_rn(v[e]);
+        lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+      }
+      __nv_bfloat16* base = img + ((size_t)blk * H + h) * ((size_t)2 * 64 * C);
+      const size_t off = (size_t)ch * (64 * 8) + (size_t)rb * 8;
+      *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<uint4*>(hi);
+      *reinterpret_cast<uint4*>(base + (size_t)64 * C + off) = *reinterpret_cast<uint4*>(lo);
+    }
+    return;
+  }
   const bool coop = (int)blockIdx.x < n_coop * H;
   int pair = coop ? (int)blockIdx.x : n_coop * H + ((int)blockIdx.x - n_coop * H) * VROW_WARPS + warp;
   if (pair >= n_rows * H) return;   // (warp mode only: whole warps leave, no barrier follows for them)
@@ -557,13 +588,16 @@ cudaError_t launch_attn_csr_vrows(const AttnCsrArgs& a, cudaStream_t s) {
   if (a.n_targets <= 0) return cudaSuccess;
   if (!a.node_list || a.scores || a.stats || a.init_acc || a.C != 32 || (a.ld & 3)) return cudaErrorInvalidValue;
   if (a.img_slot != nullptr && (a.kimg == nullptr || a.vimg == nullptr || a.img_Cpad != 32)) return cudaErrorInvalidValue;
+  if (a.gx_n > 0 && (!a.gx_src || !a.gx_slot || !a.gx_kimg || !a.gx_vimg)) return cudaErrorInvalidValue;
   const float scale = 1.0f / sqrtf((float)a.C);
   const int n_coop = a.n_coop < a.n_targets ? a.n_coop : a.n_targets;
   const int light_pairs = (a.n_targets - n_coop) * a.H;
-  const unsigned grid = (unsigned)(n_coop * a.H + (light_pairs + VROW_WARPS - 1) / VROW_WARPS);
+  const int n_vrow_ctas = n_coop * a.H + (light_pairs + VROW_WARPS - 1) / VROW_WARPS;
+  const unsigned grid = (unsigned)(n_vrow_ctas + (a.gx_n * 2 + VROW_WARPS - 1) / VROW_WARPS);
   attn_csr_vrow32_kernel<<<grid, VROW_WARPS * 32, 0, s>>>(
       a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, n_coop, a.H, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc,
-      a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad);
+      a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad, n_vrow_ctas, a.gx_n, a.gx_src, a.gx_slot, a.gx_kimg,
+      a.gx_vimg);
   return cudaGetLastError();
 }
 

@@ -117,6 +117,10 @@ struct AttnCsrArgs {
   const __nv_bfloat16* kimg = nullptr;
   const __nv_bfloat16* vimg = nullptr;
   int img_Cpad = 0;
+  // launch_attn_csr_vrows only: riders of the same launch -- the per-layer gather of the plan's gx_n promoted extra sources
+  // (fp32 K / V rows of gx_src -> split-bf16 image rows gx_slot; same work as launch_gather_extra for 32-channel heads)
+  int gx_n = 0; const int32_t* gx_src = nullptr; const int32_t* gx_slot = nullptr;
+  __nv_bfloat16* gx_kimg = nullptr; __nv_bfloat16* gx_vimg = nullptr;
 };
 cudaError_t launch_attn_csr(const AttnCsrArgs& a, cudaStream_t s);
 // warp-per-node variant for low-degree targets (all heads at once, fully coalesced rows)

@@ -126,17 +126,28 @@ head_fold_kernel(HeadFoldArgs a) {
   for (int half = 0; half < 2; ++half) {
     const int node = half ? r1 : r0;
     const bool ok = half ? v1 : v0;
+    // the per-head aggregates of this row: all H x 4 float2 words requested together (heads in groups of 8), summed in
+    // head order afterwards -- one memory latency instead of H
+    float2 ps[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    if (ok) {
+      const float* pp = a.partial + (size_t)node * a.H * 32 + 2 * t;
+      for (int h0 = 0; h0 < a.H; h0 += 8) {
+        float2 p2[8][4];
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            p2[hh][nt] = (h0 + hh < a.H) ? __ldg(reinterpret_cast<const float2*>(pp + (h0 + hh) * 32 + nt * 8)) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) { ps[nt].x += p2[hh][nt].x; ps[nt].y += p2[hh][nt].y; }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int col = nt * 8 + 2 * t;
-      float s0 = acc[nt][2 * half], s1 = acc[nt][2 * half + 1];
-      if (ok) {
-        const float* pp = a.partial + (size_t)node * a.H * 32 + col;
-        for (int hh = 0; hh < a.H; ++hh) {
-          const float2 p2 = __ldg(reinterpret_cast<const float2*>(pp + hh * 32));
-          s0 += p2.x; s1 += p2.y;
-        }
-      }
+      const float s0 = acc[nt][2 * half] + ps[nt].x, s1 = acc[nt][2 * half + 1] + ps[nt].y;
       u_s[(g + 8 * half) * HF_PITCH + col] = gelu_erf(s0 + __ldg(a.bias + col));
       u_s[(g + 8 * half) * HF_PITCH + col + 1] = gelu_erf(s1 + __ldg(a.bias + col + 1));
     }
