@@ -474,7 +474,17 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
   }
   AttnDenseArgs b = a;
   if (items < 8 * (int)grid) b.stagger_ns = 0;   // short streams (small batches): the start delay would cost more than it hides
-  if (a.dbg) attn_hidden_persist_kernel<true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
+  {  // A/B aid: DA_HIDDEN_TRACE_VARIANT=1 runs the tracing instantiation (into a scratch buffer) on every launch
+    static int force = -1;
+    static long long* scratch = nullptr;
+    if (force < 0) {
+      const char* e = getenv("DA_HIDDEN_TRACE_VARIANT");
+      force = (e != nullptr && e[0] == '1') ? 1 : 0;
+      if (force && cudaMalloc(&scratch, 4096 * sizeof(long long)) != cudaSuccess) force = 0;
+    }
+    if (force && !b.dbg) b.dbg = scratch;
+  }
+  if (b.dbg) attn_hidden_persist_kernel<true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
   else attn_hidden_persist_kernel<false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
   return cudaGetLastError();
 }

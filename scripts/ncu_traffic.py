@@ -1,6 +1,6 @@
 """profiles/r2_ncu_traffic.json from the ncu full-capture summary (scripts/ncu_round2.sh): per launch SITE of one denoising
 step, dram__bytes_read.sum + dram__bytes_write.sum per launch.  bench.py reads the table into roofline.traffic.
-    python scripts/ncu_traffic.py gpurun_out/r2_full_summary.csv c3_exphander60_v8 profiles/r2_ncu_full_step_summary.csv"""
+    python scripts/ncu_traffic.py gpurun_out/r2b_full_summary.csv c3_exphander60_v8 profiles/r2b_ncu_full_step_summary.csv"""
 import csv
 import json
 import re
@@ -23,23 +23,31 @@ def val(r, name):
 
 
 # one step = the launches between two consecutive prologue kernels
-starts = [i for i, r in enumerate(data) if "prologue_kernel" in r[ki]]
+starts = [i for i, r in enumerate(data) if "prologue" in r[ki]]
 assert len(starts) >= 2, "need two prologue launches in the capture"
 step = data[starts[0]:starts[1]]
+folded = any("attn_fold" in r[ki] or "head_fold" in r[ki] for r in step)   # weight-folded path (csrc/fold.cu)
+n_gather = sum("gather_extra" in r[ki] for r in step)
 site_of, seen = [], {}
 for r in step:
     n = r[ki]
     base = re.sub(r"\(.*", "", n)
     k = seen[base] = seen.get(base, 0) + 1
+    is_gemm = "linear_umma_kernel" in n
+    bn = int(re.search(r"linear_umma_kernel<(?:\(int\))?(\d+)", n).group(1)) if is_gemm else 0
+    mode = int(re.search(r"linear_umma_kernel<(?:\(int\))?\d+, (?:\(int\))?(\d+)", n).group(1)) if is_gemm else 0
     if "prologue" in n: site = "prologue"
-    elif "linear_umma_kernel<128" in n or "linear_umma_kernel<(int)128" in n: site = "mlp2_gemm" if k == 1 else "qkvs_gemm_first"
-    elif "linear_umma_kernel<256" in n or "linear_umma_kernel<(int)256" in n: site = "qkvs_gemm_mid" if k <= 2 else "qkvs_gemm_last"
-    elif "linear_umma_kernel<32" in n or "linear_umma_kernel<(int)32" in n: site = "head_gemm"
-    elif "attn_dense_kernel<32" in n or "attn_dense_kernel<(int)32" in n: site = "attn_dense_hidden"
-    elif "attn_dense_kernel<144" in n or "attn_dense_kernel<(int)144" in n: site = "attn_dense_last"
+    elif is_gemm and folded:   # GEMMs of a folded step, in launch order: first projection, two hidden layers, [Q | K | V'] of the last
+        seen["_g"] = seen.get("_g", 0) + 1
+        site = "qkvs_gemm_last" if mode == 3 else ("qkvs_gemm_first" if seen["_g"] == 1 else "qkvs_gemm_mid")
+    elif is_gemm and bn == 128: site = "mlp2_gemm" if k == 1 else "qkvs_gemm_first"
+    elif is_gemm and bn == 256: site = "qkvs_gemm_mid" if k <= 2 else "qkvs_gemm_last"
+    elif is_gemm and bn == 32: site = "head_gemm"
+    elif "attn_hidden_persist" in n or "attn_dense_kernel<32" in n or "attn_dense_kernel<(int)32" in n: site = "attn_dense_hidden"
+    elif "attn_fold" in n or "attn_dense_fold" in n or "attn_dense_kernel<144" in n or "attn_dense_kernel<(int)144" in n: site = "attn_dense_last"
     elif "vrow32" in n: site = "attn_hidden"
-    elif "gather_extra" in n: site = "pack_hidden" if k <= 3 else "pack_last"
-    elif "head_final" in n: site = "head_final"
+    elif "gather_extra" in n: site = "pack_last" if k == n_gather else "pack_hidden"
+    elif "head_f" in n: site = "head_final"
     else: site = "other"
     site_of.append(site)
 acc = {}
