@@ -117,7 +117,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -408,7 +408,13 @@ def run_sample2d(args, w):
     pk = peaks()
     E_dense, E_csr = stats["dense_edges"], stats["csr_edges"]
     hid, D, Hm = 256, 1152, 128
-    overlapped = {"attn_hidden"} if (stats["dense_edges"] and args.attn == "auto") else set()
+    # rows outside the dense tiles (virtual nodes): on a side stream NEXT TO the per-(tile, head) dense kernel; the persistent
+    # hidden-layer kernel (csrc/attn_hidden.cu) owns every SM, so there they run in front of it on the same stream
+    try:
+        persist_used = mod.model._engine.plan_info().get("persistent_hidden_launches", 0) > 0
+    except Exception:
+        persist_used = False
+    overlapped = {"attn_hidden"} if (stats["dense_edges"] and args.attn == "auto" and not persist_used) else set()
     step_ms_prof = sum(v["ms"] for k, v in prof.items() if k not in overlapped) / nprof
     passes = 3 if args.gemm == "bf16x3" else 1
 
@@ -432,8 +438,10 @@ def run_sample2d(args, w):
         # HBM bytes: Q / K / V operand images + skip (+ trunk residual on the last layer) in, output planes out
         "attn_dense_hidden": {"flops": 4.0 * E_dense * hid, "bytes": 4.0 * M * hid * 5, "bound": "tensor"},
         "attn_dense_last": {"flops": 4.0 * E_dense * D, "bytes": 4.0 * M * D * 6, "bound": "tensor"},
+        # rows served by the CSR kernels: every row without dense tiles, else the rows outside them (Q, skip in, output out per
+        # row; K and V rows + the index per in-edge)
         "attn_hidden": {"flops": 4.0 * (E_csr if E_dense else E_tot) * hid,
-                        "bytes": 4.0 * Mt * hid * 4 + 4.0 * (E_csr if E_dense else E_tot) * (2 * hid + 1), "bound": "hbm"},
+                        "bytes": 4.0 * ((Mt - M) if E_dense else Mt) * hid * 3 + 4.0 * (E_csr if E_dense else E_tot) * (2 * hid + 1), "bound": "hbm"},
         "attn_last": {"flops": 4.0 * (E_csr if E_dense else E_tot) * D,
                       "bytes": 4.0 * M * D * 5 + 4.0 * (E_csr if E_dense else E_tot) * (2 * D + 1), "bound": "hbm"},
         "head_final": {"flops": 2.0 * M * 32 * 4, "bytes": 4.0 * M * (32 + 12), "bound": "hbm"},
@@ -457,7 +465,7 @@ def run_sample2d(args, w):
             ent["peak"], ent["unit"] = pk["hbm"], "GB/s"
         ent["frac"] = ent["achieved"] / ent["peak"]
         ent["hbm_gbs_algorithmic"] = w_["bytes"] / (ms_layer * 1e-3) / 1e9
-        if name == "attn_hidden" and E_dense and args.attn == "auto":
+        if name in overlapped:
             # rows outside the dense tiles (virtual nodes): launched on a side stream NEXT TO the dense kernel of the same
             # layer, so this span overlaps attn_dense_hidden and is not part of the critical path
             ent["overlapped_with"] = "attn_dense_hidden"
@@ -473,8 +481,9 @@ def run_sample2d(args, w):
         n_scores = 8.0 * Bl * (((n + 127) // 128) * 128) * (((n + 2 * w["V"] + 63) // 64) * 64)  # heads x padded tiles
         roof["note"] = ("achieved = algorithmic edge FLOPs of the reference formulation (4*C per edge and head) / time; the kernel "
                         "executes dense-masked tiles (bitmap density %.2f, padded to 128x64 blocks) with 3 bf16 tensor passes per "
-                        "product; the 32-channel layers are paced by the softmax (one exp2 per score on the 16-lane/clk SFU), the "
-                        "144-channel layer by the tensor pipe" % (E_dense / max(1.0, Bl * n * n)))
+                        "product; the 32-channel layers are paced by the softmax warps (per score ~4 ALU-pipe and 1 SFU instruction on "
+                        "16-lane/clk pipes, two warps per scheduler), the 144-channel layer by the tcgen05.mma issue rate (~45 cycles "
+                        "per M=128, K=16 instruction for N <= 64: profiles/r2_mma_issue_rate_b200.txt)" % (E_dense / max(1.0, Bl * n * n)))
         roof["executed_tensor_tflops"] = passes * 4.0 * n_scores * (HCd // 8) / (dk["ms_per_launch"] * 1e-3) / 1e12
         roof["scores_per_s"] = n_scores / (dk["ms_per_launch"] * 1e-3)
     elif "gemm" in dom_name:
