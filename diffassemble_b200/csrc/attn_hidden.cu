@@ -55,7 +55,11 @@ struct HidSmem {
 // DBG: clock64 trace of CTA 0 (development aid, scripts/trace_hidden.py): a.dbg[((stream * 8 + item) * 16 + block) * 8 + k],
 // k = 0..3 softmax (wait start, S ready, S in registers, P published), 4..6 MMA (S_{j+1} issued, p_full seen, P V issued);
 // per item at a.dbg[2048 + (stream * 8 + item) * 4 + k]: Q park start / done, O complete, epilogue done
-template <bool DBG>
+// NOMAX: no running maximum in the score loop.  The reference point of a row is the masked maximum of the first block in
+// which the row has an edge and only moves when a block's row sum leaves [0, 2^60) (then the block's maximum is taken from
+// the scores still in TMEM and the block is redone): any reference point cancels in O / l, P keeps its relative
+// precision as split bf16 at any magnitude, and l >= 1 keeps the reference's 1e-16 in the denominator negligible.
+template <bool DBG, bool NOMAX>
 __global__ void __launch_bounds__(NTH, 1)
 attn_hidden_persist_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_constant__ CUtensorMap map_ohi,
                            const __grid_constant__ CUtensorMap map_olo, AttnDenseArgs a) {
@@ -304,7 +308,7 @@ attn_hidden_persist_kernel(const __grid_constant__ CUtensorMap map_skip, const _
             // masked scores become -inf once: max ignores them and ex2(-inf) = +0 exactly
             const float s0 = ((wd >> (e & 31)) & 1u) ? __uint_as_float(v[e]) : -INFINITY;
             const float s1 = ((wd >> ((e + 1) & 31)) & 1u) ? __uint_as_float(v[e + 1]) : -INFINITY;
-            bmax = fmaxf(bmax, fmaxf(s0, s1));
+            if constexpr (!NOMAX) bmax = fmaxf(bmax, fmaxf(s0, s1));
             const float p0 = ex2_approx(fmaf(s0, c_log2, -m_sub));
             const float p1 = ex2_approx(fmaf(s1, c_log2, -m_sub));
             lsum += p0 + p1;
@@ -312,8 +316,23 @@ attn_hidden_persist_kernel(const __grid_constant__ CUtensorMap map_skip, const _
             ph[e >> 1] = h2;
             pl[e >> 1] = pack_bf16x2(p0 - __uint_as_float(h2 << 16), p1 - __uint_as_float(h2 & 0xffff0000u));
           }
-          const bool exceeded = bmax > m + tau_raw;   // also true when m == -inf and the block has an edge
+          bool exceeded;
+          if constexpr (NOMAX) exceeded = !(lsum < 0x1p60f) || (m == -INFINITY && (bits.x | bits.y) != 0u);
+          else exceeded = bmax > m + tau_raw;   // also true when m == -inf and the block has an edge
           if (!__any_sync(0xffffffffu, exceeded)) break;
+          if constexpr (NOMAX) {   // the block's masked maximum, from the scores still in TMEM (P is only written after the loop)
+            bmax = m;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TS; c0 += 16) {
+              uint32_t v2[16];
+              tmem_ld16(s_addr + c0, v2);
+              tmem_ld_wait();
+              const uint32_t wd = (c0 < 32) ? bits.x : bits.y;
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if ((wd >> ((c0 + e) & 31)) & 1u) bmax = fmaxf(bmax, __uint_as_float(v2[e]));
+            }
+          }
           // rare: raise the reference point, rescale the history (l and O in TMEM), redo this block
           const float m_new = exceeded ? bmax : m;
           const float alpha = (m == -INFINITY) ? 0.f : ex2_approx((m - m_new) * c_log2);
@@ -467,8 +486,9 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
   const size_t smem_bytes = 2 * (size_t)STREAM_BYTES + sizeof(HidSmem) + 64;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_hidden_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_hidden_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(attn_hidden_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_hidden_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_hidden_persist_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -484,8 +504,13 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
     }
     if (force && !b.dbg) b.dbg = scratch;
   }
-  if (b.dbg) attn_hidden_persist_kernel<true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
-  else attn_hidden_persist_kernel<false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
+  static int nomax = -1;
+  // (A/B on B200, three hidden launches of the c3 step: 0.446 ms with the running maximum, 0.421 ms without; a first version
+  // that kept the 64 scores in registers for the rare path spilled and took 0.522 ms)
+  if (nomax < 0) { const char* e = getenv("DA_HIDDEN_NOMAX"); nomax = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  if (b.dbg) attn_hidden_persist_kernel<true, false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
+  else if (nomax) attn_hidden_persist_kernel<false, true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
+  else attn_hidden_persist_kernel<false, false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
   return cudaGetLastError();
 }
 
