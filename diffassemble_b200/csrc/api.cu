@@ -11,6 +11,14 @@
 
 using namespace da;
 
+namespace da {
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DA_NO_PDL"); on = (e != nullptr && e[0] == '1') ? 0 : 1; }
+  return on == 1;
+}
+}  // namespace da
+
 namespace {
 
 thread_local std::string g_create_error;

@@ -318,6 +318,8 @@ attn_csr_vrow32_kernel(const float* __restrict__ qkvs, int ld, const int32_t* __
   __shared__ float acc_s[VROW_WARPS][C];
   __shared__ float m_s[VROW_WARPS], l_s[VROW_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_trigger();
+  pdl_wait();   // everything below reads the projection GEMM's output
   if ((int)blockIdx.x >= n_vrow_ctas) {
     // Riders of the same launch (persistent dense path, api.cu): the per-layer gather of the planner's promoted extra
     // sources -- fp32 K / V rows -> split-bf16 rows of the padding area of the operand images (gather_extra_kernel of
@@ -594,11 +596,10 @@ cudaError_t launch_attn_csr_vrows(const AttnCsrArgs& a, cudaStream_t s) {
   const int light_pairs = (a.n_targets - n_coop) * a.H;
   const int n_vrow_ctas = n_coop * a.H + (light_pairs + VROW_WARPS - 1) / VROW_WARPS;
   const unsigned grid = (unsigned)(n_vrow_ctas + (a.gx_n * 2 + VROW_WARPS - 1) / VROW_WARPS);
-  attn_csr_vrow32_kernel<<<grid, VROW_WARPS * 32, 0, s>>>(
-      a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, n_coop, a.H, scale, a.resid, a.ld_resid, a.act, a.out.f32, a.out.ldc,
-      a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad, n_vrow_ctas, a.gx_n, a.gx_src, a.gx_slot, a.gx_kimg,
-      a.gx_vimg);
-  return cudaGetLastError();
+  return launch_pdl(attn_csr_vrow32_kernel, dim3(grid), dim3(VROW_WARPS * 32), 0, s,
+                    a.qkvs, a.ld, a.rowptr, a.col, a.weight, a.node_list, a.n_targets, n_coop, a.H, scale, a.resid, a.ld_resid, a.act,
+                    a.out.f32, a.out.ldc, a.out.hi, a.out.lo, a.out.ld_split, a.img_slot, a.kimg, a.vimg, a.img_Cpad, n_vrow_ctas,
+                    a.gx_n, a.gx_src, a.gx_slot, a.gx_kimg, a.gx_vimg);
 }
 
 cudaError_t launch_attn_csr_heavy(const AttnCsrArgs& a, cudaStream_t s) {

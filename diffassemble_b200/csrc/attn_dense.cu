@@ -82,6 +82,8 @@ __global__ void pack_images_kernel(PackArgs a) {
 // K / V rows of the plan's extra sources -> their (padding) image rows.  One warp per (entry, part); lanes over
 // (head, 8-channel chunk) items.
 __global__ void gather_extra_kernel(PackArgs a, const int32_t* __restrict__ x_src, const int32_t* __restrict__ x_slot, int n_extra) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wg = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (wg >= n_extra * 2) return;
@@ -978,6 +980,7 @@ template <int CQ_T, int ST>
 __global__ void __launch_bounds__(NTP, 1)
 attn_fold_persist_kernel(AttnFoldArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   const int Cq = CQ_T ? CQ_T : a.Cpad;
   const uint32_t k_plane = TS * Cq * 2, v_plane = TS * FV * 2;   // bytes
   uint8_t* k_sm = smem;
@@ -1011,6 +1014,7 @@ attn_fold_persist_kernel(AttnFoldArgs a) {
   const uint32_t tmem_s = tmem_base;                  // 2 x TS columns
   const uint32_t tmem_o0 = tmem_base + 2 * TS;        // 2 x FV columns: O_a = P_hi V'_hi + P_lo V'_hi | O_b = P_hi V'_lo (one buffer)
   const uint32_t tmem_q0 = tmem_o0 + 2 * FV;          // 2 x Cq columns
+  pdl_wait();   // set-up above runs under the previous kernel's tail
 
   if (warp == 0) {  // ===== bulk-copy producer: running block counter kc over all items =====
     int kc = 0;
@@ -1302,8 +1306,7 @@ cudaError_t launch_gather_extra(const PackArgs& a, const int32_t* x_src, const i
   if ((a.C % 8) || (a.ld % 4) || a.Cpad % 16 || a.Cpad < a.C) return cudaErrorInvalidValue;
   if (a.Cv > 0 && ((a.Cv % 8) || a.Cvpad % 16 || a.Cvpad < a.Cv)) return cudaErrorInvalidValue;
   const long long threads = (long long)n_extra * 2 * 32;
-  gather_extra_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(a, x_src, x_slot, n_extra);
-  return cudaGetLastError();
+  return launch_pdl(gather_extra_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, s, a, x_src, x_slot, n_extra);
 }
 
 namespace {
@@ -1421,7 +1424,7 @@ cudaError_t launch_attn_dense_fold(const AttnFoldArgs& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;                                                                             \
         smem_set = smp;                                                                                             \
       }                                                                                                             \
-      attn_fold_persist_kernel<CP, ST_><<<gridp, NTP, smp, s>>>(a);                                                 \
+      { cudaError_t e_ = launch_pdl(attn_fold_persist_kernel<CP, ST_>, dim3(gridp), dim3(NTP), smp, s, a); if (e_ != cudaSuccess) return e_; } \
     } while (0)
     if (a.Cpad == 144 && stp == 4) DA_LAUNCH_P(144, 4);
     else if (stp == 4) DA_LAUNCH_P(0, 4);

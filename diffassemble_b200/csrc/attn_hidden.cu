@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(NTH, 1)
 attn_hidden_persist_kernel(const __grid_constant__ CUtensorMap map_skip, const __grid_constant__ CUtensorMap map_ohi,
                            const __grid_constant__ CUtensorMap map_olo, AttnDenseArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   HidSmem* sh = reinterpret_cast<HidSmem*>(smem + 2 * STREAM_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps 0 / 1: producer + MMA of stream 0, warps 2 / 3: of stream 1, warps 4-7: softmax of stream 0, 8-11: of stream 1
@@ -106,6 +107,7 @@ attn_hidden_persist_kernel(const __grid_constant__ CUtensorMap map_skip, const _
   const uint32_t tmem_s = tmem_base + (uint32_t)(sidx * 256);   // 2 x TS columns
   const uint32_t tmem_o = tmem_s + 2 * TS;                       // 2 x 32 columns: O_a = P_hi V_hi + P_lo V_hi | O_b = P_hi V_lo
   const uint32_t tmem_q0 = tmem_o + 2 * HC_;                     // 2 x 32 columns: Q as packed bf16 pairs, hi plane then lo plane
+  pdl_wait();   // barriers and TMEM are set up under the previous kernel's tail; the operand images are read from here on
 
   if (role == 0) {  // ===== bulk-copy producer: running block counter kc over all items of the stream =====
     int kc = 0;
@@ -508,10 +510,9 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
   // (A/B on B200, three hidden launches of the c3 step: 0.446 ms with the running maximum, 0.421 ms without; a first version
   // that kept the 64 scores in registers for the rare path spilled and took 0.522 ms)
   if (nomax < 0) { const char* e = getenv("DA_HIDDEN_NOMAX"); nomax = (e != nullptr && e[0] == '0') ? 0 : 1; }
-  if (b.dbg) attn_hidden_persist_kernel<true, false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
-  else if (nomax) attn_hidden_persist_kernel<false, true><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
-  else attn_hidden_persist_kernel<false, false><<<grid, NTH, smem_bytes, s>>>(map_skip, map_ohi, map_olo, b);
-  return cudaGetLastError();
+  if (b.dbg) return launch_pdl(attn_hidden_persist_kernel<true, false>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
+  if (nomax) return launch_pdl(attn_hidden_persist_kernel<false, true>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
+  return launch_pdl(attn_hidden_persist_kernel<false, false>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
 }
 
 }  // namespace da

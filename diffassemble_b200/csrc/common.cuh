@@ -9,6 +9,36 @@
 
 namespace da {
 
+// ---- programmatic dependent launch (PDL) along the kernel chain of one denoising step ------------------------------------
+// Every kernel of the chain calls pdl_trigger() first (its dependents may be scheduled as soon as all of ITS CTAs are
+// running) and pdl_wait() before it touches anything a predecessor wrote or a predecessor may still read -- after its own
+// set-up (barrier init, TMEM allocation, tensor-map prefetch, staging of constant weights), which thereby runs under the
+// previous kernel's tail.  Both are no-ops for launches without the attribute.  Transitivity: kernel N+2 waits for N+1,
+// which cannot complete before its own wait for N has returned -- so every kernel waits before any early return.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef DA_PDL_EARLY_TRIGGER
+#define DA_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if DA_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+#endif
+bool pdl_enabled();   // api.cu: false with DA_NO_PDL=1
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_LRELU = 2, ACT_RELU = 3, ACT_SILU = 4, ACT_SIGMOID = 5 };
 
 __device__ __forceinline__ float gelu_erf(float x) {

@@ -56,6 +56,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 __global__ void __launch_bounds__(HF_NT)
 head_fold_kernel(HeadFoldArgs a) {
   extern __shared__ __align__(16) uint8_t hf_sm[];
+  pdl_trigger();
   const int Kt = a.Hm + a.hid, KP = Kt + 8;
   __nv_bfloat16* wh = reinterpret_cast<__nv_bfloat16*>(hf_sm);            // [32][KP]
   __nv_bfloat16* wl = wh + (size_t)32 * KP;
@@ -68,6 +69,7 @@ head_fold_kernel(HeadFoldArgs a) {
     *reinterpret_cast<uint4*>(wl + (size_t)row * KP + c8) = __ldg(reinterpret_cast<const uint4*>(a.w_lo + (size_t)row * Kt + c8));
   }
   __syncthreads();
+  pdl_wait();   // the weight stage above is constant data; h, x_3 and the per-head aggregates are the predecessors' outputs
   const HeadFinalArgs& f = a.fin;
   const int g = lane >> 2, t = lane & 3;
   const int node0 = blockIdx.x * HF_NB + warp * HF_ROWS;
@@ -202,8 +204,7 @@ cudaError_t launch_head_fold(const HeadFoldArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  head_fold_kernel<<<(a.fin.M + HF_NB - 1) / HF_NB, HF_NT, smem, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(head_fold_kernel, dim3((a.fin.M + HF_NB - 1) / HF_NB), dim3(HF_NT), smem, s, a);
 }
 
 }  // namespace da

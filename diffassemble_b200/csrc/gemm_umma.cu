@@ -157,6 +157,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
                    EpiParams p, const typename EpiExtraT<MODE>::type ex) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -186,6 +187,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();   // barriers, TMEM and tensor maps are set up under the previous kernel's tail; its outputs are read from here on
 
   if (warp == 0) {  // ===== TMA producer (warp-uniform; one elected lane issues) =====
     int stage = 0; uint32_t phase = 0;
@@ -562,7 +564,7 @@ cudaError_t launch_bn(const __nv_bfloat16* a_hi, const __nv_bfloat16* a_lo, int 
   }
   const int tiles = ((p.M + BM - 1) / BM) * (p.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  linear_umma_kernel<BN, MODE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(mah, mal, mwh, mwl, p, ex);
+  return launch_pdl(linear_umma_kernel<BN, MODE>, dim3(grid), dim3(NUM_THREADS), (size_t)C::SMEM_BYTES, s, mah, mal, mwh, mwl, p, ex);
   return cudaGetLastError();
 }
 

@@ -113,6 +113,7 @@ prologue_kernel(PrologueArgs a) {
 template <int VPL>
 __global__ void __launch_bounds__(PRO_NT)
 prologue_table_kernel(PrologueArgs a) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int gw = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
   const int Hm = a.Hm, c0 = lane * VPL;
@@ -131,6 +132,7 @@ prologue_table_kernel(PrologueArgs a) {
   float bias[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) bias[i] = __ldg(a.b1 + c0 + i);
+  pdl_wait();   // the weight slices above are constants; x (the previous step's output) and the h planes are not
   // NPW nodes per warp and iteration, their (dependent) index / row loads issued together
   constexpr int NPW = 4;
   for (int nb = gw * NPW; nb < a.M; nb += nw * NPW) {
@@ -312,10 +314,9 @@ cudaError_t launch_prologue(const PrologueArgs& a, cudaStream_t s) {
     // table form: 4 nodes per warp at a time; 8 per warp amortise the register-resident weight slice on large batches
     const long long warps = ((long long)a.M + (a.M >= 148 * 256 / 4 ? 7 : 3)) / (a.M >= 148 * 256 / 4 ? 8 : 4);
     const unsigned grid = (unsigned)((warps * 32 + PRO_NT - 1) / PRO_NT);
-    if (a.Hm == 64) prologue_table_kernel<2><<<grid, PRO_NT, 0, s>>>(a);
-    else if (a.Hm == 128) prologue_table_kernel<4><<<grid, PRO_NT, 0, s>>>(a);
-    else prologue_table_kernel<8><<<grid, PRO_NT, 0, s>>>(a);
-    return cudaGetLastError();
+    if (a.Hm == 64) return launch_pdl(prologue_table_kernel<2>, dim3(grid), dim3(PRO_NT), 0, s, a);
+    if (a.Hm == 128) return launch_pdl(prologue_table_kernel<4>, dim3(grid), dim3(PRO_NT), 0, s, a);
+    return launch_pdl(prologue_table_kernel<8>, dim3(grid), dim3(PRO_NT), 0, s, a);
   }
   const size_t smem = (size_t)64 * a.Hm * sizeof(float);
   static size_t smem_set = 0;
