@@ -113,6 +113,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin, self.t_end = None, None
+
+    def begin(self):
+        """Call right before the timed region: waits (<= 0.5 s) until nvidia-smi delivers rows, so that even a 40 ms region
+        (the 4-graph share of the 8-GPU run) is sampled, then marks the start."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < 0.5:
+            time.sleep(0.005)
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def __enter__(self):
         try:
@@ -126,7 +138,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
         if self.proc:
@@ -140,7 +152,11 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if self.t_begin is not None and self.t_end is not None:   # rows that arrived during the timed region (+ one period)
+            rows = [r for r in self.rows if self.t_begin <= r[0] <= self.t_end + 0.02]
+        for r in rows:
+            r = r[1:]
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -286,6 +302,10 @@ def run_sample2d(args, w):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize()
+        clk.begin()
+        if world > 1:   # (begin() may have waited for nvidia-smi's first row on some ranks)
+            dist.barrier()
+            torch.cuda.synchronize()
         ev0.record()
         if graphed:
             for _ in range(loops):
@@ -302,6 +322,7 @@ def run_sample2d(args, w):
             sharding.gather_poses(xa, counts)
         ev1.record()
         torch.cuda.synchronize()
+        clk.end()
     ms = max_over_ranks(ev0.elapsed_time(ev1), device, world)
     launches = eng.launch_count() - launches0   # (graphed: replays do not pass through the host-side counter; set below)
     ms_per_step = ms / steps
@@ -634,6 +655,7 @@ def run_sample3d(args, w):
             one_step(k, xa, xb); xa, xb = xb, xa
         ev1.record()
         torch.cuda.synchronize()
+        clk.end()
     ms = max_over_ranks(ev0.elapsed_time(ev1), device, world)
     launches = eng.launch_count() - launches0
     # e2e: public API with host buffers, whole 30-step loops
@@ -833,7 +855,7 @@ def main():
                     help="strong: the global batch of 32 graphs is sharded over the ranks (BASELINE configs[2]); weak: 32 graphs per GPU")
     ap.add_argument("--gemm", default="bf16x3", choices=["fp32", "bf16x3"])
     ap.add_argument("--attn", default="auto", choices=["csr", "auto"])
-    ap.add_argument("--e2e-loops", type=int, default=5)
+    ap.add_argument("--e2e-loops", type=int, default=10)
     ap.add_argument("--cpu-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-auto-graph", dest="auto_graph", action="store_false",
