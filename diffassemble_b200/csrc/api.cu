@@ -13,9 +13,8 @@ using namespace da;
 
 namespace da {
 bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("DA_NO_PDL"); on = (e != nullptr && e[0] == '1') ? 0 : 1; }
-  return on == 1;
+  const char* e = getenv("DA_NO_PDL");   // read per launch (nanoseconds), so that a test can flip it inside one process
+  return !(e != nullptr && e[0] == '1');
 }
 }  // namespace da
 

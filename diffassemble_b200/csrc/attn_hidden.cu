@@ -506,7 +506,7 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
     }
     if (force && !b.dbg) b.dbg = scratch;
   }
-  static int nomax = -1;
+  int nomax = -1;   // read per launch
   // (A/B on B200, three hidden launches of the c3 step: 0.446 ms with the running maximum, 0.421 ms without; a first version
   // that kept the 64 scores in registers for the rare path spilled and took 0.522 ms)
   if (nomax < 0) { const char* e = getenv("DA_HIDDEN_NOMAX"); nomax = (e != nullptr && e[0] == '0') ? 0 : 1; }

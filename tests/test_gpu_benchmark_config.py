@@ -249,3 +249,33 @@ def test_persistent_hidden_layer_kernel_equals_the_per_tile_kernel(monkeypatch, 
         t = torch.full((M,), 290, dtype=torch.long)
         want = ref.p_sample(x, t, 290, edge_index=ei, patch_feats=feats, batch=batch)[0]
     assert rel_err(outs["1"][0], want) < TOL, rel_err(outs["1"][0], want)
+
+
+@pytest.mark.parametrize("switch", ["DA_NO_PDL=1", "DA_HIDDEN_NOMAX=0", "DA_NO_PRO_TABLE=1", "DA_NO_GATHER_RIDE=1", "DA_FOLD_PERSIST=0"])
+def test_development_switches_change_scheduling_not_results(monkeypatch, switch):
+    """Every A/B switch of DESIGN.md section 4 selects another schedule or another grouping of the same arithmetic:
+    plain stream order instead of programmatic dependent launch (bit-identical), the running maximum in the persistent
+    kernel's score loop (another reference point of the online softmax), the literal prologue instead of its table form
+    (fp32 re-association), separate gather launches (bit-identical), per-(tile, head) CTAs for the folded last layer.  Two
+    free-running DDIM steps on the benchmarked configuration (2 x 900 nodes, Exphander 60 %, 8 virtual nodes) must agree
+    with the default path to fp32 rounding."""
+    ei, batch = synth_graph_batch([900, 900], kind="expander", degree="60%", seed=40)
+    M = 1800
+    g = torch.Generator().manual_seed(7)
+    feats, x = torch.randn(M, 1088, generator=g), torch.randn(M, 4, generator=g)
+    outs = []
+    for env in (None, switch):
+        if env is not None:
+            k, v = env.split("=")
+            monkeypatch.setenv(k, v)
+        ref, mod = _pair("exophormer", 8, "bf16x3", "auto")
+        xt = x.to(DEV)
+        for i in (290, 280):
+            t = torch.full((M,), i, dtype=torch.long, device=DEV)
+            xt, _ = mod.p_sample(xt, t, i, cond=None, edge_index=ei.to(DEV), patch_feats=feats.to(DEV), batch=batch.to(DEV))
+        outs.append(xt.cpu())
+    exact = switch in ("DA_NO_PDL=1", "DA_NO_GATHER_RIDE=1")
+    if exact:
+        assert torch.equal(outs[0], outs[1]), (switch, rel_err(outs[0], outs[1]))
+    else:
+        assert rel_err(outs[0], outs[1]) < 3e-6, (switch, rel_err(outs[0], outs[1]))

@@ -341,6 +341,24 @@ def test_dense_attention_kernel_keeps_two_ctas_per_sm(lib_built):
     assert int(m.group(1)) <= 168, f"attn_dense_kernel<32, 4> uses {m.group(1)} registers: only one CTA per SM would fit"
 
 
+def test_persistent_hidden_kernel_fits_one_cta_per_sm_without_spills(lib_built):
+    """The persistent hidden-layer kernel (csrc/attn_hidden.cu) is ONE CTA of 384 threads per SM: 65536 / 384 -> at most
+    168 registers per thread, and the production instantiation (no tracing, no running maximum: <false, true>) must reach
+    that without local-memory spills -- the variant that kept the 64 scores live for the rare path spilled 60 bytes and
+    lost 20 %.  Shared memory: 2 streams x 96 KB + barriers must stay under the 227 KB opt-in limit."""
+    import re
+    from pathlib import Path
+
+    log = (Path(lib_built).parent.parent / "build" / "attn_hidden.log").read_text()
+    m = re.search(r"attn_hidden_persist_kernelILb0ELb1EE.*?(\d+) bytes spill stores.*?Used (\d+) registers", log, re.S)
+    assert m, "attn_hidden_persist_kernel<false, true> not found in the ptxas log"
+    assert int(m.group(2)) <= 168, f"{m.group(2)} registers: the 384-thread CTA would not launch"
+    assert int(m.group(1)) == 0, f"{m.group(1)} bytes of spill stores in the production score loop"
+    src = (Path(lib_built).parent.parent / "csrc" / "attn_hidden.cu").read_text()
+    assert "constexpr int NTH = 384;" in src and "2 * HST * KV_STAGE + SKIP_BYTES + 2 * OUT_PLANE" in src
+    assert 2 * (2 * 4 * 8192 + 16384 + 2 * 8192) + 1024 <= 227 * 1024
+
+
 def test_visual_backbone_state_dict_uses_timm_names():
     """N4: the mirror's EfficientNet-B0 encoder carries timm's parameter names (all 7 stages, so that a reference
     checkpoint's `model.visual_backbone.*` entries load strictly), identical to the oracle's."""
