@@ -16,6 +16,10 @@
 // slots, and nothing is ever re-initialised: barriers keep running phases, TMEM is allocated once (S/P 2 x 64, O 2 x 32,
 // Q 2 x 32 columns per stream = all 512), skip rows and output planes have their own staging buffers.
 //
+// The score loop keeps no running maximum (template parameter NOMAX, the default): see the kernel's comment.  Launched
+// with programmatic stream serialization (common.cuh: launch_pdl / pdl_wait), so barrier set-up and the TMEM allocation
+// run under the previous kernel's tail.  What bounds it now, with the measurements: DESIGN.md section 4.
+//
 // Preconditions (checked by the host, api.cu): every valid tile row is finalised here (planner: no residual in-edge on
 // a real row, DensePlan::real_rows_clean), tcgen05 GEMM mode (split-bf16 output planes), C = Cpad = 32.
 // TransformerConv semantics: SURVEY.md section 2.3c; reference call sites Transformer_GNN.py:33-44,
@@ -506,10 +510,11 @@ cudaError_t launch_attn_hidden_persist(const AttnDenseArgs& a, cudaStream_t s) {
     }
     if (force && !b.dbg) b.dbg = scratch;
   }
-  int nomax = -1;   // read per launch
-  // (A/B on B200, three hidden launches of the c3 step: 0.446 ms with the running maximum, 0.421 ms without; a first version
-  // that kept the 64 scores in registers for the rare path spilled and took 0.522 ms)
-  if (nomax < 0) { const char* e = getenv("DA_HIDDEN_NOMAX"); nomax = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  // Score loop without a running maximum unless DA_HIDDEN_NOMAX=0 (read per launch).  A/B on B200, three hidden launches of
+  // the c3 step: 0.446 ms with the running maximum, 0.421 ms without; a first version that kept the 64 scores in registers
+  // for the rare path spilled and took 0.522 ms.
+  const char* e_nomax = getenv("DA_HIDDEN_NOMAX");
+  const bool nomax = !(e_nomax != nullptr && e_nomax[0] == '0');
   if (b.dbg) return launch_pdl(attn_hidden_persist_kernel<true, false>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
   if (nomax) return launch_pdl(attn_hidden_persist_kernel<false, true>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
   return launch_pdl(attn_hidden_persist_kernel<false, false>, dim3(grid), dim3(NTH), smem_bytes, s, map_skip, map_ohi, map_olo, b);
